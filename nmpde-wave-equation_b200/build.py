@@ -1,0 +1,74 @@
+"""Build libwavegpu.so (sm_100a) and the host executables in-tree with nvcc / g++.
+
+    python nmpde-wave-equation_b200/build.py [--force]
+
+Outputs: nmpde-wave-equation_b200/lib/libwavegpu.so, bin/main-newmark, bin/main-theta.
+nvcc cross-compiles without a GPU; the built files travel to the GPU box with the snapshot."""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+CSRC = HERE / "csrc"
+HOST = HERE / "host"
+OBJ = HERE / "build"
+LIB = HERE / "lib" / "libwavegpu.so"
+BIN = HERE / "bin"
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVFLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", *ARCH]
+CXXFLAGS = ["-std=c++17", "-O2", "-fPIC", "-Wall"]
+
+LIB_SOURCES = ["kernels.cu", "ctx.cu", "expr.cpp", "quadrature.cpp"]
+HOST_SOURCES = ["ParameterReader.cpp", "WaveEquationBase.cpp", "WaveNewmark.cpp", "WaveTheta.cpp"]
+
+
+def _newer(target: Path, deps) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(Path(d).stat().st_mtime > t for d in deps)
+
+
+def _run(cmd):
+    subprocess.check_call([str(c) for c in cmd])
+
+
+def build(force=False, verbose=False):
+    OBJ.mkdir(exist_ok=True)
+    LIB.parent.mkdir(exist_ok=True)
+    headers = list(CSRC.glob("*.h")) + list(CSRC.glob("*.hpp")) + list(CSRC.glob("*.cuh")) + \
+        [HERE.parent / "include" / "wavegpu.h"]
+    jobs = []
+    objs = []
+    for src in LIB_SOURCES:
+        s = CSRC / src
+        o = OBJ / (src + ".o")
+        objs.append(o)
+        if force or _newer(o, [s, *headers]):
+            if src.endswith(".cu"):
+                extra = ["-Xptxas", "-v"] if verbose else []
+                jobs.append([NVCC, *NVFLAGS, *extra, "-c", s, "-o", o])
+            else:
+                jobs.append(["g++", *CXXFLAGS, "-c", s, "-o", o])
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        list(ex.map(_run, jobs))
+    if force or jobs or not LIB.exists():
+        _run([NVCC, "-shared", *ARCH, "-o", LIB, *objs, "-ldl"])
+    # host executables (same names as the reference's CMake targets)
+    if HOST.exists() and all((HOST / s).exists() for s in HOST_SOURCES):
+        BIN.mkdir(exist_ok=True)
+        hdeps = list(HOST.glob("*.hpp")) + list(HOST.glob("*.cpp")) + [HERE.parent / "include" / "wavegpu.h"]
+        for exe in ("main-newmark", "main-theta"):
+            target = BIN / exe
+            if force or _newer(target, hdeps + [LIB]):
+                _run(["g++", *CXXFLAGS, "-I", HERE.parent / "include", "-o", target, HOST / (exe + ".cpp"),
+                      *[HOST / s for s in HOST_SOURCES], "-L", LIB.parent, "-lwavegpu",
+                      "-Wl,-rpath,$ORIGIN/../lib"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,1149 @@
+// ctx.cu -- the context behind the C ABI (include/wavegpu.h): owns device memory, the stream, the
+// compiled expressions and (for nranks > 1) the NCCL communicator, and sequences the kernels of
+// kernels.cu into the reference's setup / init / step operations.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_scan.cuh>
+
+#include "../../include/wavegpu.h"
+#include "expr.hpp"
+#include "kernels.cuh"
+
+namespace wv {
+Quadrature make_quadrature(int n1d);
+}
+
+using namespace wv;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- NCCL, loaded on demand (single-GPU contexts never touch it) ----------------------------------
+struct Nccl {
+    void *lib = nullptr;
+    typedef struct ncclComm *comm_t;
+    struct Uid { char internal[128]; };
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(comm_t *, int, Uid, int) = nullptr;
+    int (*CommDestroy)(comm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    static constexpr int kFloat64 = 8, kSum = 0;  // ncclFloat64, ncclSum
+    bool load(std::string &err) {
+        if (lib) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) { err = std::string("cannot load NCCL: ") + dlerror(); return false; }
+#define WV_SYM(field, name)                                              \
+    *(void **)(&field) = dlsym(lib, name);                               \
+    if (!field) { err = std::string("NCCL symbol missing: ") + name; return false; }
+        WV_SYM(GetUniqueId, "ncclGetUniqueId");
+        WV_SYM(CommInitRank, "ncclCommInitRank");
+        WV_SYM(CommDestroy, "ncclCommDestroy");
+        WV_SYM(AllReduce, "ncclAllReduce");
+        WV_SYM(Broadcast, "ncclBroadcast");
+        WV_SYM(Send, "ncclSend");
+        WV_SYM(Recv, "ncclRecv");
+        WV_SYM(GroupStart, "ncclGroupStart");
+        WV_SYM(GroupEnd, "ncclGroupEnd");
+        WV_SYM(GetErrorString, "ncclGetErrorString");
+#undef WV_SYM
+        return true;
+    }
+};
+Nccl g_nccl;
+
+enum Phase { PH_RHS = 0, PH_BC, PH_CG, PH_UPDATE, PH_ENERGY, PH_OTHER, PH_COUNT };
+
+}  // namespace
+
+struct wave_ctx {
+    wave_config cfg{};
+    Layout L{};
+    std::string err;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    Launcher launcher{};
+    bool is_setup = false, is_init = false;
+
+    // expressions
+    Program hprog[WAVE_EXPR_COUNT]{};
+    bool has[WAVE_EXPR_COUNT]{};
+    Program *dprog = nullptr;  // WAVE_EXPR_COUNT programs
+    bool forcing_active = false;
+    Quadrature q_asm{}, q_err{};
+
+    // CSR (owned rows, local column indices)
+    uint32_t *rowptr = nullptr;
+    int32_t *col = nullptr;
+    int64_t nnz = 0;
+    int maxrow = 0;
+    double *M = nullptr, *K = nullptr, *S1 = nullptr, *S2 = nullptr;
+    double *dinv1 = nullptr, *dinv2 = nullptr;
+    double *d0 = nullptr;  // [2]
+
+    // vectors: u, v, a, unew, d are local-layout (ghosts included); rhs, fvec, g, h are row-indexed
+    double *u = nullptr, *v = nullptr, *a = nullptr, *unew = nullptr, *d = nullptr;
+    double *rhs = nullptr, *fvec = nullptr, *g = nullptr, *h = nullptr;
+    double *scratch = nullptr;  // global-size staging for gathers (allocated on demand)
+    int64_t scratch_n = 0;
+
+    // boundary
+    int nb = 0;
+    int64_t nb_global = 0;
+    int32_t *brow = nullptr;
+    double *bx = nullptr, *by = nullptr;
+    std::vector<int32_t> h_bdof_global;  // all boundary DoFs (global ids, sorted)
+
+    // reductions / CG state
+    double *partials = nullptr;
+    unsigned *counter = nullptr;
+    CgScalars *S = nullptr;
+    CgScalars *hS = nullptr;  // pinned
+    double *res = nullptr;    // device scalars [8]
+    double *hres = nullptr;   // pinned [8]
+    int prev_its[2] = {0, 0};
+
+    // NCCL
+    Nccl::comm_t comm = nullptr;
+
+    // instrumentation
+    bool timers_on = false;
+    double phase_ms[PH_COUNT]{};
+    cudaEvent_t ev[2 * PH_COUNT + 4]{};
+    double cg_stats[4]{};
+    double *flush_buf = nullptr;
+    int64_t flush_n = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
+            return WAVE_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+#define NK(call)                                                                              \
+    do {                                                                                      \
+        int e_ = (call);                                                                      \
+        if (e_ != 0) {                                                                        \
+            ctx->err = std::string(#call) + ": " + g_nccl.GetErrorString(e_);                 \
+            return WAVE_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+#define RET(call)                                \
+    do {                                         \
+        int rc_ = (call);                        \
+        if (rc_ != WAVE_OK) return rc_;          \
+    } while (0)
+
+int fail(wave_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+void quad_row_split(int ny, int rank, int nranks, int &j0, int &j1) {
+    j0 = (int)((int64_t)ny * rank / nranks);
+    j1 = (int)((int64_t)ny * (rank + 1) / nranks);
+}
+
+Layout make_layout(const Mesh &m, int rank, int nranks) {
+    Layout L{};
+    L.mesh = m;
+    quad_row_split(m.ny, rank, nranks, L.jq0, L.jq1);
+    L.row0 = block_start(m, L.jq0);
+    const int64_t row1 = L.jq1 >= m.ny ? n_dofs(m) : block_start(m, L.jq1);
+    L.nown = (int)(row1 - L.row0);
+    L.col0 = block_start(m, L.jq0 > 0 ? L.jq0 - 1 : 0);
+    const int jhi = L.jq1 + 1;
+    const int64_t col1 = jhi >= m.ny ? n_dofs(m) : block_start(m, jhi);
+    L.nloc = (int)(col1 - L.col0);
+    L.own_off = (int)(L.row0 - L.col0);
+    return L;
+}
+
+int sync_check(wave_ctx *ctx) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return WAVE_OK;
+}
+
+// ---- multi-GPU plumbing: contiguous halo blocks and small all-reduces over NCCL -------------------
+int halo_exchange(wave_ctx *ctx, double *vec) {
+    if (ctx->cfg.nranks == 1) return WAVE_OK;
+    const Layout &L = ctx->L;
+    const int rank = ctx->cfg.rank, nr = ctx->cfg.nranks;
+    const Mesh &m = L.mesh;
+    NK(g_nccl.GroupStart());
+    if (rank > 0) {
+        // lower neighbour owns block jq0-1 (my lower ghost); it needs my first block jq0
+        const size_t ghost = (size_t)L.own_off;
+        const size_t mine = (size_t)(block_start(m, L.jq0 + 1) - block_start(m, L.jq0));
+        NK(g_nccl.Recv(vec, ghost, Nccl::kFloat64, rank - 1, ctx->comm, ctx->stream));
+        NK(g_nccl.Send(vec + L.own_off, mine, Nccl::kFloat64, rank - 1, ctx->comm, ctx->stream));
+    }
+    if (rank < nr - 1) {
+        // upper neighbour owns block jq1 (my upper ghost); it needs my last block jq1-1
+        const size_t ghost = (size_t)(L.nloc - L.own_off - L.nown);
+        const size_t mine = (size_t)(block_start(m, L.jq1) - block_start(m, L.jq1 - 1));
+        NK(g_nccl.Recv(vec + L.own_off + L.nown, ghost, Nccl::kFloat64, rank + 1, ctx->comm, ctx->stream));
+        NK(g_nccl.Send(vec + L.own_off + L.nown - mine, mine, Nccl::kFloat64, rank + 1, ctx->comm, ctx->stream));
+    }
+    NK(g_nccl.GroupEnd());
+    return WAVE_OK;
+}
+int allreduce(wave_ctx *ctx, double *dev, size_t count) {
+    if (ctx->cfg.nranks == 1) return WAVE_OK;
+    NK(g_nccl.AllReduce(dev, dev, count, Nccl::kFloat64, Nccl::kSum, ctx->comm, ctx->stream));
+    return WAVE_OK;
+}
+
+// ---- phase timers -----------------------------------------------------------------------------------
+struct PhaseTimer {
+    wave_ctx *ctx;
+    int ph;
+    PhaseTimer(wave_ctx *c, int p) : ctx(c), ph(p) {
+        if (ctx->timers_on) cudaEventRecord(ctx->ev[2 * ph], ctx->stream);
+    }
+    ~PhaseTimer() {
+        if (ctx->timers_on) {
+            cudaEventRecord(ctx->ev[2 * ph + 1], ctx->stream);
+            cudaEventSynchronize(ctx->ev[2 * ph + 1]);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ctx->ev[2 * ph], ctx->ev[2 * ph + 1]);
+            ctx->phase_ms[ph] += ms;
+        }
+    }
+};
+
+SpmvArgs spmv_base(wave_ctx *ctx) {
+    SpmvArgs a{};
+    a.rowptr = ctx->rowptr;
+    a.col = ctx->col;
+    a.nrows = ctx->L.nown;
+    a.partials = ctx->partials;
+    a.counter = ctx->counter;
+    return a;
+}
+
+// SolverCG::solve (src/WaveNewmark.cpp:256-261): Jacobi-PCG on the BC-modified matrix `Sval`,
+// start vector x (local layout), right-hand side b (row-indexed).
+int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, const double *b, int slot,
+             int *iters) {
+    const Layout &L = ctx->L;
+    const Launcher &l = ctx->launcher;
+    cudaEvent_t e0 = ctx->ev[2 * PH_COUNT], e1 = ctx->ev[2 * PH_COUNT + 1];
+    CK(cudaEventRecord(e0, ctx->stream));
+    RET(halo_exchange(ctx, x));
+    {   // g = A x - b ; h = D^-1 g ; d = -h ; gg, gh
+        SpmvArgs a = spmv_base(ctx);
+        a.t[0] = {Sval, x, nullptr, 1.0, 0.0, 1.0};
+        a.add0 = b; a.addc0 = -1.0;
+        a.y = ctx->g;
+        a.dinv = dinv; a.h_out = ctx->h; a.d_out = ctx->d + L.own_off;
+        a.dot_mode = 2;
+        a.result = &ctx->S->gg;
+        launch_spmv(l, a, ctx->maxrow);
+    }
+    RET(allreduce(ctx, &ctx->S->gg, 2));
+    launch_cg_start(l, ctx->S);
+    int enq = 0;
+    int chunk = ctx->prev_its[slot] > 6 ? ctx->prev_its[slot] - 2 : 4;
+    const int maxit = ctx->hS->maxit;
+    for (;;) {
+        for (int k = 0; k < chunk; ++k) {
+            RET(halo_exchange(ctx, ctx->d));
+            SpmvArgs a = spmv_base(ctx);
+            a.t[0] = {Sval, ctx->d, nullptr, 1.0, 0.0, 1.0};
+            a.y = ctx->h;
+            a.dot_mode = 1;
+            a.dotv = ctx->d + L.own_off;
+            a.result = &ctx->S->dAd;
+            a.skip_flag = &ctx->S->status;
+            launch_spmv(l, a, ctx->maxrow);
+            RET(allreduce(ctx, &ctx->S->dAd, 1));
+            launch_cg_update(l, L.nown, ctx->S, x + L.own_off, ctx->g, ctx->h, ctx->d + L.own_off, dinv,
+                             ctx->partials, ctx->counter);
+            RET(allreduce(ctx, &ctx->S->gg, 2));
+            launch_cg_direction(l, L.nown, ctx->S, ctx->d + L.own_off, ctx->h, ctx->counter);
+        }
+        enq += chunk;
+        CK(cudaMemcpyAsync(ctx->hS, ctx->S, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->hS->status != 0) break;
+        if (enq > maxit + 8) break;
+        chunk = 4;
+    }
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *iters = ctx->hS->it;
+    ctx->prev_its[slot] = ctx->hS->it;
+    ctx->cg_stats[0] += 1;
+    ctx->cg_stats[1] += ctx->hS->it;
+    ctx->cg_stats[2] += ctx->hS->it + 1;
+    ctx->cg_stats[3] += ms;
+    if (ctx->hS->status != 1)
+        return fail(ctx, WAVE_ERR_NOCONV, "CG did not converge within the iteration limit (SolverControl::NoConvergence)");
+    return WAVE_OK;
+}
+
+// scheme matrix: out = bc(M + s K); also d0 and the Jacobi diagonal
+int build_system_matrix(wave_ctx *ctx, double s, double *out, double *dinv, double *d0) {
+    const Launcher &l = ctx->launcher;
+    launch_axpy_vals(l, ctx->nnz, ctx->M, ctx->K, s, out);
+    launch_find_d0(l, ctx->L, ctx->rowptr, ctx->col, out, d0);
+    launch_bc_rows(l, ctx->L, ctx->nb, ctx->brow, ctx->rowptr, ctx->col, out, d0);
+    launch_dinv(l, ctx->L, ctx->rowptr, ctx->col, out, ctx->cfg.precond == WAVE_PRECOND_NONE, dinv);
+    return WAVE_OK;
+}
+
+int upload_cg_control(wave_ctx *ctx) {
+    CgScalars s{};
+    s.tol = ctx->cfg.cg_tol;
+    s.reduce = ctx->cfg.cg_reduce;
+    s.maxit = ctx->cfg.cg_maxit;
+    *ctx->hS = s;
+    CK(cudaMemcpyAsync(ctx->S, ctx->hS, sizeof(CgScalars), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return WAVE_OK;
+}
+
+int compute_forcing(wave_ctx *ctx, double t_np1, double t_n, double w_np1, double w_n, int two_levels) {
+    launch_fill(ctx->launcher, ctx->L.nown, 0.0, ctx->fvec);
+    launch_forcing(ctx->launcher, ctx->L, ctx->dprog + WAVE_EXPR_F, &ctx->q_asm, t_np1, t_n, w_np1, w_n,
+                   two_levels, ctx->fvec);
+    return WAVE_OK;
+}
+
+int finish_norms(wave_ctx *ctx, double norms[2]) {
+    RET(allreduce(ctx, ctx->res, 2));
+    CK(cudaMemcpyAsync(ctx->hres, ctx->res, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (norms) { norms[0] = std::sqrt(ctx->hres[0]); norms[1] = std::sqrt(ctx->hres[1]); }
+    return WAVE_OK;
+}
+
+// WaveNewmark: assemble_rhs + solve_a + update_u_v (src/WaveNewmark.cpp:116-278)
+int newmark_step(wave_ctx *ctx, double t, int32_t iters[2], double norms[2]) {
+    const Layout &L = ctx->L;
+    const Launcher &l = ctx->launcher;
+    const double dt = ctx->cfg.dt, beta = ctx->cfg.beta, gamma = ctx->cfg.gamma;
+    int its = 0;
+    {
+        PhaseTimer pt(ctx, PH_RHS);
+        // u <- z = u + dt v + dt^2(1/2-beta) a ; v <- v + dt(1-gamma) a
+        launch_newmark_predict(l, L.nown, dt, dt * dt * (0.5 - beta), dt * (1.0 - gamma), ctx->u + L.own_off,
+                               ctx->v + L.own_off, ctx->a + L.own_off);
+        RET(halo_exchange(ctx, ctx->u));
+        if (ctx->forcing_active) RET(compute_forcing(ctx, t, 0.0, 1.0, 0.0, 0));
+        SpmvArgs a = spmv_base(ctx);
+        a.t[0] = {ctx->K, ctx->u, nullptr, 1.0, 0.0, -1.0};
+        if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = 1.0; }
+        a.y = ctx->rhs;
+        launch_spmv(l, a, ctx->maxrow);
+    }
+    {
+        PhaseTimer pt(ctx, PH_BC);
+        const int mode = beta > 1e-12 ? BC_NEWMARK_IMPLICIT : BC_SECOND_DIFF;
+        launch_bc_values(l, mode, ctx->nb, ctx->brow, ctx->bx, ctx->by, ctx->dprog + WAVE_EXPR_G, t, dt,
+                         beta * dt * dt, ctx->u + L.own_off, ctx->a + L.own_off, ctx->rhs, ctx->d0);
+    }
+    {
+        PhaseTimer pt(ctx, PH_CG);
+        RET(cg_solve(ctx, ctx->S1, ctx->dinv1, ctx->a, ctx->rhs, 0, &its));
+    }
+    {
+        PhaseTimer pt(ctx, PH_UPDATE);
+        launch_newmark_correct(l, L.nown, dt * dt * beta, dt * gamma, ctx->u + L.own_off, ctx->v + L.own_off,
+                               ctx->a + L.own_off, ctx->partials, ctx->counter, ctx->res);
+        RET(finish_norms(ctx, norms));
+    }
+    if (iters) { iters[0] = its; iters[1] = 0; }
+    return WAVE_OK;
+}
+
+// WaveTheta: assemble_rhs_u + solve_u + assemble_rhs_v + solve_v (src/WaveTheta.cpp:119-339)
+int theta_step(wave_ctx *ctx, double t, int32_t iters[2], double norms[2]) {
+    const Layout &L = ctx->L;
+    const Launcher &l = ctx->launcher;
+    const double dt = ctx->cfg.dt, th = ctx->cfg.theta;
+    int its_u = 0, its_v = 0;
+    {
+        PhaseTimer pt(ctx, PH_RHS);
+        RET(halo_exchange(ctx, ctx->u));
+        RET(halo_exchange(ctx, ctx->v));
+        if (ctx->forcing_active) RET(compute_forcing(ctx, t, t - dt, th, 1.0 - th, 1));
+        // rhs = M u + dt M v - dt^2 theta (1-theta) K u + theta dt^2 F_theta
+        SpmvArgs a = spmv_base(ctx);
+        a.t[0] = {ctx->M, ctx->u, ctx->v, 1.0, dt, 1.0};
+        a.t[1] = {ctx->K, ctx->u, nullptr, 1.0, 0.0, -dt * dt * th * (1 - th)};
+        if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = th * dt * dt; }
+        a.y = ctx->rhs;
+        launch_spmv(l, a, ctx->maxrow);
+        launch_copy(l, L.nloc, ctx->u, ctx->unew);
+    }
+    {
+        PhaseTimer pt(ctx, PH_BC);
+        launch_bc_values(l, BC_DIRECT, ctx->nb, ctx->brow, ctx->bx, ctx->by, ctx->dprog + WAVE_EXPR_G, t, dt, 0.0,
+                         nullptr, ctx->unew + L.own_off, ctx->rhs, ctx->d0);
+    }
+    {
+        PhaseTimer pt(ctx, PH_CG);
+        RET(cg_solve(ctx, ctx->S1, ctx->dinv1, ctx->unew, ctx->rhs, 0, &its_u));
+    }
+    {
+        PhaseTimer pt(ctx, PH_RHS);
+        RET(halo_exchange(ctx, ctx->unew));
+        // rhs = M v - dt (1-theta) K u^n - dt theta K u^{n+1} + dt F_theta
+        SpmvArgs a = spmv_base(ctx);
+        a.t[0] = {ctx->M, ctx->v, nullptr, 1.0, 0.0, 1.0};
+        a.t[1] = {ctx->K, ctx->u, ctx->unew, 1.0 - th, th, -dt};
+        if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = dt; }
+        a.y = ctx->rhs;
+        launch_spmv(l, a, ctx->maxrow);
+    }
+    {
+        PhaseTimer pt(ctx, PH_BC);
+        launch_bc_values(l, BC_DIRECT, ctx->nb, ctx->brow, ctx->bx, ctx->by, ctx->dprog + WAVE_EXPR_DGDT, t, dt, 0.0,
+                         nullptr, ctx->v + L.own_off, ctx->rhs, ctx->d0 + 1);
+    }
+    {
+        PhaseTimer pt(ctx, PH_CG);
+        RET(cg_solve(ctx, ctx->S2, ctx->dinv2, ctx->v, ctx->rhs, 1, &its_v));
+    }
+    {
+        PhaseTimer pt(ctx, PH_UPDATE);
+        std::swap(ctx->u, ctx->unew);
+        launch_norms2(l, L.nown, ctx->u + L.own_off, ctx->v + L.own_off, ctx->partials, ctx->counter, ctx->res);
+        RET(finish_norms(ctx, norms));
+    }
+    if (iters) { iters[0] = its_u; iters[1] = its_v; }
+    return WAVE_OK;
+}
+
+double *vec_ptr(wave_ctx *ctx, int which) {
+    switch (which) {
+    case WAVE_VEC_U: return ctx->u;
+    case WAVE_VEC_V: return ctx->v;
+    case WAVE_VEC_A: return ctx->a;
+    default: return nullptr;
+    }
+}
+const double *mat_ptr(wave_ctx *ctx, int which) {
+    switch (which) {
+    case WAVE_MAT_M: return ctx->M;
+    case WAVE_MAT_K: return ctx->K;
+    case WAVE_MAT_SYS1: return ctx->S1;
+    case WAVE_MAT_SYS2: return ctx->S2;
+    default: return nullptr;
+    }
+}
+
+int ensure_scratch(wave_ctx *ctx, int64_t n) {
+    if (ctx->scratch_n >= n) return WAVE_OK;
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    ctx->scratch = nullptr;
+    ctx->scratch_n = 0;
+    CK(cudaMalloc(&ctx->scratch, sizeof(double) * n));
+    ctx->scratch_n = n;
+    return WAVE_OK;
+}
+
+// owned part of a local-layout vector -> all ranks' canonical vector in device scratch
+int gather_global(wave_ctx *ctx, const double *own_src) {
+    const int64_t n = n_dofs(ctx->L.mesh);
+    RET(ensure_scratch(ctx, n));
+    const Layout &L = ctx->L;
+    CK(cudaMemcpyAsync(ctx->scratch + L.row0, own_src, sizeof(double) * L.nown, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (ctx->cfg.nranks > 1) {
+        for (int r = 0; r < ctx->cfg.nranks; ++r) {
+            const Layout Lr = make_layout(L.mesh, r, ctx->cfg.nranks);
+            NK(g_nccl.Broadcast(ctx->scratch + Lr.row0, ctx->scratch + Lr.row0, (size_t)Lr.nown, Nccl::kFloat64, r,
+                                ctx->comm, ctx->stream));
+        }
+    }
+    return WAVE_OK;
+}
+
+template <class T>
+int dev_alloc(wave_ctx *ctx, T **p, size_t count, bool zero = true) {
+    CK(cudaMalloc((void **)p, sizeof(T) * (count ? count : 1)));
+    if (zero) CK(cudaMemsetAsync(*p, 0, sizeof(T) * (count ? count : 1), ctx->stream));
+    return WAVE_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+void wave_default_config(wave_config *c) {
+    std::memset(c, 0, sizeof(*c));
+    c->nx = c->ny = 40;                 // "Nel" default, src/ParameterReader.cpp:41-44
+    c->x0 = 0.0; c->x1 = 1.0; c->y0 = 0.0; c->y1 = 1.0;
+    c->r = 1; c->scheme = WAVE_SCHEME_NEWMARK;
+    c->dt = 0.01; c->theta = 0.5; c->beta = 0.25; c->gamma = 0.5;
+    c->cg_maxit = 10000; c->cg_tol = 1e-12; c->cg_reduce = 1e-6;  // src/WaveNewmark.cpp:256
+    c->precond = WAVE_PRECOND_JACOBI;
+    c->rank = 0; c->nranks = 1; c->device = -1;
+}
+
+const char *wave_last_error(const wave_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int wave_comm_unique_id(void *out128) {
+    std::string err;
+    if (!g_nccl.load(err)) return fail(nullptr, WAVE_ERR_CUDA, err);
+    Nccl::Uid id;
+    if (g_nccl.GetUniqueId(&id) != 0) return fail(nullptr, WAVE_ERR_CUDA, "ncclGetUniqueId failed");
+    std::memcpy(out128, &id, sizeof id);
+    return WAVE_OK;
+}
+
+int wave_create(const wave_config *cfg, wave_ctx **out) {
+    if (!cfg || !out) return fail(nullptr, WAVE_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->nx < 1 || cfg->ny < 1) return fail(nullptr, WAVE_ERR_ARG, "Nel must be >= 1");
+    if (cfg->r != 1 && cfg->r != 2)
+        return fail(nullptr, WAVE_ERR_UNSUPPORTED, "only FE_SimplexP degree R = 1 or 2 is implemented");
+    if (!(cfg->x1 > cfg->x0) || !(cfg->y1 > cfg->y0)) return fail(nullptr, WAVE_ERR_ARG, "empty geometry");
+    if (!(cfg->dt > 0.0)) return fail(nullptr, WAVE_ERR_ARG, "Dt must be positive");
+    if (cfg->scheme != WAVE_SCHEME_NEWMARK && cfg->scheme != WAVE_SCHEME_THETA)
+        return fail(nullptr, WAVE_ERR_ARG, "unknown scheme");
+    if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks)
+        return fail(nullptr, WAVE_ERR_ARG, "bad rank / nranks");
+    if (cfg->ny < cfg->nranks) return fail(nullptr, WAVE_ERR_ARG, "need at least one quad row per rank");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, WAVE_ERR_CUDA, "no CUDA device: libwavegpu has no CPU fallback");
+    wave_ctx *ctx = new wave_ctx();
+    ctx->cfg = *cfg;
+    if (ctx->cfg.cg_maxit <= 0) ctx->cfg.cg_maxit = 10000;
+    if (ctx->cfg.cg_tol <= 0.0) ctx->cfg.cg_tol = 1e-12;
+    if (ctx->cfg.cg_reduce <= 0.0) ctx->cfg.cg_reduce = 1e-6;
+    auto bail = [&](int code) { g_create_error = ctx->err; wave_destroy(ctx); return code; };
+    if (cfg->device >= 0 && cudaSetDevice(cfg->device) != cudaSuccess) {
+        ctx->err = "cudaSetDevice failed";
+        return bail(WAVE_ERR_CUDA);
+    }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        ctx->err = "cudaStreamCreate failed";
+        return bail(WAVE_ERR_CUDA);
+    }
+    ctx->launcher = Launcher{ctx->stream, &ctx->launches};
+    for (auto &e : ctx->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) { ctx->err = "cudaEventCreate failed"; return bail(WAVE_ERR_CUDA); }
+    Mesh m{};
+    m.nx = cfg->nx; m.ny = cfg->ny; m.r = cfg->r;
+    m.x0 = cfg->x0; m.y0 = cfg->y0;
+    m.dx = (cfg->x1 - cfg->x0) / cfg->nx;
+    m.dy = (cfg->y1 - cfg->y0) / cfg->ny;
+    ctx->L = make_layout(m, cfg->rank, cfg->nranks);
+    if ((int64_t)ctx->L.nloc * 19 >= (1LL << 32)) {
+        ctx->err = "local problem exceeds 32-bit CSR offsets: partition over more GPUs";
+        return bail(WAVE_ERR_UNSUPPORTED);
+    }
+    if (cfg->nranks > 1) {
+        if (!cfg->nccl_unique_id) { ctx->err = "nccl_unique_id required for nranks > 1"; return bail(WAVE_ERR_ARG); }
+        if (!g_nccl.load(ctx->err)) return bail(WAVE_ERR_CUDA);
+        Nccl::Uid id;
+        std::memcpy(&id, cfg->nccl_unique_id, sizeof id);
+        const int rc = g_nccl.CommInitRank(&ctx->comm, cfg->nranks, id, cfg->rank);
+        if (rc != 0) { ctx->err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc); return bail(WAVE_ERR_CUDA); }
+    }
+    if (cudaMalloc(&ctx->dprog, sizeof(Program) * WAVE_EXPR_COUNT) != cudaSuccess) {
+        ctx->err = "cudaMalloc failed";
+        return bail(WAVE_ERR_CUDA);
+    }
+    ctx->q_asm = make_quadrature(cfg->r + 1);  // src/WaveEquationBase.cpp:82
+    ctx->q_err = make_quadrature(cfg->r + 2);  // src/WaveEquationBase.cpp:371
+    *out = ctx;
+    return WAVE_OK;
+}
+
+void wave_destroy(wave_ctx *ctx) {
+    if (!ctx) return;
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    void *ptrs[] = {ctx->dprog, ctx->rowptr, ctx->col, ctx->M, ctx->K, ctx->S1, ctx->S2, ctx->dinv1, ctx->dinv2,
+                    ctx->d0, ctx->u, ctx->v, ctx->a, ctx->unew, ctx->d, ctx->rhs, ctx->fvec, ctx->g, ctx->h,
+                    ctx->scratch, ctx->brow, ctx->bx, ctx->by, ctx->partials, ctx->counter, ctx->S, ctx->res,
+                    ctx->flush_buf};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (ctx->hS) cudaFreeHost(ctx->hS);
+    if (ctx->hres) cudaFreeHost(ctx->hres);
+    if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
+    for (auto &e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int wave_set_expr(wave_ctx *ctx, int which, const char *expression, const char *variable_names,
+                  const char *constants) {
+    if (!ctx || which < 0 || which >= WAVE_EXPR_COUNT || !expression)
+        return fail(ctx, WAVE_ERR_ARG, "bad expression slot");
+    try {
+        ctx->hprog[which] = compile_expression(expression, variable_names ? variable_names : "",
+                                               constants ? constants : "");
+    } catch (const std::exception &e) {
+        return fail(ctx, WAVE_ERR_EXPR, e.what());
+    }
+    ctx->has[which] = true;
+    CK(cudaMemcpyAsync(ctx->dprog + which, &ctx->hprog[which], sizeof(Program), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return WAVE_OK;
+}
+
+int wave_eval_expr(wave_ctx *ctx, int which, double x, double y, double t, double *out) {
+    if (!ctx || which < 0 || which >= WAVE_EXPR_COUNT || !ctx->has[which] || !out)
+        return fail(ctx, WAVE_ERR_ARG, "expression not set");
+    *out = eval(&ctx->hprog[which], x, y, t);
+    return WAVE_OK;
+}
+
+int wave_setup(wave_ctx *ctx) {
+    if (!ctx) return WAVE_ERR_ARG;
+    for (int k = WAVE_EXPR_C; k <= WAVE_EXPR_DGDT; ++k)
+        if (!ctx->has[k]) {
+            static const char *names[] = {"C", "F", "U0", "V0", "G", "DGDT"};
+            return fail(ctx, WAVE_ERR_EXPR,
+                        std::string("Function expression for '") + names[k] + "' must be specified in the parameter file.");
+        }
+    if (ctx->is_setup) return fail(ctx, WAVE_ERR_STATE, "wave_setup called twice");
+    const Layout &L = ctx->L;
+    const Launcher &l = ctx->launcher;
+    double fconst = 1.0;
+    ctx->forcing_active = !(is_constant(ctx->hprog[WAVE_EXPR_F], &fconst) && fconst == 0.0) ||
+                          (ctx->cfg.flags & WAVE_FLAG_FORCING_EVERY_STEP);
+
+    // ---- sparsity: row lengths -> exclusive scan -> columns -------------------------------------
+    uint32_t *rowlen = nullptr;
+    RET(dev_alloc(ctx, &rowlen, (size_t)L.nown + 1));
+    RET(dev_alloc(ctx, &ctx->rowptr, (size_t)L.nown + 1));
+    launch_row_lengths(l, L, rowlen);
+    {
+        void *tmp = nullptr;
+        size_t bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, rowlen, ctx->rowptr, L.nown + 1, ctx->stream));
+        CK(cudaMalloc(&tmp, bytes));
+        CK(cub::DeviceScan::ExclusiveSum(tmp, bytes, rowlen, ctx->rowptr, L.nown + 1, ctx->stream));
+        ++ctx->launches;
+        uint32_t total = 0;
+        CK(cudaMemcpyAsync(&total, ctx->rowptr + L.nown, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaFree(tmp));
+        ctx->nnz = total;
+    }
+    CK(cudaFree(rowlen));
+    ctx->maxrow = L.mesh.r == 1 ? 7 : 19;
+    RET(dev_alloc(ctx, &ctx->col, (size_t)ctx->nnz, false));
+    launch_fill_cols(l, L, ctx->rowptr, ctx->col);
+
+    // ---- M, K ---------------------------------------------------------------------------------------
+    RET(dev_alloc(ctx, &ctx->M, (size_t)ctx->nnz));
+    RET(dev_alloc(ctx, &ctx->K, (size_t)ctx->nnz));
+    launch_assemble(l, L, ctx->dprog + WAVE_EXPR_C, &ctx->q_asm, ctx->rowptr, ctx->col, ctx->M, ctx->K);
+
+    // ---- boundary list (closed form, host) --------------------------------------------------------
+    {
+        const Mesh &m = L.mesh;
+        struct B { int64_t dof; double x, y; };
+        std::vector<B> mine;
+        ctx->h_bdof_global.clear();
+        const int nk = m.r == 1 ? 1 : 4;
+        for (int j = 0; j <= m.ny; ++j) {
+            const bool edge_row = (j == 0 || j == m.ny);
+            for (int i = 0; i <= m.nx; ++i) {
+                if (!edge_row && i != 0 && i != m.nx) continue;
+                for (int kind = 0; kind < nk; ++kind) {
+                    if (!entity_on_boundary(m, i, j, kind)) continue;
+                    const int64_t dof = entity_dof(m, i, j, kind);
+                    if (dof < 0) continue;
+                    ctx->h_bdof_global.push_back((int32_t)dof);
+                    if (dof >= L.row0 && dof < L.row0 + L.nown) {
+                        double x, y;
+                        entity_point(m, i, j, kind, x, y);
+                        mine.push_back({dof, x, y});
+                    }
+                }
+            }
+        }
+        std::sort(ctx->h_bdof_global.begin(), ctx->h_bdof_global.end());
+        std::sort(mine.begin(), mine.end(), [](const B &a, const B &b) { return a.dof < b.dof; });
+        ctx->nb = (int)mine.size();
+        ctx->nb_global = (int64_t)ctx->h_bdof_global.size();
+        std::vector<int32_t> hrow(mine.size());
+        std::vector<double> hx(mine.size()), hy(mine.size());
+        for (size_t k = 0; k < mine.size(); ++k) {
+            hrow[k] = (int32_t)(mine[k].dof - L.row0);
+            hx[k] = mine[k].x;
+            hy[k] = mine[k].y;
+        }
+        RET(dev_alloc(ctx, &ctx->brow, mine.size(), false));
+        RET(dev_alloc(ctx, &ctx->bx, mine.size(), false));
+        RET(dev_alloc(ctx, &ctx->by, mine.size(), false));
+        if (!mine.empty()) {
+            CK(cudaMemcpyAsync(ctx->brow, hrow.data(), sizeof(int32_t) * hrow.size(), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->bx, hx.data(), sizeof(double) * hx.size(), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->by, hy.data(), sizeof(double) * hy.size(), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+
+    // ---- vectors, reduction scratch, CG state ----------------------------------------------------
+    RET(dev_alloc(ctx, &ctx->u, (size_t)L.nloc));
+    RET(dev_alloc(ctx, &ctx->v, (size_t)L.nloc));
+    RET(dev_alloc(ctx, &ctx->a, (size_t)L.nloc));
+    RET(dev_alloc(ctx, &ctx->unew, (size_t)L.nloc));
+    RET(dev_alloc(ctx, &ctx->d, (size_t)L.nloc));
+    RET(dev_alloc(ctx, &ctx->rhs, (size_t)L.nown));
+    RET(dev_alloc(ctx, &ctx->fvec, (size_t)L.nown));
+    RET(dev_alloc(ctx, &ctx->g, (size_t)L.nown));
+    RET(dev_alloc(ctx, &ctx->h, (size_t)L.nown));
+    {
+        const int64_t cells = 2LL * (L.jq1 - L.jq0) * L.mesh.nx;
+        const int64_t blocks = std::max<int64_t>({(cells + 127) / 128, (L.nown + kRowsPerBlock - 1) / kRowsPerBlock,
+                                                  (int64_t)reduction_blocks(L.nown)}) + 1;
+        RET(dev_alloc(ctx, &ctx->partials, (size_t)blocks * 4));
+    }
+    RET(dev_alloc(ctx, &ctx->counter, 4));
+    RET(dev_alloc(ctx, &ctx->S, 1));
+    RET(dev_alloc(ctx, &ctx->res, 8));
+    RET(dev_alloc(ctx, &ctx->d0, 2));
+    CK(cudaMallocHost((void **)&ctx->hS, sizeof(CgScalars)));
+    CK(cudaMallocHost((void **)&ctx->hres, 8 * sizeof(double)));
+    RET(upload_cg_control(ctx));
+
+    // ---- scheme matrices (src/WaveNewmark.cpp:110-112, :372-374; src/WaveTheta.cpp:110-115) -----
+    RET(dev_alloc(ctx, &ctx->S1, (size_t)ctx->nnz, false));
+    RET(dev_alloc(ctx, &ctx->dinv1, (size_t)L.nown, false));
+    const double dt = ctx->cfg.dt;
+    if (ctx->cfg.scheme == WAVE_SCHEME_NEWMARK) {
+        // SYS1 starts as the BC-modified mass matrix of the a^0 solve; wave_init switches it to
+        // bc(M + beta dt^2 K) afterwards
+        RET(build_system_matrix(ctx, 0.0, ctx->S1, ctx->dinv1, ctx->d0));
+    } else {
+        const double th = ctx->cfg.theta;
+        RET(build_system_matrix(ctx, (th * dt) * (th * dt), ctx->S1, ctx->dinv1, ctx->d0));
+        RET(dev_alloc(ctx, &ctx->S2, (size_t)ctx->nnz, false));
+        RET(dev_alloc(ctx, &ctx->dinv2, (size_t)L.nown, false));
+        RET(build_system_matrix(ctx, 0.0, ctx->S2, ctx->dinv2, ctx->d0 + 1));
+    }
+    RET(sync_check(ctx));
+    ctx->is_setup = true;
+    return WAVE_OK;
+}
+
+int wave_init(wave_ctx *ctx) {
+    if (!ctx) return WAVE_ERR_ARG;
+    if (!ctx->is_setup) return fail(ctx, WAVE_ERR_STATE, "wave_init before wave_setup");
+    const Layout &L = ctx->L;
+    const Launcher &l = ctx->launcher;
+    launch_interpolate(l, L, ctx->dprog + WAVE_EXPR_U0, 0.0, ctx->u, nullptr, nullptr);
+    launch_interpolate(l, L, ctx->dprog + WAVE_EXPR_V0, 0.0, ctx->v, nullptr, nullptr);
+    if (ctx->cfg.scheme == WAVE_SCHEME_NEWMARK) {
+        const double dt = ctx->cfg.dt, beta = ctx->cfg.beta;
+        if (ctx->is_init)  // SYS1 must again be the BC-modified mass matrix
+            RET(build_system_matrix(ctx, 0.0, ctx->S1, ctx->dinv1, ctx->d0));
+        // M a0 = F(0) - K u0 with a0 = second difference of g on the boundary (src/WaveNewmark.cpp:300-385)
+        if (ctx->forcing_active) RET(compute_forcing(ctx, 0.0, 0.0, 1.0, 0.0, 0));
+        SpmvArgs a = spmv_base(ctx);
+        a.t[0] = {ctx->K, ctx->u, nullptr, 1.0, 0.0, -1.0};
+        if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = 1.0; }
+        a.y = ctx->rhs;
+        launch_spmv(l, a, ctx->maxrow);
+        launch_fill(l, L.nloc, 0.0, ctx->a);
+        launch_bc_values(l, BC_SECOND_DIFF, ctx->nb, ctx->brow, ctx->bx, ctx->by, ctx->dprog + WAVE_EXPR_G, dt, dt, 0.0,
+                         nullptr, ctx->a + L.own_off, ctx->rhs, ctx->d0);
+        int its = 0;
+        ctx->prev_its[0] = 0;
+        RET(cg_solve(ctx, ctx->S1, ctx->dinv1, ctx->a, ctx->rhs, 0, &its));
+        RET(halo_exchange(ctx, ctx->a));
+        RET(build_system_matrix(ctx, beta * dt * dt, ctx->S1, ctx->dinv1, ctx->d0));
+        ctx->prev_its[0] = 0;
+    }
+    RET(sync_check(ctx));
+    ctx->is_init = true;
+    return WAVE_OK;
+}
+
+int wave_step(wave_ctx *ctx, double t_np1, int32_t iters[2], double norms[2]) {
+    if (!ctx) return WAVE_ERR_ARG;
+    if (!ctx->is_init) return fail(ctx, WAVE_ERR_STATE, "wave_step before wave_init");
+    return ctx->cfg.scheme == WAVE_SCHEME_NEWMARK ? newmark_step(ctx, t_np1, iters, norms)
+                                                  : theta_step(ctx, t_np1, iters, norms);
+}
+
+int wave_run(wave_ctx *ctx, double t_start, int32_t n_steps, double *t_end, int32_t *steps_done, int32_t iters[2],
+             double norms[2], int64_t *total_iters) {
+    if (!ctx) return WAVE_ERR_ARG;
+    if (!ctx->is_init) return fail(ctx, WAVE_ERR_STATE, "wave_run before wave_init");
+    double t = t_start, nrm[2] = {0, 0};
+    int32_t it[2] = {0, 0};
+    int64_t tot = 0;
+    int done = 0, rc = WAVE_OK;
+    for (int s = 0; s < n_steps; ++s) {
+        t += ctx->cfg.dt;  // src/WaveNewmark.cpp:409
+        ++done;
+        rc = wave_step(ctx, t, it, nrm);
+        if (rc != WAVE_OK) break;
+        tot += it[0] + it[1];
+        // check_divergence, threshold 1e130 (src/WaveEquationBase.cpp:425-431, src/WaveNewmark.cpp:399)
+        if (!std::isfinite(nrm[0]) || !std::isfinite(nrm[1]) || nrm[0] > 1e130 || nrm[1] > 1e130) {
+            rc = fail(ctx, WAVE_ERR_DIVERGED, "divergence detected");
+            break;
+        }
+    }
+    if (t_end) *t_end = t;
+    if (steps_done) *steps_done = done;
+    if (iters) { iters[0] = it[0]; iters[1] = it[1]; }
+    if (norms) { norms[0] = nrm[0]; norms[1] = nrm[1]; }
+    if (total_iters) *total_iters = tot;
+    return rc;
+}
+
+int wave_set_vector(wave_ctx *ctx, int which, const double *host, size_t n) {
+    if (!ctx || !ctx->is_setup) return fail(ctx, WAVE_ERR_STATE, "wave_set_vector before wave_setup");
+    double *dst = vec_ptr(ctx, which);
+    if (!dst || !host || (int64_t)n != n_dofs(ctx->L.mesh)) return fail(ctx, WAVE_ERR_ARG, "bad vector id or size");
+    // every rank takes its local slice (ghosts included) straight from the canonical host array
+    CK(cudaMemcpyAsync(dst, host + ctx->L.col0, sizeof(double) * ctx->L.nloc, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return WAVE_OK;
+}
+
+int wave_get_vector(wave_ctx *ctx, int which, double *host, size_t n) {
+    if (!ctx || !ctx->is_setup) return fail(ctx, WAVE_ERR_STATE, "wave_get_vector before wave_setup");
+    const Layout &L = ctx->L;
+    const double *src = which == WAVE_VEC_RHS ? ctx->rhs : (vec_ptr(ctx, which) ? vec_ptr(ctx, which) + L.own_off : nullptr);
+    if (!src || !host) return fail(ctx, WAVE_ERR_ARG, "bad vector id");
+    if ((int64_t)n == (int64_t)L.nown && ctx->cfg.nranks > 1) {
+        CK(cudaMemcpyAsync(host, src, sizeof(double) * L.nown, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return WAVE_OK;
+    }
+    if ((int64_t)n != n_dofs(L.mesh)) return fail(ctx, WAVE_ERR_ARG, "bad vector size");
+    if (ctx->cfg.nranks == 1) {
+        CK(cudaMemcpyAsync(host, src, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        RET(gather_global(ctx, src));
+        CK(cudaMemcpyAsync(host, ctx->scratch, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return WAVE_OK;
+}
+
+int wave_step_host(wave_ctx *ctx, double t_np1, double *u, double *v, double *a, int32_t iters[2], double norms[2]) {
+    if (!ctx || !ctx->is_init) return fail(ctx, WAVE_ERR_STATE, "wave_step_host before wave_init");
+    const size_t n = (size_t)n_dofs(ctx->L.mesh);
+    const Layout &L = ctx->L;
+    CK(cudaMemcpyAsync(ctx->u, u + L.col0, sizeof(double) * L.nloc, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->v, v + L.col0, sizeof(double) * L.nloc, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->cfg.scheme == WAVE_SCHEME_NEWMARK) {
+        if (!a) return fail(ctx, WAVE_ERR_ARG, "Newmark needs the acceleration vector");
+        CK(cudaMemcpyAsync(ctx->a, a + L.col0, sizeof(double) * L.nloc, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    RET(wave_step(ctx, t_np1, iters, norms));
+    RET(wave_get_vector(ctx, WAVE_VEC_U, u, n));
+    RET(wave_get_vector(ctx, WAVE_VEC_V, v, n));
+    if (ctx->cfg.scheme == WAVE_SCHEME_NEWMARK) RET(wave_get_vector(ctx, WAVE_VEC_A, a, n));
+    return WAVE_OK;
+}
+
+int wave_norms(wave_ctx *ctx, double out[2]) {
+    if (!ctx || !ctx->is_setup) return fail(ctx, WAVE_ERR_STATE, "wave_norms before wave_setup");
+    const Layout &L = ctx->L;
+    launch_norms2(ctx->launcher, L.nown, ctx->u + L.own_off, ctx->v + L.own_off, ctx->partials, ctx->counter, ctx->res);
+    return finish_norms(ctx, out);
+}
+
+int wave_energy(wave_ctx *ctx, double *out) {
+    if (!ctx || !ctx->is_setup) return fail(ctx, WAVE_ERR_STATE, "wave_energy before wave_setup");
+    const Layout &L = ctx->L;
+    PhaseTimer pt(ctx, PH_ENERGY);
+    RET(halo_exchange(ctx, ctx->u));
+    RET(halo_exchange(ctx, ctx->v));
+    SpmvArgs a = spmv_base(ctx);
+    a.t[0] = {ctx->K, ctx->u, nullptr, 1.0, 0.0, 1.0};
+    a.dot_mode = 1; a.dotv = ctx->u + L.own_off; a.result = ctx->res + 2;
+    launch_spmv(ctx->launcher, a, ctx->maxrow);
+    SpmvArgs b = spmv_base(ctx);
+    b.t[0] = {ctx->M, ctx->v, nullptr, 1.0, 0.0, 1.0};
+    b.dot_mode = 1; b.dotv = ctx->v + L.own_off; b.result = ctx->res + 3;
+    launch_spmv(ctx->launcher, b, ctx->maxrow);
+    RET(allreduce(ctx, ctx->res + 2, 2));
+    CK(cudaMemcpyAsync(ctx->hres + 2, ctx->res + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *out = 0.5 * (ctx->hres[3] + ctx->hres[2]);  // 0.5 * (v.Mv + u.Ku), src/WaveEquationBase.cpp:154
+    return WAVE_OK;
+}
+
+int wave_errors(wave_ctx *ctx, double t, double out[4]) {
+    if (!ctx || !ctx->is_setup) return fail(ctx, WAVE_ERR_STATE, "wave_errors before wave_setup");
+    if (!ctx->has[WAVE_EXPR_SOLUTION]) return fail(ctx, WAVE_ERR_STATE, "no exact Solution expression");
+    RET(halo_exchange(ctx, ctx->u));
+    launch_errors(ctx->launcher, ctx->L, ctx->dprog + WAVE_EXPR_SOLUTION, &ctx->q_err, t, ctx->u, ctx->partials,
+                  ctx->counter, ctx->res + 4);
+    RET(allreduce(ctx, ctx->res + 4, 4));
+    CK(cudaMemcpyAsync(ctx->hres + 4, ctx->res + 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const double l2 = std::sqrt(ctx->hres[4]), h1 = std::sqrt(ctx->hres[5]);
+    const double nl2 = std::sqrt(ctx->hres[6]), nh1 = std::sqrt(ctx->hres[7]);
+    out[0] = l2;
+    out[1] = h1;
+    out[2] = nl2 < 1e-14 ? l2 : l2 / nl2;  // src/WaveEquationBase.cpp:419-422
+    out[3] = nh1 < 1e-14 ? h1 : h1 / nh1;
+    return WAVE_OK;
+}
+
+int wave_probe(wave_ctx *ctx, double x, double y, double *out) {
+    if (!ctx || !ctx->is_setup) return fail(ctx, WAVE_ERR_STATE, "wave_probe before wave_setup");
+    RET(halo_exchange(ctx, ctx->u));
+    launch_probe(ctx->launcher, ctx->L, x, y, ctx->u, ctx->res);
+    RET(allreduce(ctx, ctx->res, 1));
+    CK(cudaMemcpyAsync(ctx->hres, ctx->res, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *out = ctx->hres[0];
+    return WAVE_OK;
+}
+
+int64_t wave_n_dofs(const wave_ctx *ctx) { return ctx ? n_dofs(ctx->L.mesh) : 0; }
+int64_t wave_n_cells(const wave_ctx *ctx) { return ctx ? n_cells(ctx->L.mesh) : 0; }
+int64_t wave_local_rows(const wave_ctx *ctx, int64_t *first_row) {
+    if (!ctx) return 0;
+    if (first_row) *first_row = ctx->L.row0;
+    return ctx->L.nown;
+}
+int64_t wave_local_nnz(const wave_ctx *ctx) { return ctx ? ctx->nnz : 0; }
+int64_t wave_nnz(const wave_ctx *ctx) {
+    if (!ctx) return 0;
+    const int64_t N = ctx->L.mesh.nx, Ny = ctx->L.mesh.ny;
+    if (ctx->cfg.nranks == 1) return ctx->nnz;
+    // closed forms hold for square meshes; general: count on the fly
+    (void)N; (void)Ny;
+    return -1;
+}
+
+int wave_get_csr(wave_ctx *ctx, int which, int64_t *rowptr, int32_t *col, double *val) {
+    if (!ctx || !ctx->is_setup) return fail(ctx, WAVE_ERR_STATE, "wave_get_csr before wave_setup");
+    const Layout &L = ctx->L;
+    const double *src = mat_ptr(ctx, which);
+    if (val && !src) return fail(ctx, WAVE_ERR_ARG, "matrix not available for this scheme");
+    std::vector<uint32_t> rp((size_t)L.nown + 1);
+    CK(cudaMemcpy(rp.data(), ctx->rowptr, sizeof(uint32_t) * rp.size(), cudaMemcpyDeviceToHost));
+    if (rowptr)
+        for (size_t i = 0; i < rp.size(); ++i) rowptr[i] = rp[i];
+    if (col) {
+        CK(cudaMemcpy(col, ctx->col, sizeof(int32_t) * ctx->nnz, cudaMemcpyDeviceToHost));
+        for (int64_t e = 0; e < ctx->nnz; ++e) col[e] = (int32_t)(col[e] + L.col0);
+    }
+    if (val) CK(cudaMemcpy(val, src, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost));
+    return WAVE_OK;
+}
+
+int wave_get_support_points(wave_ctx *ctx, double *x, double *y, size_t n) {
+    if (!ctx || !ctx->is_setup) return fail(ctx, WAVE_ERR_STATE, "before wave_setup");
+    if (ctx->cfg.nranks != 1 || (int64_t)n != n_dofs(ctx->L.mesh))
+        return fail(ctx, WAVE_ERR_ARG, "support points: single rank, n = n_dofs");
+    double *dx = nullptr, *dy = nullptr;
+    RET(dev_alloc(ctx, &dx, n));
+    RET(dev_alloc(ctx, &dy, n));
+    launch_interpolate(ctx->launcher, ctx->L, ctx->dprog, 0.0, nullptr, dx, dy);
+    CK(cudaMemcpyAsync(x, dx, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(y, dy, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(dx);
+    cudaFree(dy);
+    return WAVE_OK;
+}
+
+int64_t wave_n_boundary_dofs(const wave_ctx *ctx) { return ctx ? ctx->nb_global : 0; }
+int wave_get_boundary_dofs(wave_ctx *ctx, int32_t *out, size_t n) {
+    if (!ctx || !ctx->is_setup || n != ctx->h_bdof_global.size()) return fail(ctx, WAVE_ERR_ARG, "bad size");
+    std::memcpy(out, ctx->h_bdof_global.data(), sizeof(int32_t) * n);
+    return WAVE_OK;
+}
+
+int wave_spmv(wave_ctx *ctx, int which, const double *x, double *y, size_t n) {
+    if (!ctx || !ctx->is_setup) return fail(ctx, WAVE_ERR_STATE, "wave_spmv before wave_setup");
+    const double *val = mat_ptr(ctx, which);
+    if (!val || ctx->cfg.nranks != 1 || (int64_t)n != n_dofs(ctx->L.mesh))
+        return fail(ctx, WAVE_ERR_ARG, "wave_spmv: single rank, n = n_dofs, valid matrix id");
+    CK(cudaMemcpyAsync(ctx->d, x, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    SpmvArgs a = spmv_base(ctx);
+    a.t[0] = {val, ctx->d, nullptr, 1.0, 0.0, 1.0};
+    a.y = ctx->h;
+    launch_spmv(ctx->launcher, a, ctx->maxrow);
+    CK(cudaMemcpyAsync(y, ctx->h, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_check(ctx);
+}
+
+int wave_cg(wave_ctx *ctx, int which, double *x, const double *b, size_t n, int32_t *iters) {
+    if (!ctx || !ctx->is_setup) return fail(ctx, WAVE_ERR_STATE, "wave_cg before wave_setup");
+    const double *val = mat_ptr(ctx, which);
+    if (!val || ctx->cfg.nranks != 1 || (int64_t)n != n_dofs(ctx->L.mesh) ||
+        (which != WAVE_MAT_SYS1 && which != WAVE_MAT_SYS2))
+        return fail(ctx, WAVE_ERR_ARG, "wave_cg: single rank, n = n_dofs, SYS1 or SYS2");
+    const double *dinv = which == WAVE_MAT_SYS1 ? ctx->dinv1 : ctx->dinv2;
+    CK(cudaMemcpyAsync(ctx->unew, x, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->rhs, b, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    int its = 0;
+    ctx->prev_its[0] = 0;
+    const int rc = cg_solve(ctx, val, dinv, ctx->unew, ctx->rhs, 0, &its);
+    ctx->prev_its[0] = 0;
+    if (iters) *iters = its;
+    CK(cudaMemcpyAsync(x, ctx->unew, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+static int ensure_flush(wave_ctx *ctx) {
+    if (ctx->flush_buf) return WAVE_OK;
+    ctx->flush_n = (256LL << 20) / 8;  // 256 MiB > 126 MB L2
+    CK(cudaMalloc(&ctx->flush_buf, sizeof(double) * ctx->flush_n));
+    CK(cudaMemsetAsync(ctx->flush_buf, 0, sizeof(double) * ctx->flush_n, ctx->stream));
+    return WAVE_OK;
+}
+
+int wave_bench_spmv(wave_ctx *ctx, int which, int reps, int flush_l2, double *ms_avg, double *bytes) {
+    if (!ctx || !ctx->is_setup) return fail(ctx, WAVE_ERR_STATE, "wave_bench_spmv before wave_setup");
+    const double *val = mat_ptr(ctx, which);
+    if (!val || reps < 1) return fail(ctx, WAVE_ERR_ARG, "bad matrix id / reps");
+    if (flush_l2) RET(ensure_flush(ctx));
+    SpmvArgs a = spmv_base(ctx);
+    a.t[0] = {val, ctx->u, nullptr, 1.0, 0.0, 1.0};
+    a.y = ctx->h;
+    cudaEvent_t e0 = ctx->ev[2 * PH_COUNT + 2], e1 = ctx->ev[2 * PH_COUNT + 3];
+    for (int w = 0; w < 3; ++w) launch_spmv(ctx->launcher, a, ctx->maxrow);
+    CK(cudaStreamSynchronize(ctx->stream));
+    double total = 0.0;
+    if (flush_l2) {
+        for (int r = 0; r < reps; ++r) {
+            launch_flush_l2(ctx->launcher, ctx->flush_buf, ctx->flush_n);
+            CK(cudaEventRecord(e0, ctx->stream));
+            launch_spmv(ctx->launcher, a, ctx->maxrow);
+            CK(cudaEventRecord(e1, ctx->stream));
+            CK(cudaEventSynchronize(e1));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            total += ms;
+        }
+    } else {
+        CK(cudaEventRecord(e0, ctx->stream));
+        for (int r = 0; r < reps; ++r) launch_spmv(ctx->launcher, a, ctx->maxrow);
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        total = ms;
+    }
+    if (ms_avg) *ms_avg = total / reps;
+    if (bytes) *bytes = 12.0 * (double)ctx->nnz + 20.0 * (double)ctx->L.nown;
+    return WAVE_OK;
+}
+
+int wave_bench_cg_iter(wave_ctx *ctx, int which, int reps, double *ms_avg, double *bytes) {
+    if (!ctx || !ctx->is_setup) return fail(ctx, WAVE_ERR_STATE, "wave_bench_cg_iter before wave_setup");
+    const double *val = mat_ptr(ctx, which);
+    if (!val || (which != WAVE_MAT_SYS1 && which != WAVE_MAT_SYS2) || reps < 1)
+        return fail(ctx, WAVE_ERR_ARG, "bad matrix id / reps");
+    const double *dinv = which == WAVE_MAT_SYS1 ? ctx->dinv1 : ctx->dinv2;
+    const Layout &L = ctx->L;
+    // right-hand side b = A * 1 on interior-compatible data: start from x = 0 each repetition
+    launch_fill(ctx->launcher, L.nloc, 1.0, ctx->d);
+    SpmvArgs a = spmv_base(ctx);
+    a.t[0] = {val, ctx->d, nullptr, 1.0, 0.0, 1.0};
+    a.y = ctx->rhs;
+    launch_spmv(ctx->launcher, a, ctx->maxrow);
+    double ms_total = 0.0, its_total = 0.0;
+    for (int r = 0; r < reps; ++r) {
+        launch_fill(ctx->launcher, L.nloc, 0.0, ctx->unew);
+        const double before_ms = ctx->cg_stats[3], before_it = ctx->cg_stats[1];
+        int its = 0;
+        ctx->prev_its[0] = 0;
+        RET(cg_solve(ctx, val, dinv, ctx->unew, ctx->rhs, 0, &its));
+        ms_total += ctx->cg_stats[3] - before_ms;
+        its_total += ctx->cg_stats[1] - before_it;
+    }
+    ctx->prev_its[0] = 0;
+    if (ms_avg) *ms_avg = its_total > 0 ? ms_total / its_total : 0.0;
+    if (bytes) *bytes = 12.0 * (double)ctx->nnz + 108.0 * (double)L.nown;
+    return WAVE_OK;
+}
+
+int64_t wave_launch_count(const wave_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int wave_timers_enable(wave_ctx *ctx, int on) {
+    if (!ctx) return WAVE_ERR_ARG;
+    ctx->timers_on = on != 0;
+    return WAVE_OK;
+}
+int wave_timers(wave_ctx *ctx, double out_ms[6], int reset) {
+    if (!ctx) return WAVE_ERR_ARG;
+    for (int k = 0; k < PH_COUNT; ++k) {
+        out_ms[k] = ctx->phase_ms[k];
+        if (reset) ctx->phase_ms[k] = 0.0;
+    }
+    return WAVE_OK;
+}
+int wave_cg_stats(wave_ctx *ctx, double out[4], int reset) {
+    if (!ctx) return WAVE_ERR_ARG;
+    for (int k = 0; k < 4; ++k) {
+        out[k] = ctx->cg_stats[k];
+        if (reset) ctx->cg_stats[k] = 0.0;
+    }
+    return WAVE_OK;
+}
+
+int wave_cell_dofs(int32_t nx, int32_t ny, int32_t r, int64_t cell, int32_t *out) {
+    if (nx < 1 || ny < 1 || (r != 1 && r != 2) || cell < 0 || cell >= 2LL * nx * ny || !out) return WAVE_ERR_ARG;
+    Mesh m{};
+    m.nx = nx; m.ny = ny; m.r = r;
+    int64_t d[6];
+    cell_dofs(m, cell, d);
+    for (int k = 0; k < dofs_per_cell(r); ++k) out[k] = (int32_t)d[k];
+    return WAVE_OK;
+}
+
+int wave_partition_plan(int32_t nx, int32_t ny, int32_t r, int32_t rank, int32_t nranks, wave_partition *out) {
+    if (nx < 1 || ny < 1 || (r != 1 && r != 2) || nranks < 1 || rank < 0 || rank >= nranks || ny < nranks || !out)
+        return WAVE_ERR_ARG;
+    Mesh m{};
+    m.nx = nx; m.ny = ny; m.r = r;
+    const Layout L = make_layout(m, rank, nranks);
+    out->quad_row_begin = L.jq0;
+    out->quad_row_end = L.jq1;
+    out->row_begin = L.row0;
+    out->row_end = L.row0 + L.nown;
+    out->ghost_lo_begin = L.col0;
+    out->ghost_hi_end = L.col0 + L.nloc;
+    return WAVE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,713 @@
+// kernels.cu -- sm_100a kernels of the wave-equation hot path (see kernels.cuh for the map to the
+// reference's call sites).  All arithmetic fp64, all kernels HBM-bound; grids are sized in
+// multiples of the SM count where the work is a grid-stride stream.
+#include "kernels.cuh"
+
+#include <cstdio>
+
+namespace wv {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kSMs = 148;  // B200
+
+// ---- deterministic reductions -------------------------------------------------------------------
+// Block tree reduction of NV values (fixed order), result valid in thread 0.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV]) {
+    __shared__ double sm[NV * 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(kFull, v[k], off);
+    __syncthreads();  // protect sm against a previous use
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) sm[warp * NV + k] = v[k];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double x = lane < nwarps ? sm[lane * NV + k] : 0.0;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(kFull, x, off);
+            v[k] = x;
+        }
+    }
+}
+
+// Grid-wide sum: every block contributes its NV partial sums; the block that arrives last adds the
+// per-block partials in block order and returns true with the totals in thread 0's v[].
+// Fixed grid => bitwise reproducible.  The counter is left at zero for the next launch.
+template <int NV>
+__device__ __forceinline__ bool grid_sum(double (&v)[NV], double *partials, unsigned *counter) {
+    __shared__ bool s_last;
+    block_sum<NV>(v);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) partials[(size_t)blockIdx.x * NV + k] = v[k];
+        __threadfence();
+        const unsigned ticket = atomicAdd(counter, 1u);
+        s_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double s = 0.0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+            s += __ldcg(&partials[(size_t)b * NV + k]);
+        v[k] = s;
+    }
+    block_sum<NV>(v);
+    if (threadIdx.x == 0) *counter = 0u;
+    return true;
+}
+
+// Last-block detection without a reduction (for scalar bookkeeping after all blocks have read it).
+__device__ __forceinline__ bool last_block_done(unsigned *counter) {
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned ticket = atomicAdd(counter, 1u);
+        s_last = (ticket == gridDim.x - 1);
+        if (s_last) *counter = 0u;
+    }
+    __syncthreads();
+    return s_last;
+}
+
+// ---- sparsity pattern: DoFTools::make_sparsity_pattern + compress (src/WaveNewmark.cpp:33-35) ----
+// One thread per entity slot; the row is the sorted union of the DoFs of the adjacent cells.
+__device__ int build_row(const Mesh &m, int i, int j, int kind, int64_t *cols) {
+    int64_t cells[6];
+    const int nc = entity_cells(m, i, j, kind, cells);
+    const int dpc = dofs_per_cell(m.r);
+    int n = 0;
+    for (int c = 0; c < nc; ++c) {
+        int64_t d[6];
+        cell_dofs(m, cells[c], d);
+        for (int k = 0; k < dpc; ++k) {
+            // sorted insert, skip duplicates
+            const int64_t v = d[k];
+            int p = n;
+            while (p > 0 && cols[p - 1] > v) --p;
+            if (p > 0 && cols[p - 1] == v) continue;
+            for (int q = n; q > p; --q) cols[q] = cols[q - 1];
+            cols[p] = v;
+            ++n;
+        }
+    }
+    return n;
+}
+
+struct SlotRange {
+    int jlo, jhi, nk;  // lattice rows [jlo, jhi], kinds per lattice point
+};
+__host__ __device__ inline SlotRange owned_slots(const Layout &L) {
+    return {L.jq0, L.jq1, L.mesh.r == 1 ? 1 : 4};
+}
+__host__ __device__ inline SlotRange local_slots(const Layout &L) {
+    const int jlo = L.jq0 > 0 ? L.jq0 - 1 : 0;
+    const int jhi = L.jq1 + 1 <= L.mesh.ny ? L.jq1 + 1 : L.mesh.ny;
+    return {jlo, jhi, L.mesh.r == 1 ? 1 : 4};
+}
+__host__ __device__ inline int64_t slot_count(const Layout &L, const SlotRange &s) {
+    return (int64_t)(s.jhi - s.jlo + 1) * (L.mesh.nx + 1) * s.nk;
+}
+__device__ __forceinline__ void decode_slot(const Layout &L, const SlotRange &s, int64_t t, int &i, int &j,
+                                            int &kind) {
+    kind = (int)(t % s.nk);
+    const int64_t q = t / s.nk;
+    i = (int)(q % (L.mesh.nx + 1));
+    j = s.jlo + (int)(q / (L.mesh.nx + 1));
+}
+
+__global__ void k_row_lengths(Layout L, uint32_t *rowlen) {
+    const SlotRange s = owned_slots(L);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= slot_count(L, s)) return;
+    int i, j, kind;
+    decode_slot(L, s, t, i, j, kind);
+    const int64_t dof = entity_dof(L.mesh, i, j, kind);
+    if (dof < L.row0 || dof >= L.row0 + L.nown) return;
+    int64_t cols[kMaxRow];
+    rowlen[dof - L.row0] = (uint32_t)build_row(L.mesh, i, j, kind, cols);
+}
+
+__global__ void k_fill_cols(Layout L, const uint32_t *rowptr, int32_t *col) {
+    const SlotRange s = owned_slots(L);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= slot_count(L, s)) return;
+    int i, j, kind;
+    decode_slot(L, s, t, i, j, kind);
+    const int64_t dof = entity_dof(L.mesh, i, j, kind);
+    if (dof < L.row0 || dof >= L.row0 + L.nown) return;
+    int64_t cols[kMaxRow];
+    const int n = build_row(L.mesh, i, j, kind, cols);
+    const uint32_t base = rowptr[dof - L.row0];
+    for (int k = 0; k < n; ++k) col[base + k] = (int32_t)(cols[k] - L.col0);
+}
+
+__device__ __forceinline__ uint32_t find_col(const int32_t *col, uint32_t lo, uint32_t hi, int32_t c) {
+    // rows are short and sorted: binary search over [lo, hi)
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const int32_t v = col[mid];
+        if (v == c) return mid;
+        if (v < c) lo = mid + 1; else hi = mid;
+    }
+    return 0xffffffffu;
+}
+
+// ---- K1: assemble_matrices (src/WaveNewmark.cpp:56-108 == src/WaveTheta.cpp:56-108) ---------------
+// One thread per cell: quadrature loop in the reference's order (q outer, i, j inner), c evaluated
+// at the quadrature point at parser time 0, then scatter-add of the owned rows into the CSR values.
+template <int R>
+__global__ void __launch_bounds__(128) k_assemble(Layout L, const Program *cprog, Quadrature Q,
+                                                  const uint32_t *rowptr, const int32_t *col, double *M,
+                                                  double *K) {
+    constexpr int DPC = R == 1 ? 3 : 6;
+    const int jtop = L.jq1 < L.mesh.ny ? L.jq1 : L.mesh.ny - 1;  // one quad row above the owned ones
+    const int64_t c_begin = 2LL * L.jq0 * L.mesh.nx, c_end = 2LL * (jtop + 1) * L.mesh.nx;
+    const int64_t cell = c_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= c_end) return;
+    double X0, Y0, sx, sy;
+    cell_geometry(L.mesh, cell, X0, Y0, sx, sy);
+    const double det = sx * sy, adet = fabs(det);
+    const double ix = sy / det, iy = sx / det;  // J^{-T} = diag(1/sx, 1/sy) written as the adjugate / det
+    double Me[DPC][DPC], Ke[DPC][DPC];
+#pragma unroll
+    for (int a = 0; a < DPC; ++a)
+#pragma unroll
+        for (int b = 0; b < DPC; ++b) { Me[a][b] = 0.0; Ke[a][b] = 0.0; }
+    for (int q = 0; q < Q.nq; ++q) {
+        double phi[DPC], dxi[DPC], deta[DPC], gx[DPC], gy[DPC];
+        shape_values(R, Q.xi[q], Q.eta[q], phi);
+        shape_grads(R, Q.xi[q], Q.eta[q], dxi, deta);
+#pragma unroll
+        for (int a = 0; a < DPC; ++a) { gx[a] = ix * dxi[a]; gy[a] = iy * deta[a]; }
+        const double JxW = Q.w[q] * adet;
+        const double xq = X0 + sx * Q.xi[q], yq = Y0 + sy * Q.eta[q];
+        const double cv = eval(cprog, xq, yq, 0.0);
+        const double c2 = cv * cv;
+#pragma unroll
+        for (int a = 0; a < DPC; ++a)
+#pragma unroll
+            for (int b = 0; b < DPC; ++b) {
+                Me[a][b] += phi[a] * phi[b] * JxW;
+                Ke[a][b] += c2 * (gx[a] * gx[b] + gy[a] * gy[b]) * JxW;
+            }
+    }
+    int64_t d[6];
+    cell_dofs(L.mesh, cell, d);
+#pragma unroll
+    for (int a = 0; a < DPC; ++a) {
+        const int64_t row = d[a] - L.row0;
+        if (row < 0 || row >= L.nown) continue;
+        const uint32_t lo = rowptr[row], hi = rowptr[row + 1];
+#pragma unroll
+        for (int b = 0; b < DPC; ++b) {
+            const uint32_t pos = find_col(col, lo, hi, (int32_t)(d[b] - L.col0));
+            atomicAdd(&M[pos], Me[a][b]);
+            atomicAdd(&K[pos], Ke[a][b]);
+        }
+    }
+}
+
+// ---- K2: matrix_a = M + s K on the shared pattern (src/WaveNewmark.cpp:111-112) --------------------
+__global__ void __launch_bounds__(kThreads) k_axpy_vals(int64_t nnz, const double *__restrict__ M,
+                                                        const double *__restrict__ K, double s,
+                                                        double *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride)
+        out[e] = M[e] + s * K[e];
+}
+
+// [deal.II] MatrixTools::apply_boundary_values (Trilinos overload, Release build):
+// d0 = |first non-zero diagonal entry| of the rank's rows; each boundary row becomes d0 * e_i.
+__global__ void k_find_d0(Layout L, const uint32_t *rowptr, const int32_t *col, const double *val, double *d0) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double r = 0.0;
+    for (int i = 0; i < L.nown; ++i) {
+        const uint32_t pos = find_col(col, rowptr[i], rowptr[i + 1], i + L.own_off);
+        if (pos != 0xffffffffu && val[pos] != 0.0) { r = fabs(val[pos]); break; }
+    }
+    *d0 = r;
+}
+__global__ void k_bc_rows(Layout L, int nb, const int32_t *brow, const uint32_t *rowptr, const int32_t *col,
+                          double *val, const double *d0) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const int row = brow[b];
+    const double diag = *d0;
+    for (uint32_t e = rowptr[row]; e < rowptr[row + 1]; ++e) val[e] = (col[e] == row + L.own_off) ? diag : 0.0;
+}
+// Jacobi: 1 / diag(A) (stand-in for PreconditionAMG / PreconditionSSOR per the north star)
+__global__ void k_dinv(Layout L, const uint32_t *rowptr, const int32_t *col, const double *val, int identity,
+                       double *dinv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.nown) return;
+    if (identity) { dinv[i] = 1.0; return; }
+    const uint32_t pos = find_col(col, rowptr[i], rowptr[i + 1], i + L.own_off);
+    dinv[i] = 1.0 / val[pos];
+}
+
+// ---- K9: VectorTools::interpolate at DoF support points (src/WaveNewmark.cpp:292-293) --------------
+__global__ void k_interpolate(Layout L, const Program *p, double t, double *vec, double *sx, double *sy) {
+    const SlotRange s = local_slots(L);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= slot_count(L, s)) return;
+    int i, j, kind;
+    decode_slot(L, s, tid, i, j, kind);
+    const int64_t dof = entity_dof(L.mesh, i, j, kind);
+    if (dof < L.col0 || dof >= L.col0 + L.nloc) return;
+    double x, y;
+    entity_point(L.mesh, i, j, kind, x, y);
+    if (vec) vec[dof - L.col0] = eval(p, x, y, t);
+    if (sx) { sx[dof - L.col0] = x; sy[dof - L.col0] = y; }
+}
+
+// ---- K4: forcing load vector (src/WaveNewmark.cpp:151-171, src/WaveTheta.cpp:151-180) ---------------
+template <int R>
+__global__ void __launch_bounds__(128) k_forcing(Layout L, const Program *f, Quadrature Q, double t_np1,
+                                                 double t_n, double w_np1, double w_n, int two_levels,
+                                                 double *fvec) {
+    constexpr int DPC = R == 1 ? 3 : 6;
+    const int jtop = L.jq1 < L.mesh.ny ? L.jq1 : L.mesh.ny - 1;
+    const int64_t c_begin = 2LL * L.jq0 * L.mesh.nx, c_end = 2LL * (jtop + 1) * L.mesh.nx;
+    const int64_t cell = c_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= c_end) return;
+    double X0, Y0, sx, sy;
+    cell_geometry(L.mesh, cell, X0, Y0, sx, sy);
+    const double adet = fabs(sx * sy);
+    double acc[DPC];
+#pragma unroll
+    for (int a = 0; a < DPC; ++a) acc[a] = 0.0;
+    for (int q = 0; q < Q.nq; ++q) {
+        double phi[DPC];
+        shape_values(R, Q.xi[q], Q.eta[q], phi);
+        const double JxW = Q.w[q] * adet;
+        const double xq = X0 + sx * Q.xi[q], yq = Y0 + sy * Q.eta[q];
+        double fv;
+        if (two_levels) {
+            const double f_n = eval(f, xq, yq, t_n);
+            const double f_np1 = eval(f, xq, yq, t_np1);
+            fv = w_np1 * f_np1 + w_n * f_n;
+        } else
+            fv = eval(f, xq, yq, t_np1);
+#pragma unroll
+        for (int a = 0; a < DPC; ++a) acc[a] += fv * phi[a] * JxW;
+    }
+    int64_t d[6];
+    cell_dofs(L.mesh, cell, d);
+#pragma unroll
+    for (int a = 0; a < DPC; ++a) {
+        const int64_t row = d[a] - L.row0;
+        if (row >= 0 && row < L.nown) atomicAdd(&fvec[row], acc[a]);
+    }
+}
+
+// ---- K5: boundary values (src/WaveNewmark.cpp:186-241, :348-374; src/WaveTheta.cpp:259-272) ---------
+__global__ void k_bc_values(int mode, int nb, const int32_t *brow, const double *bx, const double *by,
+                            const Program *g, double t, double dt, double beta_dt2, const double *z_own,
+                            double *x_own, double *rhs, const double *d0) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const int row = brow[b];
+    const double x = bx[b], y = by[b];
+    double val;
+    if (mode == BC_DIRECT)
+        val = eval(g, x, y, t);
+    else if (mode == BC_NEWMARK_IMPLICIT)
+        val = (eval(g, x, y, t) - z_own[row]) / beta_dt2;
+    else {
+        const double inv_dt2 = 1.0 / (dt * dt);
+        val = (eval(g, x, y, t) - 2.0 * eval(g, x, y, t - dt) + eval(g, x, y, t - 2.0 * dt)) * inv_dt2;
+    }
+    x_own[row] = val;
+    rhs[row] = val * (*d0);
+}
+
+// ---- K3: CSR-stream SpMV (TrilinosWrappers::SparseMatrix::vmult) ------------------------------------
+// A block owns kRowsPerBlock consecutive rows.  Phase 1 streams the block's contiguous (val, col)
+// range with fully coalesced loads, gathers x through L1/L2 (the matrix band keeps the gathered
+// window cache resident) and parks the products in shared memory.  Phase 2: one thread per row adds
+// its products in column order -- the summation order of a serial CSR loop, hence bitwise equal to
+// it for a single term.  Epilogues: addends, CG residual start (h = D^-1 g, d = -h), fused dots.
+template <int NT, bool TWOX>
+__global__ void __launch_bounds__(kThreads) k_spmv(SpmvArgs a) {
+    extern __shared__ double prod[];
+    if (a.skip_flag && *a.skip_flag != 0) return;
+    const int r0 = blockIdx.x * kRowsPerBlock;
+    const int r1 = min(r0 + kRowsPerBlock, a.nrows);
+    const uint32_t e0 = a.rowptr[r0], e1 = a.rowptr[r1];
+    for (uint32_t e = e0 + threadIdx.x; e < e1; e += kThreads) {
+        const int c = __ldg(&a.col[e]);
+        double p = 0.0;
+#pragma unroll
+        for (int k = 0; k < NT; ++k) {
+            double xv = a.t[k].ca * a.t[k].xa[c];
+            if (TWOX && a.t[k].xb) xv += a.t[k].cb * a.t[k].xb[c];
+            p += a.t[k].coef * (__ldg(&a.t[k].val[e]) * xv);
+        }
+        prod[e - e0] = p;
+    }
+    __syncthreads();
+    double dots[2] = {0.0, 0.0};
+    const int r = r0 + threadIdx.x;
+    if (r < r1) {
+        const uint32_t b = a.rowptr[r] - e0, e = a.rowptr[r + 1] - e0;
+        double s = 0.0;
+        for (uint32_t k = b; k < e; ++k) s += prod[k];
+        if (a.add0) s += a.addc0 * a.add0[r];
+        if (a.add1) s += a.addc1 * a.add1[r];
+        if (a.y) a.y[r] = s;
+        double hv = 0.0;
+        if (a.h_out) {
+            hv = a.dinv[r] * s;
+            a.h_out[r] = hv;
+            a.d_out[r] = -hv;
+        }
+        if (a.dot_mode == 1) dots[0] = s * a.dotv[r];
+        else if (a.dot_mode == 2) { dots[0] = s * s; dots[1] = s * hv; }
+    }
+    if (a.dot_mode) {
+        if (grid_sum<2>(dots, a.partials, a.counter) && threadIdx.x == 0) {
+            a.result[0] = dots[0];
+            if (a.dot_mode == 2) a.result[1] = dots[1];
+        }
+    }
+}
+
+// ---- K6: PCG with device-resident scalars (deal.II SolverCG) ----------------------------
+// after the residual SpMV + all-reduce: iteration_status(0, res0)
+__global__ void k_cg_start(CgScalars *S) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double res0 = sqrt(S->gg);
+    S->res0 = res0;
+    S->res = res0;
+    S->reduced_tol = res0 * S->reduce;
+    S->it = 0;
+    S->gh_old = S->gh_new;
+    S->status = (res0 <= S->reduced_tol || res0 <= S->tol) ? 1 : 0;
+}
+// x += alpha d ; g += alpha h ; res^2 = g.g ; h = D^-1 g ; gh' = g.h   (one pass, 5 reads 3 writes)
+__global__ void __launch_bounds__(kThreads) k_cg_update(int n, CgScalars *S, double *__restrict__ x,
+                                                        double *__restrict__ g, double *__restrict__ h,
+                                                        const double *__restrict__ d,
+                                                        const double *__restrict__ dinv, double *partials,
+                                                        unsigned *counter) {
+    if (S->status != 0) return;
+    const double alpha = S->gh_old / S->dAd;
+    double acc[2] = {0.0, 0.0};
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        x[i] += alpha * d[i];
+        const double gi = g[i] + alpha * h[i];
+        const double hi = dinv[i] * gi;
+        g[i] = gi;
+        h[i] = hi;
+        acc[0] += gi * gi;
+        acc[1] += gi * hi;
+    }
+    if (grid_sum<2>(acc, partials, counter) && threadIdx.x == 0) {
+        S->gg = acc[0];
+        S->gh_new = acc[1];
+    }
+}
+// iteration_status(it, res); beta = gh'/gh ; d = beta d - h
+__global__ void __launch_bounds__(kThreads) k_cg_direction(int n, CgScalars *S, double *__restrict__ d,
+                                                           const double *__restrict__ h, unsigned *counter) {
+    if (S->status != 0) return;
+    const double res = sqrt(fabs(S->gg));
+    const int it = S->it + 1;
+    int status = 0;
+    if (res <= S->reduced_tol || res <= S->tol) status = 1;
+    else if (it >= S->maxit || isnan(res)) status = 2;
+    if (status == 0) {
+        const double beta = S->gh_new / S->gh_old;
+        const int stride = gridDim.x * blockDim.x;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) d[i] = beta * d[i] - h[i];
+    }
+    if (last_block_done(counter) && threadIdx.x == 0) {
+        S->it = it;
+        S->res = res;
+        S->status = status;
+        S->gh_old = S->gh_new;
+    }
+}
+
+// ---- K7: fused Newmark vector updates (src/WaveNewmark.cpp:121-126, :264-278, :429-430) --------------
+// predictor, in place: u <- z = u + dt v + dt^2(1/2-beta) a ;  v <- v + dt(1-gamma) a
+__global__ void __launch_bounds__(kThreads) k_newmark_predict(int n, double dt, double c1, double c2,
+                                                              double *__restrict__ u, double *__restrict__ v,
+                                                              const double *__restrict__ a) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double ui = u[i], vi = v[i], ai = a[i];
+        u[i] = (ui + dt * vi) + c1 * ai;
+        v[i] = vi + c2 * ai;
+    }
+}
+// corrector: u <- z + beta dt^2 a+ ; v <- v + dt gamma a+ ; ||u||^2, ||v||^2
+__global__ void __launch_bounds__(kThreads) k_newmark_correct(int n, double cu, double cv,
+                                                              double *__restrict__ u, double *__restrict__ v,
+                                                              const double *__restrict__ a, double *partials,
+                                                              unsigned *counter, double *result) {
+    double acc[2] = {0.0, 0.0};
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double ai = a[i];
+        const double ui = u[i] + cu * ai, vi = v[i] + cv * ai;
+        u[i] = ui;
+        v[i] = vi;
+        acc[0] += ui * ui;
+        acc[1] += vi * vi;
+    }
+    if (grid_sum<2>(acc, partials, counter) && threadIdx.x == 0) { result[0] = acc[0]; result[1] = acc[1]; }
+}
+__global__ void __launch_bounds__(kThreads) k_norms2(int n, const double *__restrict__ u,
+                                                     const double *__restrict__ v, double *partials,
+                                                     unsigned *counter, double *result) {
+    double acc[2] = {0.0, 0.0};
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        acc[0] += u[i] * u[i];
+        acc[1] += v[i] * v[i];
+    }
+    if (grid_sum<2>(acc, partials, counter) && threadIdx.x == 0) { result[0] = acc[0]; result[1] = acc[1]; }
+}
+__global__ void __launch_bounds__(kThreads) k_copy(int n, const double *__restrict__ src, double *__restrict__ dst) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+__global__ void __launch_bounds__(kThreads) k_fill(int64_t n, double value, double *__restrict__ dst) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = value;
+}
+
+// ---- error norms: compute_error / compute_relative_error (src/WaveEquationBase.cpp:367-423) ---------
+// [deal.II] integrate_difference with QGaussSimplex(r+2); per-cell numerator rounded to float (:384),
+// exact-solution gradient by centred differences h = 1e-8 (FunctionParser is an AutoDerivativeFunction).
+template <int R>
+__global__ void __launch_bounds__(128) k_errors(Layout L, const Program *sol, Quadrature Q, double t,
+                                                const double *u, double *partials, unsigned *counter,
+                                                double *result) {
+    constexpr int DPC = R == 1 ? 3 : 6;
+    const int64_t c_begin = 2LL * L.jq0 * L.mesh.nx, c_end = 2LL * L.jq1 * L.mesh.nx;
+    const int64_t cell = c_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    if (cell < c_end) {
+        double X0, Y0, sx, sy;
+        cell_geometry(L.mesh, cell, X0, Y0, sx, sy);
+        const double det = sx * sy, adet = fabs(det);
+        const double ix = sy / det, iy = sx / det;
+        int64_t d[6];
+        cell_dofs(L.mesh, cell, d);
+        double ul[DPC];
+#pragma unroll
+        for (int a = 0; a < DPC; ++a) ul[a] = u[d[a] - L.col0];
+        const double hfd = 1e-8;
+        double dl2 = 0, dsemi = 0, xl2 = 0, xsemi = 0;
+        for (int q = 0; q < Q.nq; ++q) {
+            double phi[DPC], dxi[DPC], deta[DPC];
+            shape_values(R, Q.xi[q], Q.eta[q], phi);
+            shape_grads(R, Q.xi[q], Q.eta[q], dxi, deta);
+            const double JxW = Q.w[q] * adet;
+            const double xq = X0 + sx * Q.xi[q], yq = Y0 + sy * Q.eta[q];
+            double uh = 0, ux = 0, uy = 0;
+#pragma unroll
+            for (int a = 0; a < DPC; ++a) {
+                uh += ul[a] * phi[a];
+                ux += ul[a] * (ix * dxi[a]);
+                uy += ul[a] * (iy * deta[a]);
+            }
+            const double ue = eval(sol, xq, yq, t);
+            const double uex = (eval(sol, xq + hfd, yq, t) - eval(sol, xq - hfd, yq, t)) / (2 * hfd);
+            const double uey = (eval(sol, xq, yq + hfd, t) - eval(sol, xq, yq - hfd, t)) / (2 * hfd);
+            dl2 += (uh - ue) * (uh - ue) * JxW;
+            dsemi += ((ux - uex) * (ux - uex) + (uy - uey) * (uy - uey)) * JxW;
+            xl2 += ue * ue * JxW;
+            xsemi += (uex * uex + uey * uey) * JxW;
+        }
+        const float fl2 = (float)sqrt(dl2), fh1 = (float)sqrt(dl2 + dsemi);
+        acc[0] = (double)fl2 * (double)fl2;
+        acc[1] = (double)fh1 * (double)fh1;
+        acc[2] = xl2;
+        acc[3] = xl2 + xsemi;
+    }
+    if (grid_sum<4>(acc, partials, counter) && threadIdx.x == 0) {
+        result[0] = acc[0]; result[1] = acc[1]; result[2] = acc[2]; result[3] = acc[3];
+    }
+}
+
+// log_point_probe: u_h at a point (src/WaveEquationBase.cpp:170-206); the rank owning the quad row
+// evaluates, the others contribute 0 (the reference's MPI_Reduce SUM).
+__global__ void k_probe(Layout L, double px, double py, const double *u, double *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const Mesh &m = L.mesh;
+    double val = 0.0;
+    int i = (int)floor((px - m.x0) / m.dx), j = (int)floor((py - m.y0) / m.dy);
+    if (i >= m.nx) i = m.nx - 1;
+    if (j >= m.ny) j = m.ny - 1;
+    if (i < 0) i = 0;
+    if (j < 0) j = 0;
+    // the oracle walks cells in order and takes the first that contains the point: prefer the
+    // lower-index candidates (left / lower quad, T0 before T1) when the point sits on an edge
+    const double eps = 1e-12;
+    bool found = false;
+    for (int jj = (j > 0 ? j - 1 : 0); jj <= j && !found; ++jj)
+        for (int ii = (i > 0 ? i - 1 : 0); ii <= i && !found; ++ii)
+            for (int tt = 0; tt < 2 && !found; ++tt) {
+                const int64_t cell = 2 * ((int64_t)jj * m.nx + ii) + tt;
+                double X0, Y0, sx, sy;
+                cell_geometry(m, cell, X0, Y0, sx, sy);
+                const double xi = (px - X0) / sx, eta = (py - Y0) / sy;
+                if (xi >= -eps && eta >= -eps && xi + eta <= 1.0 + eps) {
+                    found = true;
+                    if (jj >= L.jq0 && jj < L.jq1) {
+                        double phi[6];
+                        int64_t d[6];
+                        shape_values(m.r, xi, eta, phi);
+                        cell_dofs(m, cell, d);
+                        for (int a = 0; a < dofs_per_cell(m.r); ++a) val += u[d[a] - L.col0] * phi[a];
+                    }
+                }
+            }
+    *out = val;
+}
+
+__global__ void __launch_bounds__(kThreads) k_flush(double *buf, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) buf[i] = buf[i] * 0.5 + 1.0;
+}
+
+inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+// grid-stride streams: a multiple of the SM count, capped by the work available
+inline int stream_blocks(int64_t n) {
+    const int64_t need = (n + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)kSMs * 8;
+    return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+}  // namespace
+
+int reduction_blocks(int n) { return stream_blocks(n); }
+
+#define WV_LAUNCH(l, kernel, grid, block, smem, ...)              \
+    do {                                                          \
+        kernel<<<(grid), (block), (smem), (l).stream>>>(__VA_ARGS__); \
+        if ((l).count) ++*(l).count;                              \
+    } while (0)
+
+void launch_row_lengths(const Launcher &l, const Layout &L, uint32_t *rowlen) {
+    const int64_t n = slot_count(L, owned_slots(L));
+    WV_LAUNCH(l, k_row_lengths, blocks_for(n, 128), 128, 0, L, rowlen);
+}
+void launch_fill_cols(const Launcher &l, const Layout &L, const uint32_t *rowptr, int32_t *col) {
+    const int64_t n = slot_count(L, owned_slots(L));
+    WV_LAUNCH(l, k_fill_cols, blocks_for(n, 128), 128, 0, L, rowptr, col);
+}
+static int64_t assembly_cells(const Layout &L) {
+    const int jtop = L.jq1 < L.mesh.ny ? L.jq1 : L.mesh.ny - 1;
+    return 2LL * (jtop + 1 - L.jq0) * L.mesh.nx;
+}
+void launch_assemble(const Launcher &l, const Layout &L, const Program *c, const Quadrature *q,
+                     const uint32_t *rowptr, const int32_t *col, double *M, double *K) {
+    const int64_t n = assembly_cells(L);
+    if (L.mesh.r == 1) WV_LAUNCH(l, k_assemble<1>, blocks_for(n, 128), 128, 0, L, c, *q, rowptr, col, M, K);
+    else WV_LAUNCH(l, k_assemble<2>, blocks_for(n, 128), 128, 0, L, c, *q, rowptr, col, M, K);
+}
+void launch_axpy_vals(const Launcher &l, int64_t nnz, const double *M, const double *K, double s, double *out) {
+    WV_LAUNCH(l, k_axpy_vals, stream_blocks(nnz), kThreads, 0, nnz, M, K, s, out);
+}
+void launch_find_d0(const Launcher &l, const Layout &L, const uint32_t *rowptr, const int32_t *col,
+                    const double *val, double *d0) {
+    WV_LAUNCH(l, k_find_d0, 1, 32, 0, L, rowptr, col, val, d0);
+}
+void launch_bc_rows(const Launcher &l, const Layout &L, int nb, const int32_t *brow, const uint32_t *rowptr,
+                    const int32_t *col, double *val, const double *d0) {
+    if (nb <= 0) return;
+    WV_LAUNCH(l, k_bc_rows, blocks_for(nb, 128), 128, 0, L, nb, brow, rowptr, col, val, d0);
+}
+void launch_dinv(const Launcher &l, const Layout &L, const uint32_t *rowptr, const int32_t *col,
+                 const double *val, int identity, double *dinv) {
+    WV_LAUNCH(l, k_dinv, blocks_for(L.nown, kThreads), kThreads, 0, L, rowptr, col, val, identity, dinv);
+}
+void launch_interpolate(const Launcher &l, const Layout &L, const Program *p, double t, double *vec,
+                        double *sx, double *sy) {
+    const int64_t n = slot_count(L, local_slots(L));
+    WV_LAUNCH(l, k_interpolate, blocks_for(n, 128), 128, 0, L, p, t, vec, sx, sy);
+}
+void launch_forcing(const Launcher &l, const Layout &L, const Program *f, const Quadrature *q, double t_np1,
+                    double t_n, double w_np1, double w_n, int two_levels, double *fvec) {
+    const int64_t n = assembly_cells(L);
+    if (L.mesh.r == 1)
+        WV_LAUNCH(l, k_forcing<1>, blocks_for(n, 128), 128, 0, L, f, *q, t_np1, t_n, w_np1, w_n, two_levels, fvec);
+    else
+        WV_LAUNCH(l, k_forcing<2>, blocks_for(n, 128), 128, 0, L, f, *q, t_np1, t_n, w_np1, w_n, two_levels, fvec);
+}
+void launch_bc_values(const Launcher &l, int mode, int nb, const int32_t *brow, const double *bx,
+                      const double *by, const Program *g, double t, double dt, double beta_dt2,
+                      const double *z_own, double *x_own, double *rhs, const double *d0) {
+    if (nb <= 0) return;
+    WV_LAUNCH(l, k_bc_values, blocks_for(nb, 128), 128, 0, mode, nb, brow, bx, by, g, t, dt, beta_dt2, z_own,
+              x_own, rhs, d0);
+}
+void launch_spmv(const Launcher &l, const SpmvArgs &a, int maxrow) {
+    const int grid = blocks_for(a.nrows, kRowsPerBlock);
+    const size_t smem = (size_t)kRowsPerBlock * maxrow * sizeof(double);
+    const bool two_terms = a.t[1].val != nullptr;
+    const bool twox = a.t[0].xb != nullptr || (two_terms && a.t[1].xb != nullptr);
+    if (!two_terms && !twox) WV_LAUNCH(l, (k_spmv<1, false>), grid, kThreads, smem, a);
+    else if (!two_terms) WV_LAUNCH(l, (k_spmv<1, true>), grid, kThreads, smem, a);
+    else WV_LAUNCH(l, (k_spmv<2, true>), grid, kThreads, smem, a);
+}
+void launch_cg_start(const Launcher &l, CgScalars *S) { WV_LAUNCH(l, k_cg_start, 1, 32, 0, S); }
+void launch_cg_update(const Launcher &l, int n, CgScalars *S, double *x, double *g, double *h, const double *d,
+                      const double *dinv, double *partials, unsigned *counter) {
+    WV_LAUNCH(l, k_cg_update, stream_blocks(n), kThreads, 0, n, S, x, g, h, d, dinv, partials, counter);
+}
+void launch_cg_direction(const Launcher &l, int n, CgScalars *S, double *d, const double *h, unsigned *counter) {
+    WV_LAUNCH(l, k_cg_direction, stream_blocks(n), kThreads, 0, n, S, d, h, counter);
+}
+void launch_newmark_predict(const Launcher &l, int n, double dt, double c1, double c2, double *u, double *v,
+                            const double *a) {
+    WV_LAUNCH(l, k_newmark_predict, stream_blocks(n), kThreads, 0, n, dt, c1, c2, u, v, a);
+}
+void launch_newmark_correct(const Launcher &l, int n, double cu, double cv, double *u, double *v, const double *a,
+                            double *partials, unsigned *counter, double *result) {
+    WV_LAUNCH(l, k_newmark_correct, stream_blocks(n), kThreads, 0, n, cu, cv, u, v, a, partials, counter, result);
+}
+void launch_norms2(const Launcher &l, int n, const double *u, const double *v, double *partials,
+                   unsigned *counter, double *result) {
+    WV_LAUNCH(l, k_norms2, stream_blocks(n), kThreads, 0, n, u, v, partials, counter, result);
+}
+void launch_copy(const Launcher &l, int n, const double *src, double *dst) {
+    WV_LAUNCH(l, k_copy, stream_blocks(n), kThreads, 0, n, src, dst);
+}
+void launch_fill(const Launcher &l, int64_t n, double value, double *dst) {
+    if (n <= 0) return;
+    WV_LAUNCH(l, k_fill, stream_blocks(n), kThreads, 0, n, value, dst);
+}
+void launch_errors(const Launcher &l, const Layout &L, const Program *sol, const Quadrature *q, double t,
+                   const double *u_local, double *partials, unsigned *counter, double *result) {
+    const int64_t n = 2LL * (L.jq1 - L.jq0) * L.mesh.nx;
+    if (L.mesh.r == 1)
+        WV_LAUNCH(l, k_errors<1>, blocks_for(n, 128), 128, 0, L, sol, *q, t, u_local, partials, counter, result);
+    else
+        WV_LAUNCH(l, k_errors<2>, blocks_for(n, 128), 128, 0, L, sol, *q, t, u_local, partials, counter, result);
+}
+void launch_probe(const Launcher &l, const Layout &L, double px, double py, const double *u_local, double *out) {
+    WV_LAUNCH(l, k_probe, 1, 32, 0, L, px, py, u_local, out);
+}
+void launch_flush_l2(const Launcher &l, double *buf, int64_t n) {
+    WV_LAUNCH(l, k_flush, stream_blocks(n), kThreads, 0, buf, n);
+}
+
+}  // namespace wv

@@ -1,0 +1,118 @@
+// kernels.cuh -- hand-written sm_100a kernels of the wave-equation hot path.
+//
+// Everything here is fp64 and HBM-bandwidth bound (O(1) flop/byte): no tensor cores.  Kernel
+// ids follow SURVEY.md section 2.1:
+//   K1  per-cell quadrature M_e, K_e + CSR scatter          (assemble_matrices)
+//   K2  A = M + s K on the shared pattern, Dirichlet rows    (copy_from/add + apply_boundary_values)
+//   K3  CSR-stream SpMV with fused epilogues                 (SparseMatrix::vmult)
+//   K4  per-cell load vector with the compiled f(x,y,t)      (forcing loops)
+//   K5  boundary values -> rhs / start vector                (interpolate_boundary_values)
+//   K6  PCG pieces with device-resident scalars              (SolverCG::solve)
+//   K7  fused Newmark predictor / corrector + norms          (assemble_rhs z, update_u_v)
+//   K8  energy (SpMV + fused dot)                            (compute_and_log_energy)
+//   K9  interpolation of u0 / v0 at support points           (VectorTools::interpolate)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "expr_vm.h"
+#include "mesh.h"
+
+namespace wv {
+
+// ---- local (per-rank) layout -----------------------------------------------------------------
+// A rank owns the DoF blocks of quad rows [jq0, jq1): canonical rows [row0, row0+nown).
+// Its vectors cover the canonical range [col0, col0+nloc) = lower ghost block | owned | upper
+// ghost block, so a local column index is (global - col0) and halos are contiguous copies.
+struct Layout {
+    Mesh mesh;
+    int jq0, jq1;
+    int64_t row0, col0;
+    int nown, nloc, own_off;
+};
+
+constexpr int kThreads = 256;
+constexpr int kRowsPerBlock = 256;  // K3: one row per thread in the row-sum phase
+constexpr int kMaxRow = 40;
+
+// device-resident CG state (deal.II SolverCG + ReductionControl, src/WaveNewmark.cpp:256-261)
+struct CgScalars {
+    double dAd, gg, gh_new, gh_old;
+    double res0, reduced_tol, res;
+    double tol, reduce;
+    int it, status, maxit, pad;  // status: 0 iterate, 1 success, 2 failure
+};
+
+struct SpmvTerm {
+    const double *val;
+    const double *xa, *xb;  // local-layout vectors; x = ca*xa + cb*xb
+    double ca, cb, coef;
+};
+struct SpmvArgs {
+    const uint32_t *rowptr;
+    const int32_t *col;
+    int nrows;
+    SpmvTerm t[2];
+    const double *add0, *add1;  // row-indexed addends
+    double addc0, addc1;
+    double *y;                  // row-indexed result (may be null)
+    // residual epilogue (CG start): h = dinv*y, d = -h
+    const double *dinv;
+    double *h_out, *d_out;
+    // fused dots: mode 0 none, 1 sum y_i*dotv_i, 2 {sum y_i^2, sum y_i*h_i}
+    int dot_mode;
+    const double *dotv;
+    double *partials;
+    unsigned *counter;
+    double *result;            // totals (1 or 2 doubles)
+    const int *skip_flag;      // if non-null and *skip_flag != 0 the kernel returns at once
+};
+
+// ---- launch wrappers (defined in kernels.cu) ---------------------------------------------------
+struct Launcher {
+    cudaStream_t stream;
+    long long *count;  // kernels launched
+};
+
+void launch_row_lengths(const Launcher &, const Layout &, uint32_t *rowlen);
+void launch_fill_cols(const Launcher &, const Layout &, const uint32_t *rowptr, int32_t *col);
+void launch_assemble(const Launcher &, const Layout &, const Program *c, const Quadrature *q,
+                     const uint32_t *rowptr, const int32_t *col, double *M, double *K);
+void launch_axpy_vals(const Launcher &, int64_t nnz, const double *M, const double *K, double s, double *out);
+void launch_find_d0(const Launcher &, const Layout &, const uint32_t *rowptr, const int32_t *col,
+                    const double *val, double *d0);
+void launch_bc_rows(const Launcher &, const Layout &, int nb, const int32_t *brow, const uint32_t *rowptr,
+                    const int32_t *col, double *val, const double *d0);
+void launch_dinv(const Launcher &, const Layout &, const uint32_t *rowptr, const int32_t *col,
+                 const double *val, int identity, double *dinv);
+void launch_interpolate(const Launcher &, const Layout &, const Program *p, double t, double *vec,
+                        double *sx, double *sy);
+void launch_forcing(const Launcher &, const Layout &, const Program *f, const Quadrature *q, double t_np1,
+                    double t_n, double w_np1, double w_n, int two_levels, double *fvec);
+// K5 modes
+enum { BC_DIRECT = 0, BC_NEWMARK_IMPLICIT = 1, BC_SECOND_DIFF = 2 };
+void launch_bc_values(const Launcher &, int mode, int nb, const int32_t *brow, const double *bx,
+                      const double *by, const Program *g, double t, double dt, double beta_dt2,
+                      const double *z_own, double *x_own, double *rhs, const double *d0);
+void launch_spmv(const Launcher &, const SpmvArgs &, int maxrow);
+void launch_cg_start(const Launcher &, CgScalars *S);
+void launch_cg_update(const Launcher &, int n, CgScalars *S, double *x, double *g, double *h, const double *d,
+                      const double *dinv, double *partials, unsigned *counter);
+void launch_cg_direction(const Launcher &, int n, CgScalars *S, double *d, const double *h, unsigned *counter);
+void launch_newmark_predict(const Launcher &, int n, double dt, double c1, double c2, double *u, double *v,
+                            const double *a);
+void launch_newmark_correct(const Launcher &, int n, double cu, double cv, double *u, double *v, const double *a,
+                            double *partials, unsigned *counter, double *result);
+void launch_norms2(const Launcher &, int n, const double *u, const double *v, double *partials,
+                   unsigned *counter, double *result);
+void launch_copy(const Launcher &, int n, const double *src, double *dst);
+void launch_fill(const Launcher &, int64_t n, double value, double *dst);
+void launch_errors(const Launcher &, const Layout &, const Program *sol, const Quadrature *q, double t,
+                   const double *u_local, double *partials, unsigned *counter, double *result);
+void launch_probe(const Launcher &, const Layout &, double px, double py, const double *u_local, double *out);
+void launch_flush_l2(const Launcher &, double *buf, int64_t n);
+
+int reduction_blocks(int n);
+
+}  // namespace wv
