@@ -77,6 +77,7 @@ typedef struct {
     int32_t device;             /* CUDA ordinal, -1 = current device */
     const void *nccl_unique_id; /* 128 bytes from wave_comm_unique_id (rank 0), NULL if nranks==1 */
     uint32_t flags;             /* WAVE_FLAG_* */
+    void *stream;               /* cudaStream_t to run on (caller-owned), NULL = private stream */
 } wave_config;
 
 #define WAVE_FLAG_FORCING_EVERY_STEP 1u /* assemble F even when it folds to 0 (as the reference) */
@@ -174,6 +175,10 @@ int64_t wave_launch_count(const wave_ctx *ctx);
    the context stream when enabled: {rhs, bc, cg, update, energy, other}. */
 int wave_timers_enable(wave_ctx *ctx, int on);
 int wave_timers(wave_ctx *ctx, double out_ms[6], int reset);
+/* Bracket every SpMV launch of the CG solves with CUDA events on the context stream (on != 0) and
+   read back the accumulated count and device milliseconds (roofline.achieved of bench.py is
+   algorithmic bytes / (ms / launches) taken live inside the timed steps). */
+int wave_spmv_timing(wave_ctx *ctx, int on, double *launches, double *ms_total);
 /* Device-time and iteration statistics of the CG solves since the last reset:
    out = {solves, iterations, spmv_launches, ms_total}. */
 int wave_cg_stats(wave_ctx *ctx, double out[4], int reset);

@@ -80,6 +80,7 @@ struct wave_ctx {
     Layout L{};
     std::string err;
     cudaStream_t stream = nullptr;
+    bool own_stream = false;
     long long launches = 0;
     Launcher launcher{};
     bool is_setup = false, is_init = false;
@@ -130,6 +131,10 @@ struct wave_ctx {
     double phase_ms[PH_COUNT]{};
     cudaEvent_t ev[2 * PH_COUNT + 4]{};
     double cg_stats[4]{};
+    bool spmv_timing = false;
+    std::vector<cudaEvent_t> spmv_ev;  // pairs
+    size_t spmv_ev_used = 0;
+    double spmv_ms = 0.0, spmv_count = 0.0;
     double *flush_buf = nullptr;
     int64_t flush_n = 0;
 };
@@ -238,6 +243,34 @@ struct PhaseTimer {
     }
 };
 
+// resolve the recorded SpMV event pairs into (count, ms)
+void drain_spmv_events(wave_ctx *ctx) {
+    if (!ctx->spmv_ev_used) return;
+    cudaEventSynchronize(ctx->spmv_ev[ctx->spmv_ev_used - 1]);
+    for (size_t k = 0; k + 1 < ctx->spmv_ev_used; k += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->spmv_ev[k], ctx->spmv_ev[k + 1]) == cudaSuccess) {
+            ctx->spmv_ms += ms;
+            ctx->spmv_count += 1;
+        }
+    }
+    ctx->spmv_ev_used = 0;
+}
+struct SpmvBracket {
+    wave_ctx *ctx;
+    bool on;
+    explicit SpmvBracket(wave_ctx *c) : ctx(c), on(c->spmv_timing) {
+        if (!on) return;
+        if (ctx->spmv_ev_used + 2 > ctx->spmv_ev.size()) drain_spmv_events(ctx);
+        cudaEventRecord(ctx->spmv_ev[ctx->spmv_ev_used], ctx->stream);
+    }
+    ~SpmvBracket() {
+        if (!on) return;
+        cudaEventRecord(ctx->spmv_ev[ctx->spmv_ev_used + 1], ctx->stream);
+        ctx->spmv_ev_used += 2;
+    }
+};
+
 SpmvArgs spmv_base(wave_ctx *ctx) {
     SpmvArgs a{};
     a.rowptr = ctx->rowptr;
@@ -282,7 +315,10 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
             a.dotv = ctx->d + L.own_off;
             a.result = &ctx->S->dAd;
             a.skip_flag = &ctx->S->status;
-            launch_spmv(l, a, ctx->maxrow);
+            {
+                SpmvBracket br(ctx);
+                launch_spmv(l, a, ctx->maxrow);
+            }
             RET(allreduce(ctx, &ctx->S->dAd, 1));
             launch_cg_update(l, L.nown, ctx->S, x + L.own_off, ctx->g, ctx->h, ctx->d + L.own_off, dinv,
                              ctx->partials, ctx->counter);
@@ -551,9 +587,14 @@ int wave_create(const wave_config *cfg, wave_ctx **out) {
         ctx->err = "cudaSetDevice failed";
         return bail(WAVE_ERR_CUDA);
     }
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
-        ctx->err = "cudaStreamCreate failed";
-        return bail(WAVE_ERR_CUDA);
+    if (cfg->stream) {
+        ctx->stream = (cudaStream_t)cfg->stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            ctx->err = "cudaStreamCreate failed";
+            return bail(WAVE_ERR_CUDA);
+        }
+        ctx->own_stream = true;
     }
     ctx->launcher = Launcher{ctx->stream, &ctx->launches};
     for (auto &e : ctx->ev)
@@ -600,7 +641,9 @@ void wave_destroy(wave_ctx *ctx) {
     if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (auto &e : ctx->spmv_ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
@@ -1110,6 +1153,20 @@ int wave_timers(wave_ctx *ctx, double out_ms[6], int reset) {
         out_ms[k] = ctx->phase_ms[k];
         if (reset) ctx->phase_ms[k] = 0.0;
     }
+    return WAVE_OK;
+}
+int wave_spmv_timing(wave_ctx *ctx, int on, double *launches, double *ms_total) {
+    if (!ctx) return WAVE_ERR_ARG;
+    drain_spmv_events(ctx);
+    if (launches) *launches = ctx->spmv_count;
+    if (ms_total) *ms_total = ctx->spmv_ms;
+    if (on && ctx->spmv_ev.empty()) {
+        ctx->spmv_ev.resize(2048, nullptr);
+        for (auto &e : ctx->spmv_ev) CK(cudaEventCreate(&e));
+    }
+    ctx->spmv_timing = on != 0;
+    ctx->spmv_ms = 0.0;
+    ctx->spmv_count = 0.0;
     return WAVE_OK;
 }
 int wave_cg_stats(wave_ctx *ctx, double out[4], int reset) {

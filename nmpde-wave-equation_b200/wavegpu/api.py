@@ -25,7 +25,7 @@ class WaveConfig(C.Structure):
                 ("dt", C.c_double), ("theta", C.c_double), ("beta", C.c_double), ("gamma", C.c_double),
                 ("cg_maxit", C.c_int32), ("cg_tol", C.c_double), ("cg_reduce", C.c_double),
                 ("precond", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("device", C.c_int32),
-                ("nccl_unique_id", C.c_void_p), ("flags", C.c_uint32)]
+                ("nccl_unique_id", C.c_void_p), ("flags", C.c_uint32), ("stream", C.c_void_p)]
 
 
 class WavePartition(C.Structure):
@@ -92,6 +92,7 @@ def lib():
         L.wave_timers_enable.argtypes = [vp, C.c_int]
         L.wave_timers.argtypes = [vp, dp, C.c_int]
         L.wave_cg_stats.argtypes = [vp, dp, C.c_int]
+        L.wave_spmv_timing.argtypes = [vp, C.c_int, dp, dp]
         L.wave_partition_plan.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.POINTER(WavePartition)]
         _lib = L
@@ -153,7 +154,7 @@ class WaveSolver:
     """Thin handle over wave_ctx, constructed from a reference-schema parameter dictionary."""
 
     def __init__(self, params, scheme, rank=0, nranks=1, nccl_id: bytes | None = None, device=-1, cg=None,
-                 flags=0):
+                 flags=0, stream=None):
         L = lib()
         self.L = L
         cfg = WaveConfig()
@@ -172,6 +173,7 @@ class WaveSolver:
             cfg.cg_reduce = float(cg.get("reduce", 1e-6))
             cfg.precond = int(cg.get("precond", 0))
         cfg.rank, cfg.nranks, cfg.device, cfg.flags = rank, nranks, device, flags
+        cfg.stream = stream
         self._idbuf = C.create_string_buffer(nccl_id, 128) if nccl_id else None
         cfg.nccl_unique_id = C.cast(self._idbuf, C.c_void_p) if self._idbuf else None
         self.scheme = scheme
@@ -337,6 +339,12 @@ class WaveSolver:
         out = (C.c_double * 6)()
         self._ck(self.L.wave_timers(self.h, out, int(reset)))
         return dict(zip(("rhs", "bc", "cg", "update", "energy", "other"), out))
+
+    def spmv_timing(self, on):
+        """Switch live SpMV bracketing on/off; returns (launches, ms_total) accumulated so far."""
+        cnt, ms = C.c_double(), C.c_double()
+        self._ck(self.L.wave_spmv_timing(self.h, int(on), C.byref(cnt), C.byref(ms)))
+        return cnt.value, ms.value
 
     def cg_stats(self, reset=False):
         out = (C.c_double * 4)()
