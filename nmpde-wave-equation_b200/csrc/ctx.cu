@@ -92,11 +92,14 @@ struct wave_ctx {
     bool forcing_active = false;
     Quadrature q_asm{}, q_err{};
 
-    // CSR (owned rows, local column indices)
+    // SELL-32-sigma pattern shared by all matrices (owned rows, local column indices) + CSR row pointer
     uint32_t *rowptr = nullptr;
-    int32_t *col = nullptr;
-    int64_t nnz = 0;
-    int maxrow = 0;
+    uint32_t *slice_ptr = nullptr;
+    int32_t *col = nullptr, *row_of = nullptr, *slot_of = nullptr;
+    int nslices = 0;
+    int64_t nnz = 0;      // entries of the pattern (CSR)
+    int64_t nnz_pad = 0;  // stored entries including padding
+    Sell A{};
     double *M = nullptr, *K = nullptr, *S1 = nullptr, *S2 = nullptr;
     double *dinv1 = nullptr, *dinv2 = nullptr;
     double *d0 = nullptr;  // [2]
@@ -273,9 +276,7 @@ struct SpmvBracket {
 
 SpmvArgs spmv_base(wave_ctx *ctx) {
     SpmvArgs a{};
-    a.rowptr = ctx->rowptr;
-    a.col = ctx->col;
-    a.nrows = ctx->L.nown;
+    a.A = ctx->A;
     a.partials = ctx->partials;
     a.counter = ctx->counter;
     return a;
@@ -298,7 +299,7 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
         a.dinv = dinv; a.h_out = ctx->h; a.d_out = ctx->d + L.own_off;
         a.dot_mode = 2;
         a.result = &ctx->S->gg;
-        launch_spmv(l, a, ctx->maxrow);
+        launch_spmv(l, a);
     }
     RET(allreduce(ctx, &ctx->S->gg, 2));
     launch_cg_start(l, ctx->S);
@@ -317,7 +318,7 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
             a.skip_flag = &ctx->S->status;
             {
                 SpmvBracket br(ctx);
-                launch_spmv(l, a, ctx->maxrow);
+                launch_spmv(l, a);
             }
             RET(allreduce(ctx, &ctx->S->dAd, 1));
             launch_cg_update(l, L.nown, ctx->S, x + L.own_off, ctx->g, ctx->h, ctx->d + L.own_off, dinv,
@@ -350,10 +351,10 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
 // scheme matrix: out = bc(M + s K); also d0 and the Jacobi diagonal
 int build_system_matrix(wave_ctx *ctx, double s, double *out, double *dinv, double *d0) {
     const Launcher &l = ctx->launcher;
-    launch_axpy_vals(l, ctx->nnz, ctx->M, ctx->K, s, out);
-    launch_find_d0(l, ctx->L, ctx->rowptr, ctx->col, out, d0);
-    launch_bc_rows(l, ctx->L, ctx->nb, ctx->brow, ctx->rowptr, ctx->col, out, d0);
-    launch_dinv(l, ctx->L, ctx->rowptr, ctx->col, out, ctx->cfg.precond == WAVE_PRECOND_NONE, dinv);
+    launch_axpy_vals(l, ctx->nnz_pad, ctx->M, ctx->K, s, out);
+    launch_find_d0(l, ctx->L, ctx->A, out, d0);
+    launch_bc_rows(l, ctx->L, ctx->nb, ctx->brow, ctx->A, out, d0);
+    launch_dinv(l, ctx->L, ctx->A, out, ctx->cfg.precond == WAVE_PRECOND_NONE, dinv);
     return WAVE_OK;
 }
 
@@ -400,7 +401,7 @@ int newmark_step(wave_ctx *ctx, double t, int32_t iters[2], double norms[2]) {
         a.t[0] = {ctx->K, ctx->u, nullptr, 1.0, 0.0, -1.0};
         if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = 1.0; }
         a.y = ctx->rhs;
-        launch_spmv(l, a, ctx->maxrow);
+        launch_spmv(l, a);
     }
     {
         PhaseTimer pt(ctx, PH_BC);
@@ -439,7 +440,7 @@ int theta_step(wave_ctx *ctx, double t, int32_t iters[2], double norms[2]) {
         a.t[1] = {ctx->K, ctx->u, nullptr, 1.0, 0.0, -dt * dt * th * (1 - th)};
         if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = th * dt * dt; }
         a.y = ctx->rhs;
-        launch_spmv(l, a, ctx->maxrow);
+        launch_spmv(l, a);
         launch_copy(l, L.nloc, ctx->u, ctx->unew);
     }
     {
@@ -460,7 +461,7 @@ int theta_step(wave_ctx *ctx, double t, int32_t iters[2], double norms[2]) {
         a.t[1] = {ctx->K, ctx->u, ctx->unew, 1.0 - th, th, -dt};
         if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = dt; }
         a.y = ctx->rhs;
-        launch_spmv(l, a, ctx->maxrow);
+        launch_spmv(l, a);
     }
     {
         PhaseTimer pt(ctx, PH_BC);
@@ -630,7 +631,7 @@ int wave_create(const wave_config *cfg, wave_ctx **out) {
 void wave_destroy(wave_ctx *ctx) {
     if (!ctx) return;
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void *ptrs[] = {ctx->dprog, ctx->rowptr, ctx->col, ctx->M, ctx->K, ctx->S1, ctx->S2, ctx->dinv1, ctx->dinv2,
+    void *ptrs[] = {ctx->dprog, ctx->rowptr, ctx->slice_ptr, ctx->row_of, ctx->slot_of, ctx->col, ctx->M, ctx->K, ctx->S1, ctx->S2, ctx->dinv1, ctx->dinv2,
                     ctx->d0, ctx->u, ctx->v, ctx->a, ctx->unew, ctx->d, ctx->rhs, ctx->fvec, ctx->g, ctx->h,
                     ctx->scratch, ctx->brow, ctx->bx, ctx->by, ctx->partials, ctx->counter, ctx->S, ctx->res,
                     ctx->flush_buf};
@@ -685,33 +686,48 @@ int wave_setup(wave_ctx *ctx) {
     ctx->forcing_active = !(is_constant(ctx->hprog[WAVE_EXPR_F], &fconst) && fconst == 0.0) ||
                           (ctx->cfg.flags & WAVE_FLAG_FORCING_EVERY_STEP);
 
-    // ---- sparsity: row lengths -> exclusive scan -> columns -------------------------------------
-    uint32_t *rowlen = nullptr;
+    // ---- sparsity: row lengths -> CSR row pointer; window sort -> SELL slices -> columns ----------
+    const int nslots = ((L.nown + kWindow - 1) / kWindow) * kWindow;
+    ctx->nslices = nslots / kSlice;
+    uint32_t *rowlen = nullptr, *slice_cnt = nullptr;
     RET(dev_alloc(ctx, &rowlen, (size_t)L.nown + 1));
+    RET(dev_alloc(ctx, &slice_cnt, (size_t)ctx->nslices + 1));
     RET(dev_alloc(ctx, &ctx->rowptr, (size_t)L.nown + 1));
+    RET(dev_alloc(ctx, &ctx->slice_ptr, (size_t)ctx->nslices + 1));
+    RET(dev_alloc(ctx, &ctx->row_of, (size_t)nslots, false));
+    RET(dev_alloc(ctx, &ctx->slot_of, (size_t)L.nown, false));
     launch_row_lengths(l, L, rowlen);
+    launch_window_sort(l, L.nown, nslots, rowlen, ctx->row_of, ctx->slot_of);
+    launch_slice_sizes(l, ctx->nslices, ctx->row_of, rowlen, slice_cnt);
     {
         void *tmp = nullptr;
-        size_t bytes = 0;
+        size_t bytes = 0, bytes2 = 0;
         CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, rowlen, ctx->rowptr, L.nown + 1, ctx->stream));
-        CK(cudaMalloc(&tmp, bytes));
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes2, slice_cnt, ctx->slice_ptr, ctx->nslices + 1, ctx->stream));
+        CK(cudaMalloc(&tmp, std::max(bytes, bytes2)));
         CK(cub::DeviceScan::ExclusiveSum(tmp, bytes, rowlen, ctx->rowptr, L.nown + 1, ctx->stream));
-        ++ctx->launches;
-        uint32_t total = 0;
+        CK(cub::DeviceScan::ExclusiveSum(tmp, bytes2, slice_cnt, ctx->slice_ptr, ctx->nslices + 1, ctx->stream));
+        ctx->launches += 2;
+        uint32_t total = 0, total_pad = 0;
         CK(cudaMemcpyAsync(&total, ctx->rowptr + L.nown, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(&total_pad, ctx->slice_ptr + ctx->nslices, sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                           ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaFree(tmp));
         ctx->nnz = total;
+        ctx->nnz_pad = total_pad;
     }
     CK(cudaFree(rowlen));
-    ctx->maxrow = L.mesh.r == 1 ? 7 : 19;
-    RET(dev_alloc(ctx, &ctx->col, (size_t)ctx->nnz, false));
-    launch_fill_cols(l, L, ctx->rowptr, ctx->col);
+    CK(cudaFree(slice_cnt));
+    RET(dev_alloc(ctx, &ctx->col, (size_t)ctx->nnz_pad, false));
+    ctx->A = Sell{ctx->slice_ptr, ctx->col, ctx->row_of, ctx->slot_of, ctx->rowptr, ctx->nslices, L.nown};
+    launch_fill_int(l, ctx->nnz_pad, L.own_off, ctx->col);  // padding entries: a valid column, value 0
+    launch_fill_cols(l, L, ctx->A, ctx->col);
 
     // ---- M, K ---------------------------------------------------------------------------------------
-    RET(dev_alloc(ctx, &ctx->M, (size_t)ctx->nnz));
-    RET(dev_alloc(ctx, &ctx->K, (size_t)ctx->nnz));
-    launch_assemble(l, L, ctx->dprog + WAVE_EXPR_C, &ctx->q_asm, ctx->rowptr, ctx->col, ctx->M, ctx->K);
+    RET(dev_alloc(ctx, &ctx->M, (size_t)ctx->nnz_pad));
+    RET(dev_alloc(ctx, &ctx->K, (size_t)ctx->nnz_pad));
+    launch_assemble(l, L, ctx->dprog + WAVE_EXPR_C, &ctx->q_asm, ctx->A, ctx->M, ctx->K);
 
     // ---- boundary list (closed form, host) --------------------------------------------------------
     {
@@ -771,7 +787,7 @@ int wave_setup(wave_ctx *ctx) {
     RET(dev_alloc(ctx, &ctx->h, (size_t)L.nown));
     {
         const int64_t cells = 2LL * (L.jq1 - L.jq0) * L.mesh.nx;
-        const int64_t blocks = std::max<int64_t>({(cells + 127) / 128, (L.nown + kRowsPerBlock - 1) / kRowsPerBlock,
+        const int64_t blocks = std::max<int64_t>({(cells + 127) / 128, (int64_t)(nslots / kSlice + 7) / 8,
                                                   (int64_t)reduction_blocks(L.nown)}) + 1;
         RET(dev_alloc(ctx, &ctx->partials, (size_t)blocks * 4));
     }
@@ -784,7 +800,7 @@ int wave_setup(wave_ctx *ctx) {
     RET(upload_cg_control(ctx));
 
     // ---- scheme matrices (src/WaveNewmark.cpp:110-112, :372-374; src/WaveTheta.cpp:110-115) -----
-    RET(dev_alloc(ctx, &ctx->S1, (size_t)ctx->nnz, false));
+    RET(dev_alloc(ctx, &ctx->S1, (size_t)ctx->nnz_pad, false));
     RET(dev_alloc(ctx, &ctx->dinv1, (size_t)L.nown, false));
     const double dt = ctx->cfg.dt;
     if (ctx->cfg.scheme == WAVE_SCHEME_NEWMARK) {
@@ -794,7 +810,7 @@ int wave_setup(wave_ctx *ctx) {
     } else {
         const double th = ctx->cfg.theta;
         RET(build_system_matrix(ctx, (th * dt) * (th * dt), ctx->S1, ctx->dinv1, ctx->d0));
-        RET(dev_alloc(ctx, &ctx->S2, (size_t)ctx->nnz, false));
+        RET(dev_alloc(ctx, &ctx->S2, (size_t)ctx->nnz_pad, false));
         RET(dev_alloc(ctx, &ctx->dinv2, (size_t)L.nown, false));
         RET(build_system_matrix(ctx, 0.0, ctx->S2, ctx->dinv2, ctx->d0 + 1));
     }
@@ -820,7 +836,7 @@ int wave_init(wave_ctx *ctx) {
         a.t[0] = {ctx->K, ctx->u, nullptr, 1.0, 0.0, -1.0};
         if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = 1.0; }
         a.y = ctx->rhs;
-        launch_spmv(l, a, ctx->maxrow);
+        launch_spmv(l, a);
         launch_fill(l, L.nloc, 0.0, ctx->a);
         launch_bc_values(l, BC_SECOND_DIFF, ctx->nb, ctx->brow, ctx->bx, ctx->by, ctx->dprog + WAVE_EXPR_G, dt, dt, 0.0,
                          nullptr, ctx->a + L.own_off, ctx->rhs, ctx->d0);
@@ -935,11 +951,11 @@ int wave_energy(wave_ctx *ctx, double *out) {
     SpmvArgs a = spmv_base(ctx);
     a.t[0] = {ctx->K, ctx->u, nullptr, 1.0, 0.0, 1.0};
     a.dot_mode = 1; a.dotv = ctx->u + L.own_off; a.result = ctx->res + 2;
-    launch_spmv(ctx->launcher, a, ctx->maxrow);
+    launch_spmv(ctx->launcher, a);
     SpmvArgs b = spmv_base(ctx);
     b.t[0] = {ctx->M, ctx->v, nullptr, 1.0, 0.0, 1.0};
     b.dot_mode = 1; b.dotv = ctx->v + L.own_off; b.result = ctx->res + 3;
-    launch_spmv(ctx->launcher, b, ctx->maxrow);
+    launch_spmv(ctx->launcher, b);
     RET(allreduce(ctx, ctx->res + 2, 2));
     CK(cudaMemcpyAsync(ctx->hres + 2, ctx->res + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1002,11 +1018,18 @@ int wave_get_csr(wave_ctx *ctx, int which, int64_t *rowptr, int32_t *col, double
     CK(cudaMemcpy(rp.data(), ctx->rowptr, sizeof(uint32_t) * rp.size(), cudaMemcpyDeviceToHost));
     if (rowptr)
         for (size_t i = 0; i < rp.size(); ++i) rowptr[i] = rp[i];
-    if (col) {
-        CK(cudaMemcpy(col, ctx->col, sizeof(int32_t) * ctx->nnz, cudaMemcpyDeviceToHost));
-        for (int64_t e = 0; e < ctx->nnz; ++e) col[e] = (int32_t)(col[e] + L.col0);
+    if (col || val) {
+        double *dval = nullptr;
+        int32_t *dcol = nullptr;
+        if (val) RET(dev_alloc(ctx, &dval, (size_t)ctx->nnz, false));
+        if (col) RET(dev_alloc(ctx, &dcol, (size_t)ctx->nnz, false));
+        launch_export_csr(ctx->launcher, L, ctx->A, src ? src : ctx->M, dval, dcol);
+        if (val) CK(cudaMemcpyAsync(val, dval, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost, ctx->stream));
+        if (col) CK(cudaMemcpyAsync(col, dcol, sizeof(int32_t) * ctx->nnz, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (dval) cudaFree(dval);
+        if (dcol) cudaFree(dcol);
     }
-    if (val) CK(cudaMemcpy(val, src, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost));
     return WAVE_OK;
 }
 
@@ -1042,7 +1065,7 @@ int wave_spmv(wave_ctx *ctx, int which, const double *x, double *y, size_t n) {
     SpmvArgs a = spmv_base(ctx);
     a.t[0] = {val, ctx->d, nullptr, 1.0, 0.0, 1.0};
     a.y = ctx->h;
-    launch_spmv(ctx->launcher, a, ctx->maxrow);
+    launch_spmv(ctx->launcher, a);
     CK(cudaMemcpyAsync(y, ctx->h, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     return sync_check(ctx);
 }
@@ -1083,14 +1106,14 @@ int wave_bench_spmv(wave_ctx *ctx, int which, int reps, int flush_l2, double *ms
     a.t[0] = {val, ctx->u, nullptr, 1.0, 0.0, 1.0};
     a.y = ctx->h;
     cudaEvent_t e0 = ctx->ev[2 * PH_COUNT + 2], e1 = ctx->ev[2 * PH_COUNT + 3];
-    for (int w = 0; w < 3; ++w) launch_spmv(ctx->launcher, a, ctx->maxrow);
+    for (int w = 0; w < 3; ++w) launch_spmv(ctx->launcher, a);
     CK(cudaStreamSynchronize(ctx->stream));
     double total = 0.0;
     if (flush_l2) {
         for (int r = 0; r < reps; ++r) {
             launch_flush_l2(ctx->launcher, ctx->flush_buf, ctx->flush_n);
             CK(cudaEventRecord(e0, ctx->stream));
-            launch_spmv(ctx->launcher, a, ctx->maxrow);
+            launch_spmv(ctx->launcher, a);
             CK(cudaEventRecord(e1, ctx->stream));
             CK(cudaEventSynchronize(e1));
             float ms = 0;
@@ -1099,7 +1122,7 @@ int wave_bench_spmv(wave_ctx *ctx, int which, int reps, int flush_l2, double *ms
         }
     } else {
         CK(cudaEventRecord(e0, ctx->stream));
-        for (int r = 0; r < reps; ++r) launch_spmv(ctx->launcher, a, ctx->maxrow);
+        for (int r = 0; r < reps; ++r) launch_spmv(ctx->launcher, a);
         CK(cudaEventRecord(e1, ctx->stream));
         CK(cudaEventSynchronize(e1));
         float ms = 0;
@@ -1123,7 +1146,7 @@ int wave_bench_cg_iter(wave_ctx *ctx, int which, int reps, double *ms_avg, doubl
     SpmvArgs a = spmv_base(ctx);
     a.t[0] = {val, ctx->d, nullptr, 1.0, 0.0, 1.0};
     a.y = ctx->rhs;
-    launch_spmv(ctx->launcher, a, ctx->maxrow);
+    launch_spmv(ctx->launcher, a);
     double ms_total = 0.0, its_total = 0.0;
     for (int r = 0; r < reps; ++r) {
         launch_fill(ctx->launcher, L.nloc, 0.0, ctx->unew);

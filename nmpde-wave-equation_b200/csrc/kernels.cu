@@ -5,6 +5,8 @@
 
 #include <cstdio>
 
+#include <cub/block/block_radix_sort.cuh>
+
 namespace wv {
 
 namespace {
@@ -139,7 +141,48 @@ __global__ void k_row_lengths(Layout L, uint32_t *rowlen) {
     rowlen[dof - L.row0] = (uint32_t)build_row(L.mesh, i, j, kind, cols);
 }
 
-__global__ void k_fill_cols(Layout L, const uint32_t *rowptr, int32_t *col) {
+// ---- SELL-32-sigma construction --------------------------------------------------------------------
+// One block per window of kWindow rows: stable sort by descending row length (radix sort of the key
+// (maxlen - len) << 16 | local index); slot = position after the sort.
+__global__ void __launch_bounds__(kWindow) k_window_sort(int nown, const uint32_t *rowlen, int32_t *row_of,
+                                                         int32_t *slot_of) {
+    using Sort = cub::BlockRadixSort<unsigned, kWindow, 1>;
+    __shared__ typename Sort::TempStorage tmp;
+    const int wbase = blockIdx.x * kWindow;
+    const int row = wbase + threadIdx.x;
+    const unsigned len = row < nown ? rowlen[row] : 0u;
+    unsigned key[1] = {((unsigned)(kMaxRow - len) << 16) | (unsigned)threadIdx.x};
+    Sort(tmp).Sort(key, 0, 24);
+    const int src = wbase + (int)(key[0] & 0xffffu);
+    const int slot = wbase + threadIdx.x;
+    if (src < nown) {
+        row_of[slot] = src;
+        slot_of[src] = slot;
+    } else
+        row_of[slot] = -1;
+}
+// padded size of a slice = 32 * (longest row in it); one warp per slice
+__global__ void k_slice_sizes(int nslices, const int32_t *row_of, const uint32_t *rowlen, uint32_t *slice_cnt) {
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (s >= nslices) return;
+    const int r = row_of[s * kSlice + lane];
+    unsigned len = r >= 0 ? rowlen[r] : 0u;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) len = max(len, __shfl_xor_sync(kFull, len, off));
+    if (lane == 0) slice_cnt[s] = len * kSlice;
+}
+__global__ void k_fill_int(int64_t n, int32_t value, int32_t *dst) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = value;
+}
+
+__device__ __forceinline__ uint32_t sell_row_base(const Sell &A, int row) {
+    const int slot = A.slot_of[row];
+    return A.slice_ptr[slot >> 5] + (uint32_t)(slot & 31);
+}
+__device__ __forceinline__ uint32_t sell_row_len(const Sell &A, int row) { return A.rowptr[row + 1] - A.rowptr[row]; }
+
+__global__ void k_fill_cols(Layout L, Sell A, int32_t *col) {
     const SlotRange s = owned_slots(L);
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= slot_count(L, s)) return;
@@ -149,28 +192,39 @@ __global__ void k_fill_cols(Layout L, const uint32_t *rowptr, int32_t *col) {
     if (dof < L.row0 || dof >= L.row0 + L.nown) return;
     int64_t cols[kMaxRow];
     const int n = build_row(L.mesh, i, j, kind, cols);
-    const uint32_t base = rowptr[dof - L.row0];
-    for (int k = 0; k < n; ++k) col[base + k] = (int32_t)(cols[k] - L.col0);
+    const uint32_t base = sell_row_base(A, (int)(dof - L.row0));
+    for (int k = 0; k < n; ++k) col[base + kSlice * k] = (int32_t)(cols[k] - L.col0);
 }
 
-__device__ __forceinline__ uint32_t find_col(const int32_t *col, uint32_t lo, uint32_t hi, int32_t c) {
-    // rows are short and sorted: binary search over [lo, hi)
+// position of (row, local column c) in the padded arrays; the row's entries are sorted ascending
+__device__ __forceinline__ uint32_t find_col(const Sell &A, int row, int32_t c) {
+    const uint32_t base = sell_row_base(A, row);
+    uint32_t lo = 0, hi = sell_row_len(A, row);
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        const int32_t v = col[mid];
-        if (v == c) return mid;
+        const int32_t v = A.col[base + kSlice * mid];
+        if (v == c) return base + kSlice * mid;
         if (v < c) lo = mid + 1; else hi = mid;
     }
     return 0xffffffffu;
+}
+
+__global__ void k_export_csr(Layout L, Sell A, const double *val, double *csr_val, int32_t *csr_col) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= L.nown) return;
+    const uint32_t base = sell_row_base(A, row), len = sell_row_len(A, row), o = A.rowptr[row];
+    for (uint32_t k = 0; k < len; ++k) {
+        if (csr_val) csr_val[o + k] = val[base + kSlice * k];
+        if (csr_col) csr_col[o + k] = (int32_t)(A.col[base + kSlice * k] + L.col0);
+    }
 }
 
 // ---- K1: assemble_matrices (src/WaveNewmark.cpp:56-108 == src/WaveTheta.cpp:56-108) ---------------
 // One thread per cell: quadrature loop in the reference's order (q outer, i, j inner), c evaluated
 // at the quadrature point at parser time 0, then scatter-add of the owned rows into the CSR values.
 template <int R>
-__global__ void __launch_bounds__(128) k_assemble(Layout L, const Program *cprog, Quadrature Q,
-                                                  const uint32_t *rowptr, const int32_t *col, double *M,
-                                                  double *K) {
+__global__ void __launch_bounds__(128) k_assemble(Layout L, const Program *cprog, Quadrature Q, Sell A,
+                                                  double *M, double *K) {
     constexpr int DPC = R == 1 ? 3 : 6;
     const int jtop = L.jq1 < L.mesh.ny ? L.jq1 : L.mesh.ny - 1;  // one quad row above the owned ones
     const int64_t c_begin = 2LL * L.jq0 * L.mesh.nx, c_end = 2LL * (jtop + 1) * L.mesh.nx;
@@ -209,10 +263,9 @@ __global__ void __launch_bounds__(128) k_assemble(Layout L, const Program *cprog
     for (int a = 0; a < DPC; ++a) {
         const int64_t row = d[a] - L.row0;
         if (row < 0 || row >= L.nown) continue;
-        const uint32_t lo = rowptr[row], hi = rowptr[row + 1];
 #pragma unroll
         for (int b = 0; b < DPC; ++b) {
-            const uint32_t pos = find_col(col, lo, hi, (int32_t)(d[b] - L.col0));
+            const uint32_t pos = find_col(A, (int)row, (int32_t)(d[b] - L.col0));
             atomicAdd(&M[pos], Me[a][b]);
             atomicAdd(&K[pos], Ke[a][b]);
         }
@@ -230,31 +283,30 @@ __global__ void __launch_bounds__(kThreads) k_axpy_vals(int64_t nnz, const doubl
 
 // [deal.II] MatrixTools::apply_boundary_values (Trilinos overload, Release build):
 // d0 = |first non-zero diagonal entry| of the rank's rows; each boundary row becomes d0 * e_i.
-__global__ void k_find_d0(Layout L, const uint32_t *rowptr, const int32_t *col, const double *val, double *d0) {
+__global__ void k_find_d0(Layout L, Sell A, const double *val, double *d0) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     double r = 0.0;
     for (int i = 0; i < L.nown; ++i) {
-        const uint32_t pos = find_col(col, rowptr[i], rowptr[i + 1], i + L.own_off);
+        const uint32_t pos = find_col(A, i, i + L.own_off);
         if (pos != 0xffffffffu && val[pos] != 0.0) { r = fabs(val[pos]); break; }
     }
     *d0 = r;
 }
-__global__ void k_bc_rows(Layout L, int nb, const int32_t *brow, const uint32_t *rowptr, const int32_t *col,
-                          double *val, const double *d0) {
+__global__ void k_bc_rows(Layout L, int nb, const int32_t *brow, Sell A, double *val, const double *d0) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     const int row = brow[b];
     const double diag = *d0;
-    for (uint32_t e = rowptr[row]; e < rowptr[row + 1]; ++e) val[e] = (col[e] == row + L.own_off) ? diag : 0.0;
+    const uint32_t base = sell_row_base(A, row), len = sell_row_len(A, row);
+    for (uint32_t k = 0; k < len; ++k)
+        val[base + kSlice * k] = (A.col[base + kSlice * k] == row + L.own_off) ? diag : 0.0;
 }
 // Jacobi: 1 / diag(A) (stand-in for PreconditionAMG / PreconditionSSOR per the north star)
-__global__ void k_dinv(Layout L, const uint32_t *rowptr, const int32_t *col, const double *val, int identity,
-                       double *dinv) {
+__global__ void k_dinv(Layout L, Sell A, const double *val, int identity, double *dinv) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= L.nown) return;
     if (identity) { dinv[i] = 1.0; return; }
-    const uint32_t pos = find_col(col, rowptr[i], rowptr[i + 1], i + L.own_off);
-    dinv[i] = 1.0 / val[pos];
+    dinv[i] = 1.0 / val[find_col(A, i, i + L.own_off)];
 }
 
 // ---- K9: VectorTools::interpolate at DoF support points (src/WaveNewmark.cpp:292-293) --------------
@@ -333,48 +385,57 @@ __global__ void k_bc_values(int mode, int nb, const int32_t *brow, const double 
     rhs[row] = val * (*d0);
 }
 
-// ---- K3: CSR-stream SpMV (TrilinosWrappers::SparseMatrix::vmult) ------------------------------------
-// A block owns kRowsPerBlock consecutive rows.  Phase 1 streams the block's contiguous (val, col)
-// range with fully coalesced loads, gathers x through L1/L2 (the matrix band keeps the gathered
-// window cache resident) and parks the products in shared memory.  Phase 2: one thread per row adds
-// its products in column order -- the summation order of a serial CSR loop, hence bitwise equal to
-// it for a single term.  Epilogues: addends, CG residual start (h = D^-1 g, d = -h), fused dots.
+// ---- K3: SELL-32 SpMV (TrilinosWrappers::SparseMatrix::vmult) ---------------------------------------
+// One warp per slice, one row per lane.  Every warp load of val / col is one contiguous segment; the
+// loop is unrolled so 4 x (col, val) loads are in flight per lane before the dependent x gathers.
+// A row is accumulated in ascending column order with separate multiply and add roundings, i.e. the
+// arithmetic of a serial CSR loop (bitwise equal to it for a single term).  Epilogues: addends, the
+// CG residual start (h = D^-1 g, d = -h) and fused dot products (deterministic grid reduction).
+template <int NT, bool TWOX>
+__device__ __forceinline__ double spmv_entry(const SpmvArgs &a, uint32_t p, int c) {
+    double prod = 0.0;
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+        double xv = __dmul_rn(a.t[k].ca, a.t[k].xa[c]);
+        if (TWOX && a.t[k].xb) xv = __dadd_rn(xv, __dmul_rn(a.t[k].cb, a.t[k].xb[c]));
+        const double term = __dmul_rn(a.t[k].coef, __dmul_rn(__ldg(&a.t[k].val[p]), xv));
+        prod = k == 0 ? term : __dadd_rn(prod, term);
+    }
+    return prod;
+}
 template <int NT, bool TWOX>
 __global__ void __launch_bounds__(kThreads) k_spmv(SpmvArgs a) {
-    extern __shared__ double prod[];
     if (a.skip_flag && *a.skip_flag != 0) return;
-    const int r0 = blockIdx.x * kRowsPerBlock;
-    const int r1 = min(r0 + kRowsPerBlock, a.nrows);
-    const uint32_t e0 = a.rowptr[r0], e1 = a.rowptr[r1];
-    for (uint32_t e = e0 + threadIdx.x; e < e1; e += kThreads) {
-        const int c = __ldg(&a.col[e]);
-        double p = 0.0;
-#pragma unroll
-        for (int k = 0; k < NT; ++k) {
-            double xv = a.t[k].ca * a.t[k].xa[c];
-            if (TWOX && a.t[k].xb) xv += a.t[k].cb * a.t[k].xb[c];
-            p += a.t[k].coef * (__ldg(&a.t[k].val[e]) * xv);
-        }
-        prod[e - e0] = p;
-    }
-    __syncthreads();
+    const int slice = (blockIdx.x * kThreads + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     double dots[2] = {0.0, 0.0};
-    const int r = r0 + threadIdx.x;
-    if (r < r1) {
-        const uint32_t b = a.rowptr[r] - e0, e = a.rowptr[r + 1] - e0;
+    if (slice < a.A.nslices) {
+        const uint32_t b = a.A.slice_ptr[slice] + lane, e = a.A.slice_ptr[slice + 1];
+        const int r = a.A.row_of[slice * kSlice + lane];
         double s = 0.0;
-        for (uint32_t k = b; k < e; ++k) s += prod[k];
-        if (a.add0) s += a.addc0 * a.add0[r];
-        if (a.add1) s += a.addc1 * a.add1[r];
-        if (a.y) a.y[r] = s;
-        double hv = 0.0;
-        if (a.h_out) {
-            hv = a.dinv[r] * s;
-            a.h_out[r] = hv;
-            a.d_out[r] = -hv;
+        uint32_t p = b;
+        for (; p + 3 * kSlice < e; p += 4 * kSlice) {
+            const int c0 = __ldg(&a.A.col[p]), c1 = __ldg(&a.A.col[p + kSlice]);
+            const int c2 = __ldg(&a.A.col[p + 2 * kSlice]), c3 = __ldg(&a.A.col[p + 3 * kSlice]);
+            const double p0 = spmv_entry<NT, TWOX>(a, p, c0);
+            const double p1 = spmv_entry<NT, TWOX>(a, p + kSlice, c1);
+            const double p2 = spmv_entry<NT, TWOX>(a, p + 2 * kSlice, c2);
+            const double p3 = spmv_entry<NT, TWOX>(a, p + 3 * kSlice, c3);
+            s = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(s, p0), p1), p2), p3);
         }
-        if (a.dot_mode == 1) dots[0] = s * a.dotv[r];
-        else if (a.dot_mode == 2) { dots[0] = s * s; dots[1] = s * hv; }
+        for (; p < e; p += kSlice) s = __dadd_rn(s, spmv_entry<NT, TWOX>(a, p, __ldg(&a.A.col[p])));
+        if (r >= 0) {
+            if (a.add0) s += a.addc0 * a.add0[r];
+            if (a.add1) s += a.addc1 * a.add1[r];
+            if (a.y) a.y[r] = s;
+            double hv = 0.0;
+            if (a.h_out) {
+                hv = a.dinv[r] * s;
+                a.h_out[r] = hv;
+                a.d_out[r] = -hv;
+            }
+            if (a.dot_mode == 1) dots[0] = s * a.dotv[r];
+            else if (a.dot_mode == 2) { dots[0] = s * s; dots[1] = s * hv; }
+        }
     }
     if (a.dot_mode) {
         if (grid_sum<2>(dots, a.partials, a.counter) && threadIdx.x == 0) {
@@ -609,35 +670,50 @@ void launch_row_lengths(const Launcher &l, const Layout &L, uint32_t *rowlen) {
     const int64_t n = slot_count(L, owned_slots(L));
     WV_LAUNCH(l, k_row_lengths, blocks_for(n, 128), 128, 0, L, rowlen);
 }
-void launch_fill_cols(const Launcher &l, const Layout &L, const uint32_t *rowptr, int32_t *col) {
+void launch_window_sort(const Launcher &l, int nown, int nslots, const uint32_t *rowlen, int32_t *row_of,
+                        int32_t *slot_of) {
+    WV_LAUNCH(l, k_window_sort, nslots / kWindow, kWindow, 0, nown, rowlen, row_of, slot_of);
+}
+void launch_slice_sizes(const Launcher &l, int nslices, const int32_t *row_of, const uint32_t *rowlen,
+                        uint32_t *slice_cnt) {
+    WV_LAUNCH(l, k_slice_sizes, blocks_for((int64_t)nslices * 32, kThreads), kThreads, 0, nslices, row_of, rowlen,
+              slice_cnt);
+}
+void launch_fill_int(const Launcher &l, int64_t n, int32_t value, int32_t *dst) {
+    if (n <= 0) return;
+    WV_LAUNCH(l, k_fill_int, stream_blocks(n), kThreads, 0, n, value, dst);
+}
+void launch_fill_cols(const Launcher &l, const Layout &L, const Sell &A, int32_t *col) {
     const int64_t n = slot_count(L, owned_slots(L));
-    WV_LAUNCH(l, k_fill_cols, blocks_for(n, 128), 128, 0, L, rowptr, col);
+    WV_LAUNCH(l, k_fill_cols, blocks_for(n, 128), 128, 0, L, A, col);
+}
+void launch_export_csr(const Launcher &l, const Layout &L, const Sell &A, const double *val, double *csr_val,
+                       int32_t *csr_col) {
+    WV_LAUNCH(l, k_export_csr, blocks_for(L.nown, kThreads), kThreads, 0, L, A, val, csr_val, csr_col);
 }
 static int64_t assembly_cells(const Layout &L) {
     const int jtop = L.jq1 < L.mesh.ny ? L.jq1 : L.mesh.ny - 1;
     return 2LL * (jtop + 1 - L.jq0) * L.mesh.nx;
 }
-void launch_assemble(const Launcher &l, const Layout &L, const Program *c, const Quadrature *q,
-                     const uint32_t *rowptr, const int32_t *col, double *M, double *K) {
+void launch_assemble(const Launcher &l, const Layout &L, const Program *c, const Quadrature *q, const Sell &A,
+                     double *M, double *K) {
     const int64_t n = assembly_cells(L);
-    if (L.mesh.r == 1) WV_LAUNCH(l, k_assemble<1>, blocks_for(n, 128), 128, 0, L, c, *q, rowptr, col, M, K);
-    else WV_LAUNCH(l, k_assemble<2>, blocks_for(n, 128), 128, 0, L, c, *q, rowptr, col, M, K);
+    if (L.mesh.r == 1) WV_LAUNCH(l, k_assemble<1>, blocks_for(n, 128), 128, 0, L, c, *q, A, M, K);
+    else WV_LAUNCH(l, k_assemble<2>, blocks_for(n, 128), 128, 0, L, c, *q, A, M, K);
 }
 void launch_axpy_vals(const Launcher &l, int64_t nnz, const double *M, const double *K, double s, double *out) {
     WV_LAUNCH(l, k_axpy_vals, stream_blocks(nnz), kThreads, 0, nnz, M, K, s, out);
 }
-void launch_find_d0(const Launcher &l, const Layout &L, const uint32_t *rowptr, const int32_t *col,
-                    const double *val, double *d0) {
-    WV_LAUNCH(l, k_find_d0, 1, 32, 0, L, rowptr, col, val, d0);
+void launch_find_d0(const Launcher &l, const Layout &L, const Sell &A, const double *val, double *d0) {
+    WV_LAUNCH(l, k_find_d0, 1, 32, 0, L, A, val, d0);
 }
-void launch_bc_rows(const Launcher &l, const Layout &L, int nb, const int32_t *brow, const uint32_t *rowptr,
-                    const int32_t *col, double *val, const double *d0) {
+void launch_bc_rows(const Launcher &l, const Layout &L, int nb, const int32_t *brow, const Sell &A, double *val,
+                    const double *d0) {
     if (nb <= 0) return;
-    WV_LAUNCH(l, k_bc_rows, blocks_for(nb, 128), 128, 0, L, nb, brow, rowptr, col, val, d0);
+    WV_LAUNCH(l, k_bc_rows, blocks_for(nb, 128), 128, 0, L, nb, brow, A, val, d0);
 }
-void launch_dinv(const Launcher &l, const Layout &L, const uint32_t *rowptr, const int32_t *col,
-                 const double *val, int identity, double *dinv) {
-    WV_LAUNCH(l, k_dinv, blocks_for(L.nown, kThreads), kThreads, 0, L, rowptr, col, val, identity, dinv);
+void launch_dinv(const Launcher &l, const Layout &L, const Sell &A, const double *val, int identity, double *dinv) {
+    WV_LAUNCH(l, k_dinv, blocks_for(L.nown, kThreads), kThreads, 0, L, A, val, identity, dinv);
 }
 void launch_interpolate(const Launcher &l, const Layout &L, const Program *p, double t, double *vec,
                         double *sx, double *sy) {
@@ -659,9 +735,9 @@ void launch_bc_values(const Launcher &l, int mode, int nb, const int32_t *brow, 
     WV_LAUNCH(l, k_bc_values, blocks_for(nb, 128), 128, 0, mode, nb, brow, bx, by, g, t, dt, beta_dt2, z_own,
               x_own, rhs, d0);
 }
-void launch_spmv(const Launcher &l, const SpmvArgs &a, int maxrow) {
-    const int grid = blocks_for(a.nrows, kRowsPerBlock);
-    const size_t smem = (size_t)kRowsPerBlock * maxrow * sizeof(double);
+void launch_spmv(const Launcher &l, const SpmvArgs &a) {
+    const int grid = blocks_for((int64_t)a.A.nslices * kSlice, kThreads);
+    const size_t smem = 0;
     const bool two_terms = a.t[1].val != nullptr;
     const bool twox = a.t[0].xb != nullptr || (two_terms && a.t[1].xb != nullptr);
     if (!two_terms && !twox) WV_LAUNCH(l, (k_spmv<1, false>), grid, kThreads, smem, a);

@@ -33,8 +33,27 @@ struct Layout {
 };
 
 constexpr int kThreads = 256;
-constexpr int kRowsPerBlock = 256;  // K3: one row per thread in the row-sum phase
 constexpr int kMaxRow = 40;
+
+// ---- matrix storage: SELL-32-sigma ---------------------------------------------------------------
+// Sliced ELLPACK with C = 32 rows per slice (one warp), rows sorted by descending length inside
+// windows of kWindow rows (sigma) so a slice holds rows of one length (P2: 19 / 9; P1: 7) and padding
+// is limited to boundary rows.  Slice s stores its entries column-major: element k of the row in
+// lane l sits at slice_ptr[s] + 32 k + l, so one warp load of val / col is one contiguous 256 B /
+// 128 B segment, and -- because consecutive lanes are consecutive DoFs of one kind -- the k-th
+// x gathers of a warp fall on neighbouring addresses.  Entries of a row keep ascending column order
+// (the order of the CSR pattern deal.II builds); the CSR row pointer is kept for lengths / export.
+// All four value arrays (M, K, SYS1, SYS2) share this one pattern.
+constexpr int kSlice = 32;
+constexpr int kWindow = 1024;
+struct Sell {
+    const uint32_t *slice_ptr;  // nslices + 1, element offsets (multiples of 32)
+    const int32_t *col;         // padded local column indices (padding: a valid column, value 0)
+    const int32_t *row_of;      // nslices * 32: owned row of (slice, lane), -1 = none
+    const int32_t *slot_of;     // nown: slot = slice * 32 + lane of an owned row
+    const uint32_t *rowptr;     // CSR row pointer (nown + 1) of the unpadded pattern
+    int nslices, nrows;
+};
 
 // device-resident CG state (deal.II SolverCG + ReductionControl, src/WaveNewmark.cpp:256-261)
 struct CgScalars {
@@ -50,9 +69,7 @@ struct SpmvTerm {
     double ca, cb, coef;
 };
 struct SpmvArgs {
-    const uint32_t *rowptr;
-    const int32_t *col;
-    int nrows;
+    Sell A;
     SpmvTerm t[2];
     const double *add0, *add1;  // row-indexed addends
     double addc0, addc1;
@@ -76,16 +93,23 @@ struct Launcher {
 };
 
 void launch_row_lengths(const Launcher &, const Layout &, uint32_t *rowlen);
-void launch_fill_cols(const Launcher &, const Layout &, const uint32_t *rowptr, int32_t *col);
-void launch_assemble(const Launcher &, const Layout &, const Program *c, const Quadrature *q,
-                     const uint32_t *rowptr, const int32_t *col, double *M, double *K);
+// window sort (descending length, stable) -> row_of / slot_of; then per-slice padded sizes
+void launch_window_sort(const Launcher &, int nown, int nslots, const uint32_t *rowlen, int32_t *row_of,
+                        int32_t *slot_of);
+void launch_slice_sizes(const Launcher &, int nslices, const int32_t *row_of, const uint32_t *rowlen,
+                        uint32_t *slice_cnt);
+void launch_fill_int(const Launcher &, int64_t n, int32_t value, int32_t *dst);
+void launch_fill_cols(const Launcher &, const Layout &, const Sell &A, int32_t *col);
+void launch_assemble(const Launcher &, const Layout &, const Program *c, const Quadrature *q, const Sell &A,
+                     double *M, double *K);
 void launch_axpy_vals(const Launcher &, int64_t nnz, const double *M, const double *K, double s, double *out);
-void launch_find_d0(const Launcher &, const Layout &, const uint32_t *rowptr, const int32_t *col,
-                    const double *val, double *d0);
-void launch_bc_rows(const Launcher &, const Layout &, int nb, const int32_t *brow, const uint32_t *rowptr,
-                    const int32_t *col, double *val, const double *d0);
-void launch_dinv(const Launcher &, const Layout &, const uint32_t *rowptr, const int32_t *col,
-                 const double *val, int identity, double *dinv);
+void launch_find_d0(const Launcher &, const Layout &, const Sell &A, const double *val, double *d0);
+void launch_bc_rows(const Launcher &, const Layout &, int nb, const int32_t *brow, const Sell &A, double *val,
+                    const double *d0);
+void launch_dinv(const Launcher &, const Layout &, const Sell &A, const double *val, int identity, double *dinv);
+// SELL -> CSR export of one value array and of the (global) column indices
+void launch_export_csr(const Launcher &, const Layout &, const Sell &A, const double *val, double *csr_val,
+                       int32_t *csr_col);
 void launch_interpolate(const Launcher &, const Layout &, const Program *p, double t, double *vec,
                         double *sx, double *sy);
 void launch_forcing(const Launcher &, const Layout &, const Program *f, const Quadrature *q, double t_np1,
@@ -95,7 +119,7 @@ enum { BC_DIRECT = 0, BC_NEWMARK_IMPLICIT = 1, BC_SECOND_DIFF = 2 };
 void launch_bc_values(const Launcher &, int mode, int nb, const int32_t *brow, const double *bx,
                       const double *by, const Program *g, double t, double dt, double beta_dt2,
                       const double *z_own, double *x_own, double *rhs, const double *d0);
-void launch_spmv(const Launcher &, const SpmvArgs &, int maxrow);
+void launch_spmv(const Launcher &, const SpmvArgs &);
 void launch_cg_start(const Launcher &, CgScalars *S);
 void launch_cg_update(const Launcher &, int n, CgScalars *S, double *x, double *g, double *h, const double *d,
                       const double *dinv, double *partials, unsigned *counter);

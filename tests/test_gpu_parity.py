@@ -163,8 +163,11 @@ def test_energy_and_error_series():
         g.step()
         assert abs(g.energy() - E) <= 1e-10 * abs(E)
         ge = g.errors()
-        # float per-cell rounding (src/WaveEquationBase.cpp:384) is replicated, so this is tight too
-        assert np.allclose(ge, err[2:], rtol=1e-9, atol=0)
+        # float per-cell rounding (src/WaveEquationBase.cpp:384) is replicated, so L2 is tight too;
+        # the H1 part differentiates the exact solution by centred differences with h = 1e-8
+        # ([deal.II] AutoDerivativeFunction), which amplifies 1-ulp libm differences by 1/(2h)
+        assert np.allclose([ge[0], ge[2]], [err[2], err[4]], rtol=1e-9, atol=0)
+        assert np.allclose([ge[1], ge[3]], [err[3], err[5]], rtol=2e-7, atol=0)
     g.close()
 
 
