@@ -1147,6 +1147,7 @@ int wave_bench_cg_iter(wave_ctx *ctx, int which, int reps, double *ms_avg, doubl
     a.t[0] = {val, ctx->d, nullptr, 1.0, 0.0, 1.0};
     a.y = ctx->rhs;
     launch_spmv(ctx->launcher, a);
+    launch_zero_rows(ctx->launcher, ctx->nb, ctx->brow, ctx->rhs);  // x_B = 0 must satisfy the Dirichlet rows
     double ms_total = 0.0, its_total = 0.0;
     for (int r = 0; r < reps; ++r) {
         launch_fill(ctx->launcher, L.nloc, 0.0, ctx->unew);

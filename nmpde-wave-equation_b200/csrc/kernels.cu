@@ -3,6 +3,7 @@
 // multiples of the SM count where the work is a grid-stride stream.
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <cstdio>
 
 #include <cub/block/block_radix_sort.cuh>
@@ -391,38 +392,48 @@ __global__ void k_bc_values(int mode, int nb, const int32_t *brow, const double 
 // A row is accumulated in ascending column order with separate multiply and add roundings, i.e. the
 // arithmetic of a serial CSR loop (bitwise equal to it for a single term).  Epilogues: addends, the
 // CG residual start (h = D^-1 g, d = -h) and fused dot products (deterministic grid reduction).
-template <int NT, bool TWOX>
-__device__ __forceinline__ double spmv_entry(const SpmvArgs &a, uint32_t p, int c) {
-    double prod = 0.0;
-#pragma unroll
-    for (int k = 0; k < NT; ++k) {
-        double xv = __dmul_rn(a.t[k].ca, a.t[k].xa[c]);
-        if (TWOX && a.t[k].xb) xv = __dadd_rn(xv, __dmul_rn(a.t[k].cb, a.t[k].xb[c]));
-        const double term = __dmul_rn(a.t[k].coef, __dmul_rn(__ldg(&a.t[k].val[p]), xv));
-        prod = k == 0 ? term : __dadd_rn(prod, term);
-    }
-    return prod;
-}
-template <int NT, bool TWOX>
+// streaming loads for the matrix arrays (read once per launch): evict-first, keep L1/L2 for x
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
+
+template <int NT, bool TWOX, int CH>
 __global__ void __launch_bounds__(kThreads) k_spmv(SpmvArgs a) {
     if (a.skip_flag && *a.skip_flag != 0) return;
-    const int slice = (blockIdx.x * kThreads + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (kThreads / 32);
     double dots[2] = {0.0, 0.0};
-    if (slice < a.A.nslices) {
+    // persistent warps: grid-stride over slices, CH (col, val) pairs of a row in flight per lane
+    for (int slice = (blockIdx.x * kThreads + threadIdx.x) >> 5; slice < a.A.nslices; slice += nwarps) {
         const uint32_t b = a.A.slice_ptr[slice] + lane, e = a.A.slice_ptr[slice + 1];
         const int r = a.A.row_of[slice * kSlice + lane];
         double s = 0.0;
-        uint32_t p = b;
-        for (; p + 3 * kSlice < e; p += 4 * kSlice) {
-            const int c0 = __ldg(&a.A.col[p]), c1 = __ldg(&a.A.col[p + kSlice]);
-            const int c2 = __ldg(&a.A.col[p + 2 * kSlice]), c3 = __ldg(&a.A.col[p + 3 * kSlice]);
-            const double p0 = spmv_entry<NT, TWOX>(a, p, c0);
-            const double p1 = spmv_entry<NT, TWOX>(a, p + kSlice, c1);
-            const double p2 = spmv_entry<NT, TWOX>(a, p + 2 * kSlice, c2);
-            const double p3 = spmv_entry<NT, TWOX>(a, p + 3 * kSlice, c3);
-            s = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(s, p0), p1), p2), p3);
+        for (uint32_t p = b; p < e; p += CH * kSlice) {
+            int c[CH];
+            double v[NT][CH];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const uint32_t q = p + k * kSlice;
+                if (q < e) {  // warp-uniform
+                    c[k] = ld_stream(&a.A.col[q]);
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) v[t][k] = ld_stream(&a.t[t].val[q]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                if (p + k * kSlice < e) {
+                    double prod = 0.0;
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) {
+                        double xv = __dmul_rn(a.t[t].ca, a.t[t].xa[c[k]]);
+                        if (TWOX && a.t[t].xb) xv = __dadd_rn(xv, __dmul_rn(a.t[t].cb, a.t[t].xb[c[k]]));
+                        const double term = __dmul_rn(a.t[t].coef, __dmul_rn(v[t][k], xv));
+                        prod = t == 0 ? term : __dadd_rn(prod, term);
+                    }
+                    s = __dadd_rn(s, prod);
+                }
+            }
         }
-        for (; p < e; p += kSlice) s = __dadd_rn(s, spmv_entry<NT, TWOX>(a, p, __ldg(&a.A.col[p])));
         if (r >= 0) {
             if (a.add0) s += a.addc0 * a.add0[r];
             if (a.add1) s += a.addc1 * a.add1[r];
@@ -433,8 +444,8 @@ __global__ void __launch_bounds__(kThreads) k_spmv(SpmvArgs a) {
                 a.h_out[r] = hv;
                 a.d_out[r] = -hv;
             }
-            if (a.dot_mode == 1) dots[0] = s * a.dotv[r];
-            else if (a.dot_mode == 2) { dots[0] = s * s; dots[1] = s * hv; }
+            if (a.dot_mode == 1) dots[0] += s * a.dotv[r];
+            else if (a.dot_mode == 2) { dots[0] += s * s; dots[1] += s * hv; }
         }
     }
     if (a.dot_mode) {
@@ -443,6 +454,11 @@ __global__ void __launch_bounds__(kThreads) k_spmv(SpmvArgs a) {
             if (a.dot_mode == 2) a.result[1] = dots[1];
         }
     }
+}
+
+__global__ void k_zero_rows(int nb, const int32_t *brow, double *vec) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb) vec[brow[b]] = 0.0;
 }
 
 // ---- K6: PCG with device-resident scalars (deal.II SolverCG) ----------------------------
@@ -735,14 +751,33 @@ void launch_bc_values(const Launcher &l, int mode, int nb, const int32_t *brow, 
     WV_LAUNCH(l, k_bc_values, blocks_for(nb, 128), 128, 0, mode, nb, brow, bx, by, g, t, dt, beta_dt2, z_own,
               x_own, rhs, d0);
 }
+template <class Kernel>
+static int persistent_grid(Kernel kernel, int64_t blocks_needed) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess || occ < 1) occ = 4;
+    const int64_t cap = (int64_t)kSMs * occ;
+    return (int)(blocks_needed < cap ? (blocks_needed > 0 ? blocks_needed : 1) : cap);
+}
+constexpr int kChunk = 10;
 void launch_spmv(const Launcher &l, const SpmvArgs &a) {
-    const int grid = blocks_for((int64_t)a.A.nslices * kSlice, kThreads);
-    const size_t smem = 0;
+    const int64_t need = blocks_for((int64_t)a.A.nslices * kSlice, kThreads);
     const bool two_terms = a.t[1].val != nullptr;
     const bool twox = a.t[0].xb != nullptr || (two_terms && a.t[1].xb != nullptr);
-    if (!two_terms && !twox) WV_LAUNCH(l, (k_spmv<1, false>), grid, kThreads, smem, a);
-    else if (!two_terms) WV_LAUNCH(l, (k_spmv<1, true>), grid, kThreads, smem, a);
-    else WV_LAUNCH(l, (k_spmv<2, true>), grid, kThreads, smem, a);
+    static int g10 = 0, g11 = 0, g21 = 0;
+    if (!two_terms && !twox) {
+        if (!g10) g10 = persistent_grid(k_spmv<1, false, kChunk>, 1 << 30);
+        WV_LAUNCH(l, (k_spmv<1, false, kChunk>), (int)std::min<int64_t>(need, g10), kThreads, 0, a);
+    } else if (!two_terms) {
+        if (!g11) g11 = persistent_grid(k_spmv<1, true, kChunk>, 1 << 30);
+        WV_LAUNCH(l, (k_spmv<1, true, kChunk>), (int)std::min<int64_t>(need, g11), kThreads, 0, a);
+    } else {
+        if (!g21) g21 = persistent_grid(k_spmv<2, true, kChunk>, 1 << 30);
+        WV_LAUNCH(l, (k_spmv<2, true, kChunk>), (int)std::min<int64_t>(need, g21), kThreads, 0, a);
+    }
+}
+void launch_zero_rows(const Launcher &l, int nb, const int32_t *brow, double *vec) {
+    if (nb <= 0) return;
+    WV_LAUNCH(l, k_zero_rows, blocks_for(nb, 128), 128, 0, nb, brow, vec);
 }
 void launch_cg_start(const Launcher &l, CgScalars *S) { WV_LAUNCH(l, k_cg_start, 1, 32, 0, S); }
 void launch_cg_update(const Launcher &l, int n, CgScalars *S, double *x, double *g, double *h, const double *d,
@@ -787,3 +822,6 @@ void launch_flush_l2(const Launcher &l, double *buf, int64_t n) {
 }
 
 }  // namespace wv
+namespace wv {
+int spmv_grid_blocks(int nslices) { return (nslices + 7) / 8; }
+}

@@ -120,6 +120,8 @@ void launch_bc_values(const Launcher &, int mode, int nb, const int32_t *brow, c
                       const double *by, const Program *g, double t, double dt, double beta_dt2,
                       const double *z_own, double *x_own, double *rhs, const double *d0);
 void launch_spmv(const Launcher &, const SpmvArgs &);
+void launch_zero_rows(const Launcher &, int nb, const int32_t *brow, double *vec);
+int spmv_grid_blocks(int nslices);
 void launch_cg_start(const Launcher &, CgScalars *S);
 void launch_cg_update(const Launcher &, int n, CgScalars *S, double *x, double *g, double *h, const double *d,
                       const double *dinv, double *partials, unsigned *counter);

@@ -239,7 +239,8 @@ def test_step_host_matches_resident_path():
     for _ in range(5):
         a.step()
         b.step_host(u, v, acc)
-    assert np.array_equal(a.vector(api.VEC_U), u)
+    # two contexts assemble with atomics in different orders: equal to round-off, not bitwise
+    assert rel(a.vector(api.VEC_U), u) < 1e-12
     a.close()
     b.close()
 
