@@ -720,7 +720,8 @@ int wave_setup(wave_ctx *ctx) {
     CK(cudaFree(rowlen));
     CK(cudaFree(slice_cnt));
     RET(dev_alloc(ctx, &ctx->col, (size_t)ctx->nnz_pad, false));
-    ctx->A = Sell{ctx->slice_ptr, ctx->col, ctx->row_of, ctx->slot_of, ctx->rowptr, ctx->nslices, L.nown};
+    ctx->A = Sell{ctx->slice_ptr, ctx->col, ctx->row_of, ctx->slot_of, ctx->rowptr, ctx->nslices, L.nown,
+                  L.mesh.r == 1 ? 7 : 10};
     launch_fill_int(l, ctx->nnz_pad, L.own_off, ctx->col);  // padding entries: a valid column, value 0
     launch_fill_cols(l, L, ctx->A, ctx->col);
 

@@ -397,39 +397,61 @@ __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p);
 __device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
 
 template <int NT, bool TWOX, int CH>
-__global__ void __launch_bounds__(kThreads) k_spmv(SpmvArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) k_spmv(SpmvArgs a) {
     if (a.skip_flag && *a.skip_flag != 0) return;
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (kThreads / 32);
     double dots[2] = {0.0, 0.0};
-    // persistent warps: grid-stride over slices, CH (col, val) pairs of a row in flight per lane
-    for (int slice = (blockIdx.x * kThreads + threadIdx.x) >> 5; slice < a.A.nslices; slice += nwarps) {
-        const uint32_t b = a.A.slice_ptr[slice] + lane, e = a.A.slice_ptr[slice + 1];
-        const int r = a.A.row_of[slice * kSlice + lane];
+    // Persistent warps, grid-stride over slices.  Per chunk a lane issues CH col loads and CH*NT val
+    // loads back to back (unconditional: a short tail re-reads the row's last entry and is masked out
+    // of the sum), then the CH dependent x gathers, then accumulates in column order.
+    int slice = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+    uint32_t b = 0, e = 0;
+    int r = -1;
+    if (slice < a.A.nslices) {
+        b = a.A.slice_ptr[slice];
+        e = a.A.slice_ptr[slice + 1];
+        r = a.A.row_of[slice * kSlice + lane];
+    }
+    while (slice < a.A.nslices) {
+        // metadata of this warp's next slice, requested before the long-latency work below
+        const int nslice = slice + nwarps;
+        uint32_t nb = 0, ne = 0;
+        int nr = -1;
+        if (nslice < a.A.nslices) {
+            nb = a.A.slice_ptr[nslice];
+            ne = a.A.slice_ptr[nslice + 1];
+            nr = a.A.row_of[nslice * kSlice + lane];
+        }
+        const int len = (int)((e - b) >> 5);
+        const uint32_t base = b + lane;
         double s = 0.0;
-        for (uint32_t p = b; p < e; p += CH * kSlice) {
+        for (int k0 = 0; k0 < len; k0 += CH) {
             int c[CH];
-            double v[NT][CH];
+            double v[NT][CH], x[NT][CH];
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
-                const uint32_t q = p + k * kSlice;
-                if (q < e) {  // warp-uniform
-                    c[k] = ld_stream(&a.A.col[q]);
+                const int kk = min(k0 + k, len - 1);
+                const uint32_t q = base + (uint32_t)kk * kSlice;
+                c[k] = ld_stream(&a.A.col[q]);
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) v[t][k] = ld_stream(&a.t[t].val[q]);
-                }
+                for (int t = 0; t < NT; ++t) v[t][k] = ld_stream(&a.t[t].val[q]);
             }
 #pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                if (p + k * kSlice < e) {
-                    double prod = 0.0;
+            for (int k = 0; k < CH; ++k)
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) {
-                        double xv = __dmul_rn(a.t[t].ca, a.t[t].xa[c[k]]);
-                        if (TWOX && a.t[t].xb) xv = __dadd_rn(xv, __dmul_rn(a.t[t].cb, a.t[t].xb[c[k]]));
-                        const double term = __dmul_rn(a.t[t].coef, __dmul_rn(v[t][k], xv));
-                        prod = t == 0 ? term : __dadd_rn(prod, term);
-                    }
+                for (int t = 0; t < NT; ++t) {
+                    double xv = __dmul_rn(a.t[t].ca, a.t[t].xa[c[k]]);
+                    if (TWOX && a.t[t].xb) xv = __dadd_rn(xv, __dmul_rn(a.t[t].cb, a.t[t].xb[c[k]]));
+                    x[t][k] = xv;
+                }
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                if (k0 + k < len) {  // warp-uniform
+                    double prod = __dmul_rn(a.t[0].coef, __dmul_rn(v[0][k], x[0][k]));
+#pragma unroll
+                    for (int t = 1; t < NT; ++t)
+                        prod = __dadd_rn(prod, __dmul_rn(a.t[t].coef, __dmul_rn(v[t][k], x[t][k])));
                     s = __dadd_rn(s, prod);
                 }
             }
@@ -447,6 +469,7 @@ __global__ void __launch_bounds__(kThreads) k_spmv(SpmvArgs a) {
             if (a.dot_mode == 1) dots[0] += s * a.dotv[r];
             else if (a.dot_mode == 2) { dots[0] += s * s; dots[1] += s * hv; }
         }
+        slice = nslice; b = nb; e = ne; r = nr;
     }
     if (a.dot_mode) {
         if (grid_sum<2>(dots, a.partials, a.counter) && threadIdx.x == 0) {
@@ -758,22 +781,21 @@ static int persistent_grid(Kernel kernel, int64_t blocks_needed) {
     const int64_t cap = (int64_t)kSMs * occ;
     return (int)(blocks_needed < cap ? (blocks_needed > 0 ? blocks_needed : 1) : cap);
 }
-constexpr int kChunk = 10;
-void launch_spmv(const Launcher &l, const SpmvArgs &a) {
+template <int NT, bool TWOX, int CH>
+static void launch_spmv_t(const Launcher &l, const SpmvArgs &a) {
+    static int grid_cap = 0;
+    if (!grid_cap) grid_cap = persistent_grid(k_spmv<NT, TWOX, CH>, 1 << 30);
     const int64_t need = blocks_for((int64_t)a.A.nslices * kSlice, kThreads);
+    WV_LAUNCH(l, (k_spmv<NT, TWOX, CH>), (int)std::min<int64_t>(need, grid_cap), kThreads, 0, a);
+}
+// chunk = the dominant row length of the element: P1 rows hold 7 entries, P2 rows 19 / 9
+void launch_spmv(const Launcher &l, const SpmvArgs &a) {
     const bool two_terms = a.t[1].val != nullptr;
     const bool twox = a.t[0].xb != nullptr || (two_terms && a.t[1].xb != nullptr);
-    static int g10 = 0, g11 = 0, g21 = 0;
-    if (!two_terms && !twox) {
-        if (!g10) g10 = persistent_grid(k_spmv<1, false, kChunk>, 1 << 30);
-        WV_LAUNCH(l, (k_spmv<1, false, kChunk>), (int)std::min<int64_t>(need, g10), kThreads, 0, a);
-    } else if (!two_terms) {
-        if (!g11) g11 = persistent_grid(k_spmv<1, true, kChunk>, 1 << 30);
-        WV_LAUNCH(l, (k_spmv<1, true, kChunk>), (int)std::min<int64_t>(need, g11), kThreads, 0, a);
-    } else {
-        if (!g21) g21 = persistent_grid(k_spmv<2, true, kChunk>, 1 << 30);
-        WV_LAUNCH(l, (k_spmv<2, true, kChunk>), (int)std::min<int64_t>(need, g21), kThreads, 0, a);
-    }
+    const bool p1 = a.A.chunk <= 7;
+    if (!two_terms && !twox) { if (p1) launch_spmv_t<1, false, 7>(l, a); else launch_spmv_t<1, false, 10>(l, a); }
+    else if (!two_terms) { if (p1) launch_spmv_t<1, true, 7>(l, a); else launch_spmv_t<1, true, 10>(l, a); }
+    else { if (p1) launch_spmv_t<2, true, 7>(l, a); else launch_spmv_t<2, true, 10>(l, a); }
 }
 void launch_zero_rows(const Launcher &l, int nb, const int32_t *brow, double *vec) {
     if (nb <= 0) return;

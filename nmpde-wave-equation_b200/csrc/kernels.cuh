@@ -53,6 +53,7 @@ struct Sell {
     const int32_t *slot_of;     // nown: slot = slice * 32 + lane of an owned row
     const uint32_t *rowptr;     // CSR row pointer (nown + 1) of the unpadded pattern
     int nslices, nrows;
+    int chunk;                  // entries a lane keeps in flight: 7 (P1) or 10 (P2)
 };
 
 // device-resident CG state (deal.II SolverCG + ReductionControl, src/WaveNewmark.cpp:256-261)
