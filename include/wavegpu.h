@@ -102,6 +102,15 @@ int wave_set_expr(wave_ctx *ctx, int which, const char *expression, const char *
 /* Evaluate one compiled expression on the host side of the ABI (parser self-test). */
 int wave_eval_expr(wave_ctx *ctx, int which, double x, double y, double t, double *out);
 
+/* Context-free expression handles for the host classes (FunctionParser::value on the host side:
+   boundary tables, convergence.csv bookkeeping).  Host only, no device needed. */
+typedef struct wave_expr wave_expr;
+int wave_expr_create(const char *expression, const char *variable_names, const char *constants,
+                     wave_expr **out, char *errbuf, size_t errbuf_len);
+double wave_expr_value(const wave_expr *e, double x, double y, double t);
+int wave_expr_is_time_dependent(const wave_expr *e);
+void wave_expr_destroy(wave_expr *e);
+
 /* Replaces setup() + assemble_matrices(): mesh, DoF numbering, sparsity pattern, M, K, the
    scheme matrices and their Dirichlet rows (src/WaveNewmark.cpp:12-114, src/WaveTheta.cpp:12-117,
    src/WaveEquationBase.cpp:37-94). */

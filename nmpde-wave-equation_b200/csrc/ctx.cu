@@ -664,6 +664,27 @@ int wave_set_expr(wave_ctx *ctx, int which, const char *expression, const char *
     return WAVE_OK;
 }
 
+struct wave_expr {
+    Program prog;
+};
+int wave_expr_create(const char *expression, const char *variable_names, const char *constants, wave_expr **out,
+                     char *errbuf, size_t errbuf_len) {
+    if (!expression || !out) return WAVE_ERR_ARG;
+    *out = nullptr;
+    try {
+        wave_expr *e = new wave_expr();
+        e->prog = compile_expression(expression, variable_names ? variable_names : "", constants ? constants : "");
+        *out = e;
+        return WAVE_OK;
+    } catch (const std::exception &ex) {
+        if (errbuf && errbuf_len) std::snprintf(errbuf, errbuf_len, "%s", ex.what());
+        return WAVE_ERR_EXPR;
+    }
+}
+double wave_expr_value(const wave_expr *e, double x, double y, double t) { return eval(&e->prog, x, y, t); }
+int wave_expr_is_time_dependent(const wave_expr *e) { return e->prog.time_dependent; }
+void wave_expr_destroy(wave_expr *e) { delete e; }
+
 int wave_eval_expr(wave_ctx *ctx, int which, double x, double y, double t, double *out) {
     if (!ctx || which < 0 || which >= WAVE_EXPR_COUNT || !ctx->has[which] || !out)
         return fail(ctx, WAVE_ERR_ARG, "expression not set");

@@ -1,0 +1,339 @@
+// WaveEquationBase.cpp -- logging, file naming and C-ABI plumbing shared by WaveNewmark / WaveTheta.
+// Follows src/WaveEquationBase.cpp of the reference for every user-visible artefact (folder names,
+// CSV headers, stream formatting, step line); the numerics behind each call are libwavegpu's.
+#include "WaveEquationBase.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <sstream>
+#include <stdexcept>
+
+namespace
+{
+bool env_flag_enabled(const char* name, const bool default_value)
+{
+    const char* v = std::getenv(name);
+    if (!v)
+        return default_value;
+    const std::string s(v);
+    if (s == "0" || s == "false" || s == "FALSE" || s == "False")
+        return false;
+    if (s == "1" || s == "true" || s == "TRUE" || s == "True")
+        return true;
+    return default_value;
+}
+
+const FunctionParser<2>& as_parser(const Function<2>& fn, const char* name)
+{
+    const auto* p = dynamic_cast<const FunctionParser<2>*>(&fn);
+    if (!p || !p->is_initialized())
+        throw std::invalid_argument(std::string("function '") + name +
+                                    "' must be an initialised FunctionParser to be evaluated on the device");
+    return *p;
+}
+} // namespace
+
+WaveEquationBase::WaveEquationBase(const std::string& problem_name_,
+                                   const std::pair<unsigned int, unsigned int>& N_el_,
+                                   const std::pair<Point<dim>, Point<dim>>& geometry_,
+                                   const unsigned int& r_,
+                                   const double& T_,
+                                   const double& delta_t_,
+                                   const Function<dim>& c_,
+                                   Function<dim>& f_,
+                                   const Function<dim>& u0_,
+                                   const Function<dim>& v0_,
+                                   Function<dim>& g_,
+                                   Function<dim>& dgdt_,
+                                   const unsigned int log_every_,
+                                   const unsigned int print_every_,
+                                   Function<dim>* exact_solution_)
+    : problem_name(problem_name_), N_el(N_el_), geometry(geometry_), r(r_), T(T_), delta_t(delta_t_), c(c_), f(f_),
+      u0(u0_), v0(v0_), g(g_), dgdt(dgdt_), log_every(log_every_), print_every(print_every_),
+      exact_solution(exact_solution_), mpi_size(1), mpi_rank(0), pcout(std::cout, true)
+{
+}
+
+WaveEquationBase::~WaveEquationBase()
+{
+    if (ctx)
+        wave_destroy(ctx);
+}
+
+void WaveEquationBase::check(int status, const char* what) const
+{
+    if (status == WAVE_OK)
+        return;
+    const std::string msg = std::string(what) + ": " + wave_last_error(ctx);
+    if (status == WAVE_ERR_EXPR || status == WAVE_ERR_ARG)
+        throw std::invalid_argument(msg);
+    throw std::runtime_error(msg);
+}
+
+void WaveEquationBase::create_context(int scheme, double theta, double beta, double gamma)
+{
+    wave_config cfg;
+    wave_default_config(&cfg);
+    cfg.nx = static_cast<int32_t>(N_el.first);
+    cfg.ny = static_cast<int32_t>(N_el.second);
+    cfg.x0 = geometry.first[0];
+    cfg.x1 = geometry.second[0];
+    cfg.y0 = geometry.first[1];
+    cfg.y1 = geometry.second[1];
+    cfg.r = static_cast<int32_t>(r);
+    cfg.scheme = scheme;
+    cfg.dt = delta_t;
+    cfg.theta = theta;
+    cfg.beta = beta;
+    cfg.gamma = gamma;
+    if (wave_create(&cfg, &ctx) != WAVE_OK)
+        throw std::runtime_error(std::string("wave_create: ") + wave_last_error(nullptr));
+
+    struct Slot { int id; const Function<dim>* fn; const char* name; };
+    const Slot slots[] = { { WAVE_EXPR_C, &c, "C" }, { WAVE_EXPR_F, &f, "F" }, { WAVE_EXPR_U0, &u0, "U0" },
+                           { WAVE_EXPR_V0, &v0, "V0" }, { WAVE_EXPR_G, &g, "G" }, { WAVE_EXPR_DGDT, &dgdt, "DGDT" } };
+    for (const auto& s : slots)
+    {
+        const auto& p = as_parser(*s.fn, s.name);
+        check(wave_set_expr(ctx, s.id, p.get_expression().c_str(), p.get_variables().c_str(),
+                            p.get_constants().c_str()),
+              s.name);
+    }
+    if (exact_solution != nullptr)
+    {
+        const auto& p = as_parser(*exact_solution, "Solution");
+        check(wave_set_expr(ctx, WAVE_EXPR_SOLUTION, p.get_expression().c_str(), p.get_variables().c_str(),
+                            p.get_constants().c_str()),
+              "Solution");
+    }
+}
+
+void WaveEquationBase::setup_mesh()
+{
+    pcout << "Initializing the mesh" << std::endl;
+    // the structured simplex mesh is generated analytically on the device; no mesh file is written
+    pcout << "  Number of elements = " << 2ull * N_el.first * N_el.second << std::endl;
+}
+
+void WaveEquationBase::setup_fe()
+{
+    pcout << "Initializing the finite element space" << std::endl;
+    pcout << "  Degree                     = " << r << std::endl;
+    pcout << "  DoFs per cell              = " << (r == 1 ? 3 : 6) << std::endl;
+    pcout << "  Quadrature points per cell = " << (r == 1 ? 3 : 7) << std::endl;
+}
+
+void WaveEquationBase::setup_dof_handler()
+{
+    pcout << "Initializing the DoF handler" << std::endl;
+    pcout << "  Number of DoFs = " << wave_n_dofs(ctx) << std::endl;
+}
+
+void WaveEquationBase::prepare_output_filename(const std::string& method_params)
+{
+    output_folder = "../results/" + problem_name + "/run-R" + std::to_string(r) + "-N" +
+                    std::to_string(N_el.first) + "x" + std::to_string(N_el.second) + "-dt" + clean_double(delta_t) +
+                    "-T" + clean_double(T) + method_params + "/";
+
+    pcout << "Output folder: " << output_folder << std::endl;
+
+    if (mpi_rank == 0)
+    {
+        if (!std::filesystem::exists(output_folder))
+            std::filesystem::create_directories(output_folder);
+
+        if (const char* param_env = std::getenv("NMPDE_PARAM_FILE"))
+        {
+            try
+            {
+                const std::filesystem::path src(param_env);
+                const std::filesystem::path dst = std::filesystem::path(output_folder) / "parameters.json";
+                if (std::filesystem::exists(src))
+                {
+                    std::filesystem::copy_file(src, dst, std::filesystem::copy_options::overwrite_existing);
+                    pcout << "  Parameters copied to " << dst << std::endl;
+                }
+                else
+                    pcout << "  Parameter file not found: " << src << std::endl;
+            }
+            catch (const std::exception& e)
+            {
+                pcout << "  Warning: could not copy parameter file (" << e.what() << ")" << std::endl;
+            }
+        }
+
+        // energy/error CSV files are opened lazily so that log_every = 0 produces no files
+        if (exact_solution != nullptr)
+        {
+            const std::string convergence_file_path = "../results/" + problem_name + "/convergence.csv";
+            const bool file_exists = std::filesystem::exists(convergence_file_path);
+            convergence_file.open(convergence_file_path, std::ios_base::app);
+            if (convergence_file.is_open() && !file_exists)
+                convergence_file << "h,N_el_x,N_el_y,r,dt,T,method,theta,beta,gamma,rel_L2_error_final,"
+                                    "rel_H1_error_final,elapsed_time_s"
+                                 << std::endl;
+        }
+    }
+}
+
+void WaveEquationBase::compute_and_log_energy()
+{
+    check(wave_energy(ctx, &current_energy), "wave_energy");
+    if (mpi_rank == 0)
+    {
+        if (!energy_log_file.is_open())
+        {
+            energy_log_file.open(output_folder + "energy.csv");
+            if (energy_log_file.is_open())
+                energy_log_file << "timestep,time,energy" << std::endl;
+        }
+        if (energy_log_file.is_open())
+            energy_log_file << timestep_number << "," << time << "," << current_energy << std::endl;
+    }
+}
+
+void WaveEquationBase::log_point_probe()
+{
+    const double px = 0.5 * (geometry.first[0] + geometry.second[0]);
+    const double py = 0.5 * (geometry.first[1] + geometry.second[1]);
+    double u_probe = 0.0;
+    check(wave_probe(ctx, px, py, &u_probe), "wave_probe");
+    if (mpi_rank == 0)
+    {
+        if (!point_probe_log_file.is_open())
+        {
+            point_probe_log_file.open(output_folder + "probe.csv");
+            if (point_probe_log_file.is_open())
+                point_probe_log_file << "timestep,time,u_probe" << std::endl;
+        }
+        if (point_probe_log_file.is_open())
+            point_probe_log_file << timestep_number << "," << time << "," << std::scientific
+                                 << std::setprecision(10) << u_probe << std::endl;
+    }
+}
+
+void WaveEquationBase::log_iterations(const unsigned int n_iterations_1, const unsigned int n_iterations_2)
+{
+    if (mpi_rank == 0)
+    {
+        if (!iterations_log_file.is_open())
+        {
+            iterations_log_file.open(output_folder + "iterations.csv");
+            if (iterations_log_file.is_open())
+                iterations_log_file << "timestep,time,iterations_1,iterations_2" << std::endl;
+        }
+        if (iterations_log_file.is_open())
+            iterations_log_file << timestep_number << "," << time << "," << n_iterations_1 << "," << n_iterations_2
+                                << std::endl;
+    }
+}
+
+void WaveEquationBase::compute_and_log_error()
+{
+    if (exact_solution == nullptr)
+        return;
+    double e[4];
+    check(wave_errors(ctx, time, e), "wave_errors");
+    if (mpi_rank == 0)
+    {
+        if (!error_log_file.is_open())
+        {
+            error_log_file.open(output_folder + "error.csv");
+            if (error_log_file.is_open())
+                error_log_file << "timestep,time,L2_error,H1_error,rel_L2_error,rel_H1_error" << std::endl;
+        }
+        if (error_log_file.is_open())
+            error_log_file << timestep_number << "," << time << "," << std::scientific << std::setprecision(6) << e[0]
+                           << "," << e[1] << "," << e[2] << "," << e[3] << std::endl;
+    }
+}
+
+void WaveEquationBase::compute_final_errors() { compute_final_errors("", "", ""); }
+
+void WaveEquationBase::compute_final_errors(const std::string& theta_str, const std::string& beta_str,
+                                            const std::string& gamma_str)
+{
+    if (exact_solution == nullptr)
+        return;
+    double e[4];
+    check(wave_errors(ctx, time, e), "wave_errors");
+    const double rel_error_L2 = e[2], rel_error_H1 = e[3];
+    if (mpi_rank == 0 && convergence_file.is_open())
+    {
+        const double h = 1.0 / std::sqrt(N_el.first * N_el.second);
+        convergence_file << h << "," << N_el.first << "," << N_el.second << "," << r << "," << delta_t << "," << T
+                         << "," << problem_name << ",";
+        convergence_file << (theta_str.empty() ? "N/A" : theta_str) << "," << (beta_str.empty() ? "N/A" : beta_str)
+                         << "," << (gamma_str.empty() ? "N/A" : gamma_str) << ",";
+        convergence_file << std::scientific << std::setprecision(6) << rel_error_L2 << "," << rel_error_H1 << ",";
+        convergence_file << std::fixed << std::setprecision(3) << simulation_time << std::endl;
+
+        pcout << "Final (last-iteration) errors:" << std::endl;
+        pcout << "  Relative L2 error  = " << std::scientific << std::setprecision(6) << rel_error_L2 << std::endl;
+        pcout << "  Relative H1 error  = " << std::scientific << std::setprecision(6) << rel_error_H1 << std::endl;
+    }
+}
+
+void WaveEquationBase::print_step_info()
+{
+    std::ostringstream oss;
+    oss << "Step " << std::setw(6) << timestep_number << ",  t=" << std::scientific << std::setprecision(3)
+        << std::setw(9) << time << ",  ||u||=" << std::scientific << std::setprecision(3) << std::setw(9) << norm_u
+        << ",  ||v||=" << std::scientific << std::setprecision(3) << std::setw(9) << norm_v;
+    const char* env_p = std::getenv("NMPDE_LOG_EVERY");
+    if (!env_p || std::atoi(env_p) != 0)
+        oss << ",  E=" << std::scientific << std::setprecision(3) << std::setw(9) << current_energy;
+    pcout << oss.str() << std::endl;
+}
+
+void WaveEquationBase::output() const
+{
+    // VTU/PVTU visualisation output (src/WaveEquationBase.cpp:330-365) is outside the accelerated
+    // path; runs that ask for it are told once and continue.
+    static bool warned = false;
+    if (env_flag_enabled("NMPDE_SAVE_SOLUTION", true) && !warned)
+    {
+        warned = true;
+        std::cout << "  Note: 'Save Solution' (VTU output) is not provided by the GPU build; "
+                     "set \"Save Solution\": false to silence this note."
+                  << std::endl;
+    }
+}
+
+bool WaveEquationBase::check_divergence(const double nu, const double nv, const double threshold) const
+{
+    return (!std::isfinite(nu) || !std::isfinite(nv) || nu > threshold || nv > threshold);
+}
+
+void WaveEquationBase::close_logs()
+{
+    if (mpi_rank == 0)
+    {
+        if (energy_log_file.is_open())
+            energy_log_file.close();
+        if (error_log_file.is_open())
+            error_log_file.close();
+        if (convergence_file.is_open())
+            convergence_file.close();
+        if (iterations_log_file.is_open())
+            iterations_log_file.close();
+        if (point_probe_log_file.is_open())
+            point_probe_log_file.close();
+    }
+}
+
+std::string clean_double(double x, int precision)
+{
+    std::ostringstream out;
+    out << std::fixed << std::setprecision(precision) << x;
+    std::string s = out.str();
+    if (s.find('.') != std::string::npos)
+    {
+        while (!s.empty() && s.back() == '0')
+            s.pop_back();
+        if (!s.empty() && s.back() == '.')
+            s.pop_back();
+    }
+    std::replace(s.begin(), s.end(), '.', '_');
+    return s.empty() ? "0" : s;
+}

@@ -1,0 +1,112 @@
+// WaveEquationBase.hpp -- shared base of the two time integrators, with the reference's surface
+// (include/WaveEquationBase.hpp:55-370): constructor arguments, run(), the logging helpers and the
+// CSV formats.  Mesh, DoFs, matrices and vectors live on the GPU behind a wave_ctx; this class
+// only sequences C-ABI calls and writes the files.
+#ifndef WAVE_EQUATION_BASE_HPP
+#define WAVE_EQUATION_BASE_HPP
+
+#include <chrono>
+#include <cstdlib>
+#include <filesystem>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <string>
+#include <utility>
+
+#include "wave_types.hpp"
+
+class WaveEquationBase
+{
+  public:
+    static constexpr unsigned int dim = 2;
+
+    virtual ~WaveEquationBase();
+    /// Run the full simulation (setup, assembly, time loop, output).
+    virtual void run() = 0;
+
+  protected:
+    WaveEquationBase(const std::string& problem_name_,
+                     const std::pair<unsigned int, unsigned int>& N_el_,
+                     const std::pair<Point<dim>, Point<dim>>& geometry_,
+                     const unsigned int& r_,
+                     const double& T_,
+                     const double& delta_t_,
+                     const Function<dim>& c_,
+                     Function<dim>& f_,
+                     const Function<dim>& u0_,
+                     const Function<dim>& v0_,
+                     Function<dim>& g_,
+                     Function<dim>& dgdt_,
+                     const unsigned int log_every_,
+                     const unsigned int print_every_,
+                     Function<dim>* exact_solution_);
+
+    // ---- Mesh & FE initialisation (device side: wave_create / wave_set_expr / wave_setup) -------
+    void create_context(int scheme, double theta, double beta, double gamma);
+    void setup_mesh();
+    void setup_fe();
+    void setup_dof_handler();
+
+    // ---- Output & logging ---------------------------------------------------------------------
+    void prepare_output_filename(const std::string& method_params);
+    void compute_and_log_energy();
+    void log_point_probe();
+    void log_iterations(const unsigned int n_iterations_1, const unsigned int n_iterations_2);
+    void compute_and_log_error();
+    void compute_final_errors();
+    void compute_final_errors(const std::string& theta_str, const std::string& beta_str,
+                              const std::string& gamma_str);
+    void print_step_info();
+    void output() const;
+    bool check_divergence(const double norm_u, const double norm_v, const double threshold) const;
+    void close_logs();
+    void check(int status, const char* what) const;
+
+    // ---- Problem description --------------------------------------------------------------------
+    const std::string problem_name;
+    std::string output_folder;
+    std::ofstream energy_log_file;
+    std::ofstream error_log_file;
+    std::ofstream convergence_file;
+    std::ofstream iterations_log_file;
+    std::ofstream point_probe_log_file;
+
+    std::pair<unsigned int, unsigned int> N_el;
+    const std::pair<Point<dim>, Point<dim>> geometry;
+    const unsigned int r;
+
+    const double T;
+    const double delta_t;
+    double time = 0.0;
+    unsigned int timestep_number = 0;
+
+    double current_energy = 0.0;
+    double simulation_time = 0.0;
+    double norm_u = 0.0, norm_v = 0.0; // ||u||_2, ||v||_2 of the last step
+
+    const Function<dim>& c;
+    Function<dim>& f;
+    const Function<dim>& u0;
+    const Function<dim>& v0;
+    Function<dim>& g;
+    Function<dim>& dgdt;
+
+    const unsigned int log_every;
+    const unsigned int print_every;
+    Function<dim>* exact_solution;
+
+    // one process drives one GPU; the strip partition over several GPUs is configured through
+    // WAVE_RANK / WAVE_NRANKS by a launcher
+    const unsigned int mpi_size;
+    const unsigned int mpi_rank;
+
+    wave_ctx* ctx = nullptr;
+    ConditionalOStream pcout;
+};
+
+/// Format a double for folder names: fixed notation, trailing zeros stripped, '.' -> '_'
+/// (src/WaveEquationBase.cpp:433-452).
+std::string clean_double(double x, int precision = 6);
+
+#endif

@@ -1,0 +1,89 @@
+"""Multi-GPU parity (needs >= 2 GPUs, run with `gpurun --gpus 2`): the same run on 2 ranks (strip
+partition, NCCL halo exchange + all-reduces) must give the 1-rank answer to 1e-10 in the canonical
+numbering."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, nccl_id, name, scheme, over, nsteps, q):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "nmpde-wave-equation_b200"))
+    from wavegpu import WaveSolver, api, problem
+
+    torch.cuda.set_device(rank)
+    g = WaveSolver(problem(name, **over), scheme, rank=rank, nranks=world, nccl_id=nccl_id, device=rank)
+    g.init()
+    its = []
+    for _ in range(nsteps):
+        i, nrm = g.step()
+        its.append(i)
+    u, v = g.vector(api.VEC_U), g.vector(api.VEC_V)
+    e = g.energy()
+    err = g.errors() if g.has_solution else None
+    if rank == 0:
+        q.put((u, v, e, err, its, nrm))
+    g.close()
+
+
+CASES = [
+    ("standing-mode-wsol", "newmark", dict(Nel="24", R=2, Dt="0.01")),
+    ("standing-mode-wsol", "theta", dict(Nel="33, 17", R=1, Dt="0.02", Theta="0.5")),
+    ("sine-membrane", "newmark", dict(Nel="30, 10")),
+    ("ricker-wavelet", "theta", dict(Nel="16", R=2, Theta="1.0")),
+]
+
+
+@pytest.mark.parametrize("name,scheme,over", CASES)
+def test_two_ranks_match_one_rank(name, scheme, over):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    from wavegpu import WaveSolver, api, problem
+
+    nsteps = 12
+    g = WaveSolver(problem(name, **over), scheme)
+    g.init()
+    its1 = []
+    for _ in range(nsteps):
+        i, nrm1 = g.step()
+        its1.append(i)
+    u1, v1, e1 = g.vector(api.VEC_U), g.vector(api.VEC_V), g.energy()
+    err1 = g.errors() if g.has_solution else None
+    g.close()
+
+    nccl_id = api.comm_unique_id()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(rk, 2, nccl_id, name, scheme, over, nsteps, q)) for rk in range(2)]
+    for p in procs:
+        p.start()
+    u2, v2, e2, err2, its2, nrm2 = q.get(timeout=300)
+    for p in procs:
+        p.join(120)
+    assert all(p.exitcode == 0 for p in procs)
+    scale = max(np.abs(u1).max(), 1e-300)
+    assert np.abs(u2 - u1).max() <= 1e-10 * scale
+    assert np.abs(v2 - v1).max() <= 1e-10 * max(np.abs(v1).max(), 1e-300)
+    assert abs(e2 - e1) <= 1e-10 * max(abs(e1), 1e-300)
+    assert its2 == its1
+    assert np.allclose(nrm2, nrm1, rtol=1e-10)
+    if err1 is not None:
+        assert np.allclose([err2[0], err2[2]], [err1[0], err1[2]], rtol=1e-8)

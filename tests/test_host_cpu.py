@@ -1,0 +1,154 @@
+"""CPU-side tests (no GPU): the C ABI loads and exports every declared symbol, the expression
+compiler agrees with the oracle's independent evaluator, the closed-form DoF numbering equals the
+oracle's first-touch numbering, the partition plan is consistent, and the host executables keep
+the reference's error behaviour (src/main-newmark.cpp:92-102,155-166: message + exit code 1)."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from wavegpu import api, cell_dofs, partition_plan, problem
+from wavegpu.problems import NAMES, write_json
+
+ROOT = Path(__file__).resolve().parent.parent
+BIN = ROOT / "nmpde-wave-equation_b200" / "bin"
+
+
+def test_abi_exports_every_declared_symbol():
+    header = (ROOT / "include" / "wavegpu.h").read_text()
+    names = set(re.findall(r"\b(wave_[a-z0-9_]+)\s*\(", header))
+    names -= {"wave_status"}
+    L = api.lib()
+    assert len(names) > 35
+    for n in sorted(names):
+        assert hasattr(L, n), f"{n} declared in include/wavegpu.h but not exported"
+
+
+def test_no_device_fails_loudly():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("has a GPU")
+    with pytest.raises(api.WaveError) as ei:
+        api.WaveSolver(problem("standing-mode-wsol", Nel=4), "newmark")
+    assert ei.value.code == -3 and "no CPU fallback" in str(ei.value)
+
+
+@pytest.mark.parametrize("nx,ny,r", [(1, 1, 1), (1, 1, 2), (2, 1, 2), (1, 3, 2), (3, 2, 1), (5, 4, 2), (7, 3, 1),
+                                     (4, 6, 2), (16, 9, 2), (9, 16, 1)])
+def test_closed_form_numbering_is_first_touch(nx, ny, r):
+    """DoFHandler::distribute_dofs numbering: closed form == oracle's cell walk."""
+    o = O.Oracle.from_params(problem("standing-mode-wsol", Nel=f"{nx}, {ny}", R=r))
+    assert np.array_equal(cell_dofs(nx, ny, r), o.cell_dofs())
+
+
+def _expr(block):
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    L = api.lib()
+    L.wave_expr_create.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+    L.wave_expr_value.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+    L.wave_expr_value.restype = C.c_double
+    L.wave_expr_destroy.argtypes = [C.c_void_p]
+    L.wave_expr_destroy.restype = None
+    rc = L.wave_expr_create(block["Function expression"].encode(), block["Variable names"].encode(),
+                            block["Function constants"].encode(), C.byref(h), err, 512)
+    return rc, h, err.value.decode()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_expressions_match_oracle_evaluator(name):
+    p = problem(name, Nel=2)
+    o = O.Oracle.from_params(p)
+    rng = np.random.default_rng(11)
+    L = api.lib()
+    for i, blk in enumerate(O.EXPR_NAMES):
+        if blk not in p:
+            continue
+        rc, h, err = _expr(p[blk])
+        assert rc == 0, err
+        for _ in range(40):
+            x, y, t = rng.uniform(-1, 3), rng.uniform(-1, 3), rng.uniform(0, 2)
+            a = L.wave_expr_value(h, x, y, t)
+            b = o.eval(i, x, y, t)
+            assert a == pytest.approx(b, rel=1e-13, abs=1e-300), (blk, x, y, t)
+        L.wave_expr_destroy(h)
+
+
+@pytest.mark.parametrize("text,expect", [
+    ("2^3^2", 512.0), ("-2^2", -4.0), ("2^-1", 0.5), ("1 - 2 - 3", -4.0), ("8/4/2", 1.0),
+    ("if(1<2 && 3>=3, 10, 20)", 10.0), ("if(0 || 0, 1, 2)", 2.0), ("(1<2) + (2<=2) + (3>4)", 2.0),
+    ("max(min(3, 5), 4)", 4.0), ("1 ? 7 : 9", 7.0), ("abs(-3)*sign(-2)", -3.0), ("1e-3*1E3", 1.0),
+    ("sqrt(16)+exp(0)+cos(0)+tanh(0)+cosh(0)", 7.0), ("pow(2, 10)", 1024.0), ("pi", np.pi), ("k*pi", 4 * np.pi),
+])
+def test_expression_semantics(text, expect):
+    rc, h, err = _expr({"Function expression": text, "Variable names": "x, y, t", "Function constants": "k=4.0"})
+    assert rc == 0, err
+    assert api.lib().wave_expr_value(h, 0.3, 0.4, 0.5) == pytest.approx(expect, rel=1e-15)
+    api.lib().wave_expr_destroy(h)
+
+
+@pytest.mark.parametrize("text", ["", "sin(pi*x", "foo(x)", "x +* y", "1 +", "if(x, 1)", "q + 1", "x y"])
+def test_bad_expressions_are_rejected(text):
+    rc, h, err = _expr({"Function expression": text, "Variable names": "x, y", "Function constants": ""})
+    assert rc == -2 and err
+
+
+def test_constants_with_pi():
+    rc, h, err = _expr({"Function expression": "a+b+c", "Variable names": "x, y",
+                        "Function constants": "a=pi, b= 2.5*pi , c=1e-1"})
+    assert rc == 0, err
+    assert api.lib().wave_expr_value(h, 0, 0, 0) == pytest.approx(3.5 * np.pi + 0.1, rel=1e-15)
+
+
+@pytest.mark.parametrize("nx,ny,r,nranks", [(8, 8, 1, 2), (8, 8, 2, 3), (5, 9, 2, 4), (16, 8, 1, 8), (7, 2, 2, 2)])
+def test_partition_plan_is_consistent(nx, ny, r, nranks):
+    o = O.Oracle.from_params(problem("standing-mode-wsol", Nel=f"{nx}, {ny}", R=r))
+    rowptr, col = o.csr()
+    prev_end = 0
+    for rank in range(nranks):
+        p = partition_plan(nx, ny, r, rank, nranks)
+        assert p.row_begin == prev_end and p.row_end > p.row_begin
+        prev_end = p.row_end
+        assert p.ghost_lo_begin <= p.row_begin and p.ghost_hi_end >= p.row_end
+        cols = col[rowptr[p.row_begin]:rowptr[p.row_end]]
+        # every column an owned row touches lies inside the local (ghosted) range
+        assert cols.min() >= p.ghost_lo_begin and cols.max() < p.ghost_hi_end
+        # halos are whole blocks owned by the direct neighbours
+        if rank > 0:
+            lo = partition_plan(nx, ny, r, rank - 1, nranks)
+            assert lo.row_begin <= p.ghost_lo_begin < lo.row_end == p.row_begin
+        if rank < nranks - 1:
+            hi = partition_plan(nx, ny, r, rank + 1, nranks)
+            assert hi.row_begin == p.row_end < p.ghost_hi_end <= hi.row_end
+    assert prev_end == o.n
+
+
+def _run(exe, param_path, cwd):
+    return subprocess.run([str(BIN / exe), str(param_path)], cwd=cwd, capture_output=True, text=True, timeout=120)
+
+
+@pytest.mark.parametrize("exe", ["main-newmark", "main-theta"])
+def test_cli_error_behaviour(exe, tmp_path):
+    (tmp_path / "build").mkdir()
+    (tmp_path / "parameters").mkdir()
+    bad_num = {**problem("standing-mode-wsol"), "R": "abc"}
+    write_json(tmp_path / "parameters" / "bad-num.json", bad_num)
+    r = _run(exe, "../parameters/bad-num.json", tmp_path / "build")
+    assert r.returncode == 1 and "Error while parsing parameters/functions" in r.stdout
+    bad_expr = problem("standing-mode-wsol")
+    bad_expr["G"]["Function expression"] = ""
+    write_json(tmp_path / "parameters" / "bad-expr.json", bad_expr)
+    r = _run(exe, "../parameters/bad-expr.json", tmp_path / "build")
+    assert r.returncode == 1 and "Function expression for 'G' must be specified" in r.stdout
+    no_sol = problem("gaussian-pulse")  # Solution block absent: allowed
+    no_sol["Theta"] = "1.5"  # outside Patterns::Double(0, 1)
+    write_json(tmp_path / "parameters" / "range.json", no_sol)
+    r = _run(exe, "../parameters/range.json", tmp_path / "build")
+    assert r.returncode == 1
+    r = _run(exe, "../parameters/missing.json", tmp_path / "build")
+    assert r.returncode == 1 and "Unexpected error while parsing parameters" in r.stdout
