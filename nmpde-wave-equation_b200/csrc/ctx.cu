@@ -606,7 +606,7 @@ int wave_create(const wave_config *cfg, wave_ctx **out) {
     m.dx = (cfg->x1 - cfg->x0) / cfg->nx;
     m.dy = (cfg->y1 - cfg->y0) / cfg->ny;
     ctx->L = make_layout(m, cfg->rank, cfg->nranks);
-    if ((int64_t)ctx->L.nloc * 19 >= (1LL << 32)) {
+    if ((int64_t)ctx->L.nloc * (cfg->r == 1 ? 7 : 12) >= (1LL << 32)) {  // padded entries must fit uint32 offsets
         ctx->err = "local problem exceeds 32-bit CSR offsets: partition over more GPUs";
         return bail(WAVE_ERR_UNSUPPORTED);
     }

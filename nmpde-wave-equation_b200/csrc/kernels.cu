@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include <cub/block/block_radix_sort.cuh>
 
@@ -396,8 +397,8 @@ __global__ void k_bc_values(int mode, int nb, const int32_t *brow, const double 
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
 
-template <int NT, bool TWOX, int CH>
-__global__ void __launch_bounds__(kThreads, 4) k_spmv(SpmvArgs a) {
+template <int NT, bool TWOX, int CH, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_spmv(SpmvArgs a) {
     if (a.skip_flag && *a.skip_flag != 0) return;
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (kThreads / 32);
@@ -781,21 +782,42 @@ static int persistent_grid(Kernel kernel, int64_t blocks_needed) {
     const int64_t cap = (int64_t)kSMs * occ;
     return (int)(blocks_needed < cap ? (blocks_needed > 0 ? blocks_needed : 1) : cap);
 }
-template <int NT, bool TWOX, int CH>
+template <int NT, bool TWOX, int CH, int MINB>
 static void launch_spmv_t(const Launcher &l, const SpmvArgs &a) {
     static int grid_cap = 0;
-    if (!grid_cap) grid_cap = persistent_grid(k_spmv<NT, TWOX, CH>, 1 << 30);
+    if (!grid_cap) grid_cap = persistent_grid(k_spmv<NT, TWOX, CH, MINB>, 1 << 30);
     const int64_t need = blocks_for((int64_t)a.A.nslices * kSlice, kThreads);
-    WV_LAUNCH(l, (k_spmv<NT, TWOX, CH>), (int)std::min<int64_t>(need, grid_cap), kThreads, 0, a);
+    WV_LAUNCH(l, (k_spmv<NT, TWOX, CH, MINB>), (int)std::min<int64_t>(need, grid_cap), kThreads, 0, a);
+}
+static int spmv_variant() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("WAVE_SPMV_VARIANT"); v = e ? atoi(e) : 0; }
+    return v;
 }
 // chunk = the dominant row length of the element: P1 rows hold 7 entries, P2 rows 19 / 9
 void launch_spmv(const Launcher &l, const SpmvArgs &a) {
     const bool two_terms = a.t[1].val != nullptr;
     const bool twox = a.t[0].xb != nullptr || (two_terms && a.t[1].xb != nullptr);
     const bool p1 = a.A.chunk <= 7;
-    if (!two_terms && !twox) { if (p1) launch_spmv_t<1, false, 7>(l, a); else launch_spmv_t<1, false, 10>(l, a); }
-    else if (!two_terms) { if (p1) launch_spmv_t<1, true, 7>(l, a); else launch_spmv_t<1, true, 10>(l, a); }
-    else { if (p1) launch_spmv_t<2, true, 7>(l, a); else launch_spmv_t<2, true, 10>(l, a); }
+    if (!two_terms && !twox) {
+        if (p1) {
+            switch (spmv_variant()) {
+            case 1: launch_spmv_t<1, false, 7, 3>(l, a); break;
+            case 2: launch_spmv_t<1, false, 7, 2>(l, a); break;
+            case 3: launch_spmv_t<1, false, 7, 5>(l, a); break;
+            default: launch_spmv_t<1, false, 7, 4>(l, a);
+            }
+        } else {
+            switch (spmv_variant()) {
+            case 1: launch_spmv_t<1, false, 19, 3>(l, a); break;
+            case 2: launch_spmv_t<1, false, 10, 2>(l, a); break;
+            case 3: launch_spmv_t<1, false, 19, 2>(l, a); break;
+            default: launch_spmv_t<1, false, 19, 1>(l, a);
+            }
+        }
+    }
+    else if (!two_terms) { if (p1) launch_spmv_t<1, true, 7, 4>(l, a); else launch_spmv_t<1, true, 10, 4>(l, a); }
+    else { if (p1) launch_spmv_t<2, true, 7, 4>(l, a); else launch_spmv_t<2, true, 10, 4>(l, a); }
 }
 void launch_zero_rows(const Launcher &l, int nb, const int32_t *brow, double *vec) {
     if (nb <= 0) return;
