@@ -96,6 +96,9 @@ struct wave_ctx {
     uint32_t *rowptr = nullptr;
     uint32_t *slice_ptr = nullptr;
     int32_t *col = nullptr, *row_of = nullptr, *slot_of = nullptr;
+    int32_t *c2i = nullptr, *i2c = nullptr;  // canonical <-> storage numbering of the local range (P2)
+    bool permuted = false;
+    double *tmp = nullptr;                   // nloc staging for the permutation at the ABI
     int nslices = 0;
     int64_t nnz = 0;      // entries of the pattern (CSR)
     int64_t nnz_pad = 0;  // stored entries including padding
@@ -510,12 +513,34 @@ int ensure_scratch(wave_ctx *ctx, int64_t n) {
     return WAVE_OK;
 }
 
+// canonical local-range vector (device) -> storage order
+int to_storage(wave_ctx *ctx, const double *canon_local, double *dst_local) {
+    const Layout &L = ctx->L;
+    if (ctx->permuted) launch_gather(ctx->launcher, L.nloc, ctx->i2c, canon_local, dst_local);
+    else CK(cudaMemcpyAsync(dst_local, canon_local, sizeof(double) * L.nloc, cudaMemcpyDeviceToDevice, ctx->stream));
+    return WAVE_OK;
+}
+// row-indexed (owned, storage order) vector -> canonical order of the owned rows
+int own_to_canonical(wave_ctx *ctx, const double *src_own, double *dst_own) {
+    const Layout &L = ctx->L;
+    if (ctx->permuted) launch_gather(ctx->launcher, L.nown, ctx->c2i + L.own_off, src_own - L.own_off, dst_own);
+    else CK(cudaMemcpyAsync(dst_own, src_own, sizeof(double) * L.nown, cudaMemcpyDeviceToDevice, ctx->stream));
+    return WAVE_OK;
+}
+int upload_local(wave_ctx *ctx, const double *host_global, double *dst_local) {
+    const Layout &L = ctx->L;
+    double *stage = ctx->permuted ? ctx->tmp : dst_local;
+    CK(cudaMemcpyAsync(stage, host_global + L.col0, sizeof(double) * L.nloc, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->permuted) RET(to_storage(ctx, stage, dst_local));
+    return WAVE_OK;
+}
+
 // owned part of a local-layout vector -> all ranks' canonical vector in device scratch
 int gather_global(wave_ctx *ctx, const double *own_src) {
     const int64_t n = n_dofs(ctx->L.mesh);
     RET(ensure_scratch(ctx, n));
     const Layout &L = ctx->L;
-    CK(cudaMemcpyAsync(ctx->scratch + L.row0, own_src, sizeof(double) * L.nown, cudaMemcpyDeviceToDevice, ctx->stream));
+    RET(own_to_canonical(ctx, own_src, ctx->scratch + L.row0));
     if (ctx->cfg.nranks > 1) {
         for (int r = 0; r < ctx->cfg.nranks; ++r) {
             const Layout Lr = make_layout(L.mesh, r, ctx->cfg.nranks);
@@ -631,7 +656,7 @@ int wave_create(const wave_config *cfg, wave_ctx **out) {
 void wave_destroy(wave_ctx *ctx) {
     if (!ctx) return;
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void *ptrs[] = {ctx->dprog, ctx->rowptr, ctx->slice_ptr, ctx->row_of, ctx->slot_of, ctx->col, ctx->M, ctx->K, ctx->S1, ctx->S2, ctx->dinv1, ctx->dinv2,
+    void *ptrs[] = {ctx->dprog, ctx->rowptr, ctx->slice_ptr, ctx->row_of, ctx->slot_of, ctx->col, ctx->c2i, ctx->i2c, ctx->tmp, ctx->M, ctx->K, ctx->S1, ctx->S2, ctx->dinv1, ctx->dinv2,
                     ctx->d0, ctx->u, ctx->v, ctx->a, ctx->unew, ctx->d, ctx->rhs, ctx->fvec, ctx->g, ctx->h,
                     ctx->scratch, ctx->brow, ctx->bx, ctx->by, ctx->partials, ctx->counter, ctx->S, ctx->res,
                     ctx->flush_buf};
@@ -707,6 +732,15 @@ int wave_setup(wave_ctx *ctx) {
     ctx->forcing_active = !(is_constant(ctx->hprog[WAVE_EXPR_F], &fconst) && fconst == 0.0) ||
                           (ctx->cfg.flags & WAVE_FLAG_FORCING_EVERY_STEP);
 
+    // ---- storage numbering (kind-major inside each block for P2, see mesh.h) -------------------------
+    ctx->permuted = L.mesh.r == 2;
+    RET(dev_alloc(ctx, &ctx->tmp, (size_t)L.nloc));
+    if (ctx->permuted) {
+        RET(dev_alloc(ctx, &ctx->c2i, (size_t)L.nloc, false));
+        RET(dev_alloc(ctx, &ctx->i2c, (size_t)L.nloc, false));
+        launch_build_perm(l, L, ctx->c2i, ctx->i2c);
+    }
+
     // ---- sparsity: row lengths -> CSR row pointer; window sort -> SELL slices -> columns ----------
     const int nslots = ((L.nown + kWindow - 1) / kWindow) * kWindow;
     ctx->nslices = nslots / kSlice;
@@ -754,7 +788,7 @@ int wave_setup(wave_ctx *ctx) {
     // ---- boundary list (closed form, host) --------------------------------------------------------
     {
         const Mesh &m = L.mesh;
-        struct B { int64_t dof; double x, y; };
+        struct B { int64_t dof, idof; double x, y; };
         std::vector<B> mine;
         ctx->h_bdof_global.clear();
         const int nk = m.r == 1 ? 1 : 4;
@@ -770,7 +804,7 @@ int wave_setup(wave_ctx *ctx) {
                     if (dof >= L.row0 && dof < L.row0 + L.nown) {
                         double x, y;
                         entity_point(m, i, j, kind, x, y);
-                        mine.push_back({dof, x, y});
+                        mine.push_back({dof, entity_dof_internal(m, i, j, kind), x, y});
                     }
                 }
             }
@@ -782,7 +816,7 @@ int wave_setup(wave_ctx *ctx) {
         std::vector<int32_t> hrow(mine.size());
         std::vector<double> hx(mine.size()), hy(mine.size());
         for (size_t k = 0; k < mine.size(); ++k) {
-            hrow[k] = (int32_t)(mine[k].dof - L.row0);
+            hrow[k] = (int32_t)(mine[k].idof - L.row0);  // storage row
             hx[k] = mine[k].x;
             hy[k] = mine[k].y;
         }
@@ -914,7 +948,7 @@ int wave_set_vector(wave_ctx *ctx, int which, const double *host, size_t n) {
     double *dst = vec_ptr(ctx, which);
     if (!dst || !host || (int64_t)n != n_dofs(ctx->L.mesh)) return fail(ctx, WAVE_ERR_ARG, "bad vector id or size");
     // every rank takes its local slice (ghosts included) straight from the canonical host array
-    CK(cudaMemcpyAsync(dst, host + ctx->L.col0, sizeof(double) * ctx->L.nloc, cudaMemcpyHostToDevice, ctx->stream));
+    RET(upload_local(ctx, host, dst));
     CK(cudaStreamSynchronize(ctx->stream));
     return WAVE_OK;
 }
@@ -925,13 +959,15 @@ int wave_get_vector(wave_ctx *ctx, int which, double *host, size_t n) {
     const double *src = which == WAVE_VEC_RHS ? ctx->rhs : (vec_ptr(ctx, which) ? vec_ptr(ctx, which) + L.own_off : nullptr);
     if (!src || !host) return fail(ctx, WAVE_ERR_ARG, "bad vector id");
     if ((int64_t)n == (int64_t)L.nown && ctx->cfg.nranks > 1) {
-        CK(cudaMemcpyAsync(host, src, sizeof(double) * L.nown, cudaMemcpyDeviceToHost, ctx->stream));
+        RET(own_to_canonical(ctx, src, ctx->tmp));
+        CK(cudaMemcpyAsync(host, ctx->tmp, sizeof(double) * L.nown, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         return WAVE_OK;
     }
     if ((int64_t)n != n_dofs(L.mesh)) return fail(ctx, WAVE_ERR_ARG, "bad vector size");
     if (ctx->cfg.nranks == 1) {
-        CK(cudaMemcpyAsync(host, src, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        RET(own_to_canonical(ctx, src, ctx->tmp));
+        CK(cudaMemcpyAsync(host, ctx->tmp, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     } else {
         RET(gather_global(ctx, src));
         CK(cudaMemcpyAsync(host, ctx->scratch, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -944,11 +980,12 @@ int wave_step_host(wave_ctx *ctx, double t_np1, double *u, double *v, double *a,
     if (!ctx || !ctx->is_init) return fail(ctx, WAVE_ERR_STATE, "wave_step_host before wave_init");
     const size_t n = (size_t)n_dofs(ctx->L.mesh);
     const Layout &L = ctx->L;
-    CK(cudaMemcpyAsync(ctx->u, u + L.col0, sizeof(double) * L.nloc, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->v, v + L.col0, sizeof(double) * L.nloc, cudaMemcpyHostToDevice, ctx->stream));
+    (void)L;
+    RET(upload_local(ctx, u, ctx->u));
+    RET(upload_local(ctx, v, ctx->v));
     if (ctx->cfg.scheme == WAVE_SCHEME_NEWMARK) {
         if (!a) return fail(ctx, WAVE_ERR_ARG, "Newmark needs the acceleration vector");
-        CK(cudaMemcpyAsync(ctx->a, a + L.col0, sizeof(double) * L.nloc, cudaMemcpyHostToDevice, ctx->stream));
+        RET(upload_local(ctx, a, ctx->a));
     }
     RET(wave_step(ctx, t_np1, iters, norms));
     RET(wave_get_vector(ctx, WAVE_VEC_U, u, n));
@@ -1036,22 +1073,39 @@ int wave_get_csr(wave_ctx *ctx, int which, int64_t *rowptr, int32_t *col, double
     const Layout &L = ctx->L;
     const double *src = mat_ptr(ctx, which);
     if (val && !src) return fail(ctx, WAVE_ERR_ARG, "matrix not available for this scheme");
-    std::vector<uint32_t> rp((size_t)L.nown + 1);
-    CK(cudaMemcpy(rp.data(), ctx->rowptr, sizeof(uint32_t) * rp.size(), cudaMemcpyDeviceToHost));
-    if (rowptr)
+    // canonical row pointer: lengths of the storage rows in canonical row order, then a scan
+    uint32_t *len_c = nullptr, *rp_c = nullptr;
+    RET(dev_alloc(ctx, &len_c, (size_t)L.nown + 1));
+    RET(dev_alloc(ctx, &rp_c, (size_t)L.nown + 1));
+    launch_canonical_lengths(ctx->launcher, L, ctx->A, ctx->c2i, len_c);
+    {
+        void *tmp = nullptr;
+        size_t bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, len_c, rp_c, L.nown + 1, ctx->stream));
+        CK(cudaMalloc(&tmp, bytes));
+        CK(cub::DeviceScan::ExclusiveSum(tmp, bytes, len_c, rp_c, L.nown + 1, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaFree(tmp));
+    }
+    if (rowptr) {
+        std::vector<uint32_t> rp((size_t)L.nown + 1);
+        CK(cudaMemcpy(rp.data(), rp_c, sizeof(uint32_t) * rp.size(), cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < rp.size(); ++i) rowptr[i] = rp[i];
+    }
     if (col || val) {
         double *dval = nullptr;
         int32_t *dcol = nullptr;
         if (val) RET(dev_alloc(ctx, &dval, (size_t)ctx->nnz, false));
         if (col) RET(dev_alloc(ctx, &dcol, (size_t)ctx->nnz, false));
-        launch_export_csr(ctx->launcher, L, ctx->A, src ? src : ctx->M, dval, dcol);
+        launch_export_csr(ctx->launcher, L, ctx->A, ctx->c2i, ctx->i2c, rp_c, src ? src : ctx->M, dval, dcol);
         if (val) CK(cudaMemcpyAsync(val, dval, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost, ctx->stream));
         if (col) CK(cudaMemcpyAsync(col, dcol, sizeof(int32_t) * ctx->nnz, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         if (dval) cudaFree(dval);
         if (dcol) cudaFree(dcol);
     }
+    cudaFree(len_c);
+    cudaFree(rp_c);
     return WAVE_OK;
 }
 
@@ -1083,12 +1137,13 @@ int wave_spmv(wave_ctx *ctx, int which, const double *x, double *y, size_t n) {
     const double *val = mat_ptr(ctx, which);
     if (!val || ctx->cfg.nranks != 1 || (int64_t)n != n_dofs(ctx->L.mesh))
         return fail(ctx, WAVE_ERR_ARG, "wave_spmv: single rank, n = n_dofs, valid matrix id");
-    CK(cudaMemcpyAsync(ctx->d, x, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    RET(upload_local(ctx, x, ctx->d));
     SpmvArgs a = spmv_base(ctx);
     a.t[0] = {val, ctx->d, nullptr, 1.0, 0.0, 1.0};
     a.y = ctx->h;
     launch_spmv(ctx->launcher, a);
-    CK(cudaMemcpyAsync(y, ctx->h, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    RET(own_to_canonical(ctx, ctx->h, ctx->tmp));
+    CK(cudaMemcpyAsync(y, ctx->tmp, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     return sync_check(ctx);
 }
 
@@ -1099,14 +1154,16 @@ int wave_cg(wave_ctx *ctx, int which, double *x, const double *b, size_t n, int3
         (which != WAVE_MAT_SYS1 && which != WAVE_MAT_SYS2))
         return fail(ctx, WAVE_ERR_ARG, "wave_cg: single rank, n = n_dofs, SYS1 or SYS2");
     const double *dinv = which == WAVE_MAT_SYS1 ? ctx->dinv1 : ctx->dinv2;
-    CK(cudaMemcpyAsync(ctx->unew, x, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->rhs, b, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    RET(upload_local(ctx, x, ctx->unew));
+    RET(upload_local(ctx, b, ctx->fvec));  // single rank: nloc == nown
+    CK(cudaMemcpyAsync(ctx->rhs, ctx->fvec, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
     int its = 0;
     ctx->prev_its[0] = 0;
     const int rc = cg_solve(ctx, val, dinv, ctx->unew, ctx->rhs, 0, &its);
     ctx->prev_its[0] = 0;
     if (iters) *iters = its;
-    CK(cudaMemcpyAsync(x, ctx->unew, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    RET(own_to_canonical(ctx, ctx->unew, ctx->tmp));
+    CK(cudaMemcpyAsync(x, ctx->tmp, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return rc;
 }

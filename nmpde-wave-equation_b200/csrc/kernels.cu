@@ -87,22 +87,25 @@ __device__ __forceinline__ bool last_block_done(unsigned *counter) {
 
 // ---- sparsity pattern: DoFTools::make_sparsity_pattern + compress (src/WaveNewmark.cpp:33-35) ----
 // One thread per entity slot; the row is the sorted union of the DoFs of the adjacent cells.
-__device__ int build_row(const Mesh &m, int i, int j, int kind, int64_t *cols) {
+// cols: canonical ids in ascending order (the CSR order); icols: the same entries' storage ids
+__device__ int build_row(const Mesh &m, int i, int j, int kind, int64_t *cols, int64_t *icols) {
     int64_t cells[6];
     const int nc = entity_cells(m, i, j, kind, cells);
     const int dpc = dofs_per_cell(m.r);
     int n = 0;
     for (int c = 0; c < nc; ++c) {
-        int64_t d[6];
+        int64_t d[6], di[6];
         cell_dofs(m, cells[c], d);
+        cell_dofs_internal(m, cells[c], di);
         for (int k = 0; k < dpc; ++k) {
             // sorted insert, skip duplicates
             const int64_t v = d[k];
             int p = n;
             while (p > 0 && cols[p - 1] > v) --p;
             if (p > 0 && cols[p - 1] == v) continue;
-            for (int q = n; q > p; --q) cols[q] = cols[q - 1];
+            for (int q = n; q > p; --q) { cols[q] = cols[q - 1]; icols[q] = icols[q - 1]; }
             cols[p] = v;
+            icols[p] = di[k];
             ++n;
         }
     }
@@ -137,10 +140,10 @@ __global__ void k_row_lengths(Layout L, uint32_t *rowlen) {
     if (t >= slot_count(L, s)) return;
     int i, j, kind;
     decode_slot(L, s, t, i, j, kind);
-    const int64_t dof = entity_dof(L.mesh, i, j, kind);
+    const int64_t dof = entity_dof_internal(L.mesh, i, j, kind);
     if (dof < L.row0 || dof >= L.row0 + L.nown) return;
-    int64_t cols[kMaxRow];
-    rowlen[dof - L.row0] = (uint32_t)build_row(L.mesh, i, j, kind, cols);
+    int64_t cols[kMaxRow], icols[kMaxRow];
+    rowlen[dof - L.row0] = (uint32_t)build_row(L.mesh, i, j, kind, cols, icols);
 }
 
 // ---- SELL-32-sigma construction --------------------------------------------------------------------
@@ -190,35 +193,63 @@ __global__ void k_fill_cols(Layout L, Sell A, int32_t *col) {
     if (t >= slot_count(L, s)) return;
     int i, j, kind;
     decode_slot(L, s, t, i, j, kind);
-    const int64_t dof = entity_dof(L.mesh, i, j, kind);
+    const int64_t dof = entity_dof_internal(L.mesh, i, j, kind);
     if (dof < L.row0 || dof >= L.row0 + L.nown) return;
-    int64_t cols[kMaxRow];
-    const int n = build_row(L.mesh, i, j, kind, cols);
+    int64_t cols[kMaxRow], icols[kMaxRow];
+    const int n = build_row(L.mesh, i, j, kind, cols, icols);
     const uint32_t base = sell_row_base(A, (int)(dof - L.row0));
-    for (int k = 0; k < n; ++k) col[base + kSlice * k] = (int32_t)(cols[k] - L.col0);
+    for (int k = 0; k < n; ++k) col[base + kSlice * k] = (int32_t)(icols[k] - L.col0);
 }
 
-// position of (row, local column c) in the padded arrays; the row's entries are sorted ascending
+// position of (row, local storage column c) in the padded arrays; rows are short (<= 19 entries) and
+// ordered by canonical column, so the storage ids are searched linearly
 __device__ __forceinline__ uint32_t find_col(const Sell &A, int row, int32_t c) {
-    const uint32_t base = sell_row_base(A, row);
-    uint32_t lo = 0, hi = sell_row_len(A, row);
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        const int32_t v = A.col[base + kSlice * mid];
-        if (v == c) return base + kSlice * mid;
-        if (v < c) lo = mid + 1; else hi = mid;
-    }
+    const uint32_t base = sell_row_base(A, row), len = sell_row_len(A, row);
+    for (uint32_t k = 0; k < len; ++k)
+        if (A.col[base + kSlice * k] == c) return base + kSlice * k;
     return 0xffffffffu;
 }
 
-__global__ void k_export_csr(Layout L, Sell A, const double *val, double *csr_val, int32_t *csr_col) {
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= L.nown) return;
-    const uint32_t base = sell_row_base(A, row), len = sell_row_len(A, row), o = A.rowptr[row];
+// canonical row lengths (for the exported CSR row pointer), then the export itself: canonical row r is
+// storage row c2i[r]; its entries are already in ascending canonical column order
+__global__ void k_canonical_lengths(Layout L, Sell A, const int32_t *c2i, uint32_t *len) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= L.nown) return;
+    const int row = (c2i ? c2i[r + L.own_off] : r + L.own_off) - L.own_off;
+    len[r] = sell_row_len(A, row);
+}
+__global__ void k_export_csr(Layout L, Sell A, const int32_t *c2i, const int32_t *i2c, const uint32_t *rowptr_c,
+                             const double *val, double *csr_val, int32_t *csr_col) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= L.nown) return;
+    const int row = (c2i ? c2i[r + L.own_off] : r + L.own_off) - L.own_off;
+    const uint32_t base = sell_row_base(A, row), len = sell_row_len(A, row), o = rowptr_c[r];
     for (uint32_t k = 0; k < len; ++k) {
         if (csr_val) csr_val[o + k] = val[base + kSlice * k];
-        if (csr_col) csr_col[o + k] = (int32_t)(A.col[base + kSlice * k] + L.col0);
+        if (csr_col) {
+            const int32_t ic = A.col[base + kSlice * k];
+            csr_col[o + k] = (int32_t)((i2c ? i2c[ic] : ic) + L.col0);
+        }
     }
+}
+// storage <-> canonical permutation of the local range (identity for P1)
+__global__ void k_build_perm(Layout L, int32_t *c2i, int32_t *i2c) {
+    const SlotRange s = local_slots(L);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= slot_count(L, s)) return;
+    int i, j, kind;
+    decode_slot(L, s, tid, i, j, kind);
+    const int64_t c = entity_dof(L.mesh, i, j, kind);
+    if (c < L.col0 || c >= L.col0 + L.nloc) return;
+    const int64_t t = entity_dof_internal(L.mesh, i, j, kind);
+    c2i[c - L.col0] = (int32_t)(t - L.col0);
+    i2c[t - L.col0] = (int32_t)(c - L.col0);
+}
+// dst[i] = src[map[i]]
+__global__ void __launch_bounds__(kThreads) k_gather(int n, const int32_t *__restrict__ map,
+                                                     const double *__restrict__ src, double *__restrict__ dst) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[map[i]];
 }
 
 // ---- K1: assemble_matrices (src/WaveNewmark.cpp:56-108 == src/WaveTheta.cpp:56-108) ---------------
@@ -260,7 +291,7 @@ __global__ void __launch_bounds__(128) k_assemble(Layout L, const Program *cprog
             }
     }
     int64_t d[6];
-    cell_dofs(L.mesh, cell, d);
+    cell_dofs_internal(L.mesh, cell, d);
 #pragma unroll
     for (int a = 0; a < DPC; ++a) {
         const int64_t row = d[a] - L.row0;
@@ -322,8 +353,8 @@ __global__ void k_interpolate(Layout L, const Program *p, double t, double *vec,
     if (dof < L.col0 || dof >= L.col0 + L.nloc) return;
     double x, y;
     entity_point(L.mesh, i, j, kind, x, y);
-    if (vec) vec[dof - L.col0] = eval(p, x, y, t);
-    if (sx) { sx[dof - L.col0] = x; sy[dof - L.col0] = y; }
+    if (vec) vec[entity_dof_internal(L.mesh, i, j, kind) - L.col0] = eval(p, x, y, t);  // storage order
+    if (sx) { sx[dof - L.col0] = x; sy[dof - L.col0] = y; }                             // canonical order
 }
 
 // ---- K4: forcing load vector (src/WaveNewmark.cpp:151-171, src/WaveTheta.cpp:151-180) ---------------
@@ -358,7 +389,7 @@ __global__ void __launch_bounds__(128) k_forcing(Layout L, const Program *f, Qua
         for (int a = 0; a < DPC; ++a) acc[a] += fv * phi[a] * JxW;
     }
     int64_t d[6];
-    cell_dofs(L.mesh, cell, d);
+    cell_dofs_internal(L.mesh, cell, d);
 #pragma unroll
     for (int a = 0; a < DPC; ++a) {
         const int64_t row = d[a] - L.row0;
@@ -609,7 +640,7 @@ __global__ void __launch_bounds__(128) k_errors(Layout L, const Program *sol, Qu
         const double det = sx * sy, adet = fabs(det);
         const double ix = sy / det, iy = sx / det;
         int64_t d[6];
-        cell_dofs(L.mesh, cell, d);
+        cell_dofs_internal(L.mesh, cell, d);
         double ul[DPC];
 #pragma unroll
         for (int a = 0; a < DPC; ++a) ul[a] = u[d[a] - L.col0];
@@ -675,7 +706,7 @@ __global__ void k_probe(Layout L, double px, double py, const double *u, double 
                         double phi[6];
                         int64_t d[6];
                         shape_values(m.r, xi, eta, phi);
-                        cell_dofs(m, cell, d);
+                        cell_dofs_internal(m, cell, d);
                         for (int a = 0; a < dofs_per_cell(m.r); ++a) val += u[d[a] - L.col0] * phi[a];
                     }
                 }
@@ -727,9 +758,21 @@ void launch_fill_cols(const Launcher &l, const Layout &L, const Sell &A, int32_t
     const int64_t n = slot_count(L, owned_slots(L));
     WV_LAUNCH(l, k_fill_cols, blocks_for(n, 128), 128, 0, L, A, col);
 }
-void launch_export_csr(const Launcher &l, const Layout &L, const Sell &A, const double *val, double *csr_val,
-                       int32_t *csr_col) {
-    WV_LAUNCH(l, k_export_csr, blocks_for(L.nown, kThreads), kThreads, 0, L, A, val, csr_val, csr_col);
+void launch_canonical_lengths(const Launcher &l, const Layout &L, const Sell &A, const int32_t *c2i, uint32_t *len) {
+    WV_LAUNCH(l, k_canonical_lengths, blocks_for(L.nown, kThreads), kThreads, 0, L, A, c2i, len);
+}
+void launch_export_csr(const Launcher &l, const Layout &L, const Sell &A, const int32_t *c2i, const int32_t *i2c,
+                       const uint32_t *rowptr_c, const double *val, double *csr_val, int32_t *csr_col) {
+    WV_LAUNCH(l, k_export_csr, blocks_for(L.nown, kThreads), kThreads, 0, L, A, c2i, i2c, rowptr_c, val, csr_val,
+              csr_col);
+}
+void launch_build_perm(const Launcher &l, const Layout &L, int32_t *c2i, int32_t *i2c) {
+    const int64_t n = slot_count(L, local_slots(L));
+    WV_LAUNCH(l, k_build_perm, blocks_for(n, 128), 128, 0, L, c2i, i2c);
+}
+void launch_gather(const Launcher &l, int n, const int32_t *map, const double *src, double *dst) {
+    if (n <= 0) return;
+    WV_LAUNCH(l, k_gather, stream_blocks(n), kThreads, 0, n, map, src, dst);
 }
 static int64_t assembly_cells(const Layout &L) {
     const int jtop = L.jq1 < L.mesh.ny ? L.jq1 : L.mesh.ny - 1;

@@ -109,8 +109,12 @@ void launch_bc_rows(const Launcher &, const Layout &, int nb, const int32_t *bro
                     const double *d0);
 void launch_dinv(const Launcher &, const Layout &, const Sell &A, const double *val, int identity, double *dinv);
 // SELL -> CSR export of one value array and of the (global) column indices
-void launch_export_csr(const Launcher &, const Layout &, const Sell &A, const double *val, double *csr_val,
-                       int32_t *csr_col);
+void launch_canonical_lengths(const Launcher &, const Layout &, const Sell &A, const int32_t *c2i, uint32_t *len);
+void launch_export_csr(const Launcher &, const Layout &, const Sell &A, const int32_t *c2i, const int32_t *i2c,
+                       const uint32_t *rowptr_c, const double *val, double *csr_val, int32_t *csr_col);
+// storage <-> canonical maps of the local range (P2 only) and dst[i] = src[map[i]]
+void launch_build_perm(const Launcher &, const Layout &, int32_t *c2i, int32_t *i2c);
+void launch_gather(const Launcher &, int n, const int32_t *map, const double *src, double *dst);
 void launch_interpolate(const Launcher &, const Layout &, const Program *p, double t, double *vec,
                         double *sx, double *sy);
 void launch_forcing(const Launcher &, const Layout &, const Program *f, const Quadrature *q, double t_np1,

@@ -91,6 +91,44 @@ WV_HD void cell_dofs(const Mesh &m, int64_t cell, int64_t *d) {
     }
 }
 
+// ---- internal (storage) numbering ---------------------------------------------------------------
+// Vectors and matrix rows are stored in a permutation of the canonical numbering that keeps every
+// block [block_start(j), block_start(j+1)) but lists its DoFs kind by kind (all vertices of the line,
+// then the horizontal, vertical and diagonal edge DoFs, each in ascending i).  Neighbouring DoFs of
+// one kind are then neighbours in memory, so the k-th column of 32 consecutive rows is a contiguous
+// run: SpMV gathers coalesce for P2 as they do for P1.  For r == 1 the internal numbering is the
+// canonical one.  The C ABI speaks canonical numbering only (wave_get_vector / wave_get_csr permute).
+WV_HD int64_t idof_V(const Mesh &m, int i, int j) {
+    if (m.r == 1) return dof_V(m, i, j);
+    if (j == 0) return i;
+    if (j == 1) return (int64_t)(m.nx + 1) + i;
+    return block_start(m, j - 1) + i;
+}
+WV_HD int64_t idof_B(const Mesh &m, int i, int j) {
+    if (j == 0) return 2 * (int64_t)(m.nx + 1) + i;
+    if (j == 1) return 2 * (int64_t)(m.nx + 1) + m.nx + i;
+    return block_start(m, j - 1) + (m.nx + 1) + i;
+}
+WV_HD int64_t idof_L(const Mesh &m, int i, int j) {
+    if (j == 0) return 2 * (int64_t)(m.nx + 1) + 2 * (int64_t)m.nx + i;
+    return block_start(m, j) + (m.nx + 1) + m.nx + i;
+}
+WV_HD int64_t idof_D(const Mesh &m, int i, int j) {
+    if (j == 0) return 2 * (int64_t)(m.nx + 1) + 2 * (int64_t)m.nx + (m.nx + 1) + i;
+    return block_start(m, j) + (m.nx + 1) + m.nx + (m.nx + 1) + i;
+}
+WV_HD void cell_dofs_internal(const Mesh &m, int64_t cell, int64_t *d) {
+    const int64_t q = cell >> 1;
+    const int j = (int)(q / m.nx), i = (int)(q - (int64_t)j * m.nx);
+    if ((cell & 1) == 0) {
+        d[0] = idof_V(m, i, j); d[1] = idof_V(m, i + 1, j); d[2] = idof_V(m, i, j + 1);
+        if (m.r == 2) { d[3] = idof_B(m, i, j); d[4] = idof_D(m, i, j); d[5] = idof_L(m, i, j); }
+    } else {
+        d[0] = idof_V(m, i + 1, j + 1); d[1] = idof_V(m, i, j + 1); d[2] = idof_V(m, i + 1, j);
+        if (m.r == 2) { d[3] = idof_B(m, i, j + 1); d[4] = idof_D(m, i, j); d[5] = idof_L(m, i + 1, j); }
+    }
+}
+
 // affine geometry of a cell: origin (v0), and the diagonal Jacobian (sx, sy) with x = X0 + sx*xi,
 // y = Y0 + sy*eta.  T0: (dx, dy); T1: (-dx, -dy).  |det J| = dx*dy for both.
 WV_HD void cell_geometry(const Mesh &m, int64_t cell, double &X0, double &Y0, double &sx, double &sy) {
@@ -113,6 +151,14 @@ WV_HD int64_t entity_dof(const Mesh &m, int i, int j, int kind) {
     case 1: return (m.r == 2 && i < m.nx) ? dof_B(m, i, j) : -1;
     case 2: return (m.r == 2 && j < m.ny) ? dof_L(m, i, j) : -1;
     default: return (m.r == 2 && i < m.nx && j < m.ny) ? dof_D(m, i, j) : -1;
+    }
+}
+WV_HD int64_t entity_dof_internal(const Mesh &m, int i, int j, int kind) {
+    switch (kind) {
+    case 0: return idof_V(m, i, j);
+    case 1: return (m.r == 2 && i < m.nx) ? idof_B(m, i, j) : -1;
+    case 2: return (m.r == 2 && j < m.ny) ? idof_L(m, i, j) : -1;
+    default: return (m.r == 2 && i < m.nx && j < m.ny) ? idof_D(m, i, j) : -1;
     }
 }
 // support point of an entity (vertex, or edge midpoint as the mean of its two vertices)
