@@ -40,6 +40,7 @@ WORKLOADS = {
                                           C={"Function constants": "", "Variable names": "x, y, t",
                                              "Function expression": "1.0 + 0.25*sin(2*pi*x/3)*sin(2*pi*y/3)"}),
                                      "weak", True),
+    "newmark-4096-p2": ("standing-mode-wsol", "newmark", dict(Nel="4096", R="2", Dt="0.001"), "strong", False),
     "newmark-2048-p2": ("standing-mode-wsol", "newmark", dict(Nel="2048", R="2", Dt="0.002"), "strong", False),
 }
 DEFAULT = "c2-standing-newmark-1024-p1"

@@ -852,15 +852,15 @@ void launch_spmv(const Launcher &l, const SpmvArgs &a) {
             }
         } else {
             switch (spmv_variant()) {
-            case 1: launch_spmv_t<1, false, 19, 3>(l, a); break;
-            case 2: launch_spmv_t<1, false, 10, 2>(l, a); break;
-            case 3: launch_spmv_t<1, false, 19, 2>(l, a); break;
-            default: launch_spmv_t<1, false, 19, 1>(l, a);
+            case 1: launch_spmv_t<1, false, 10, 3>(l, a); break;
+            case 2: launch_spmv_t<1, false, 10, 4>(l, a); break;
+            case 3: launch_spmv_t<1, false, 13, 2>(l, a); break;
+            default: launch_spmv_t<1, false, 10, 2>(l, a);
             }
         }
     }
-    else if (!two_terms) { if (p1) launch_spmv_t<1, true, 7, 4>(l, a); else launch_spmv_t<1, true, 10, 4>(l, a); }
-    else { if (p1) launch_spmv_t<2, true, 7, 4>(l, a); else launch_spmv_t<2, true, 10, 4>(l, a); }
+    else if (!two_terms) { if (p1) launch_spmv_t<1, true, 7, 4>(l, a); else launch_spmv_t<1, true, 10, 2>(l, a); }
+    else { if (p1) launch_spmv_t<2, true, 7, 4>(l, a); else launch_spmv_t<2, true, 10, 2>(l, a); }
 }
 void launch_zero_rows(const Launcher &l, int nb, const int32_t *brow, double *vec) {
     if (nb <= 0) return;
