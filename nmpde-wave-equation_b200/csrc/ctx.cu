@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -129,8 +130,13 @@ struct wave_ctx {
     double *hres = nullptr;   // pinned [8]
     int prev_its[2] = {0, 0};
 
-    // NCCL
+    // NCCL + NVLink peer exchange
     Nccl::comm_t comm = nullptr;
+    PeerComm pc{};                       // enabled only for 1 < nranks <= kMaxPeers
+    PeerMailbox *mailbox = nullptr;
+    void *ipc_opened[2 * kMaxPeers]{};   // mapped peer allocations (closed in wave_destroy)
+    int n_ipc_opened = 0;
+    unsigned long long ar_seq = 0, halo_seq = 0;
 
     // instrumentation
     bool timers_on = false;
@@ -282,6 +288,7 @@ SpmvArgs spmv_base(wave_ctx *ctx) {
     a.A = ctx->A;
     a.partials = ctx->partials;
     a.counter = ctx->counter;
+    a.pc = PeerComm{};  // peer exchange only inside the CG loop (cg_solve sets it)
     return a;
 }
 
@@ -311,7 +318,11 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
     const int maxit = ctx->hS->maxit;
     for (;;) {
         for (int k = 0; k < chunk; ++k) {
-            RET(halo_exchange(ctx, ctx->d));
+            const bool p2p = ctx->pc.enabled != 0;
+            const bool first_it = (enq + k) == 0;
+            // halo of d: NCCL for the first iteration (d comes from the residual kernel), afterwards the
+            // neighbours' k_cg_direction wrote it into the ghost blocks and raised halo flag `halo_seq`
+            if (!p2p || first_it) RET(halo_exchange(ctx, ctx->d));
             SpmvArgs a = spmv_base(ctx);
             a.t[0] = {Sval, ctx->d, nullptr, 1.0, 0.0, 1.0};
             a.y = ctx->h;
@@ -319,15 +330,23 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
             a.dotv = ctx->d + L.own_off;
             a.result = &ctx->S->dAd;
             a.skip_flag = &ctx->S->status;
+            if (p2p) {
+                a.pc = ctx->pc;
+                a.ar_seq = ++ctx->ar_seq;
+                a.halo_wait_seq = first_it ? 0ull : ctx->halo_seq;
+            }
             {
                 SpmvBracket br(ctx);
                 launch_spmv(l, a);
             }
-            RET(allreduce(ctx, &ctx->S->dAd, 1));
+            if (!p2p) RET(allreduce(ctx, &ctx->S->dAd, 1));
+            const unsigned long long seq_b = p2p ? ++ctx->ar_seq : 0ull;
             launch_cg_update(l, L.nown, ctx->S, x + L.own_off, ctx->g, ctx->h, ctx->d + L.own_off, dinv,
-                             ctx->partials, ctx->counter);
-            RET(allreduce(ctx, &ctx->S->gg, 2));
-            launch_cg_direction(l, L.nown, ctx->S, ctx->d + L.own_off, ctx->h, ctx->counter);
+                             ctx->partials, ctx->counter, p2p ? ctx->pc : PeerComm{}, seq_b);
+            if (!p2p) RET(allreduce(ctx, &ctx->S->gg, 2));
+            const unsigned long long seq_h = p2p ? ++ctx->halo_seq : 0ull;
+            launch_cg_direction(l, L.nown, ctx->S, ctx->d + L.own_off, ctx->h, ctx->counter,
+                                p2p ? ctx->pc : PeerComm{}, seq_h);
         }
         enq += chunk;
         CK(cudaMemcpyAsync(ctx->hS, ctx->S, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
@@ -346,6 +365,8 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
     ctx->cg_stats[1] += ctx->hS->it;
     ctx->cg_stats[2] += ctx->hS->it + 1;
     ctx->cg_stats[3] += ms;
+    if (ctx->hS->status == 3)
+        return fail(ctx, WAVE_ERR_CUDA, "peer exchange timed out: a neighbouring rank did not arrive (NVLink mailbox)");
     if (ctx->hS->status != 1)
         return fail(ctx, WAVE_ERR_NOCONV, "CG did not converge within the iteration limit (SolverControl::NoConvergence)");
     return WAVE_OK;
@@ -558,6 +579,61 @@ int dev_alloc(wave_ctx *ctx, T **p, size_t count, bool zero = true) {
     return WAVE_OK;
 }
 
+// Map every rank's mailbox and the neighbours' search-direction vectors through CUDA IPC; the 64-byte
+// handles travel over NCCL broadcasts.  Disabled (NCCL collectives stay) for nranks > kMaxPeers or
+// when WAVE_NO_P2P is set.
+int setup_peer_exchange(wave_ctx *ctx) {
+    const int R = ctx->cfg.nranks, rank = ctx->cfg.rank;
+    if (R == 1 || R > kMaxPeers || std::getenv("WAVE_NO_P2P")) return WAVE_OK;
+    RET(dev_alloc(ctx, &ctx->mailbox, 1));
+    struct Handles { cudaIpcMemHandle_t box, d; };
+    std::vector<Handles> all((size_t)R);
+    CK(cudaIpcGetMemHandle(&all[rank].box, ctx->mailbox));
+    CK(cudaIpcGetMemHandle(&all[rank].d, ctx->d));
+    Handles *dev = nullptr;
+    RET(dev_alloc(ctx, &dev, (size_t)R));
+    CK(cudaMemcpyAsync(dev + rank, &all[rank], sizeof(Handles), cudaMemcpyHostToDevice, ctx->stream));
+    for (int r = 0; r < R; ++r)
+        NK(g_nccl.Broadcast(dev + r, dev + r, sizeof(Handles), /*ncclInt8*/ 0, r, ctx->comm, ctx->stream));
+    CK(cudaMemcpyAsync(all.data(), dev, sizeof(Handles) * R, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(dev));
+    PeerComm pc{};
+    pc.rank = rank;
+    pc.nranks = R;
+    pc.status = &ctx->S->status;
+    for (int r = 0; r < R; ++r) {
+        if (r == rank) { pc.box[r] = ctx->mailbox; continue; }
+        void *p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, all[r].box, cudaIpcMemLazyEnablePeerAccess));
+        ctx->ipc_opened[ctx->n_ipc_opened++] = p;
+        pc.box[r] = (PeerMailbox *)p;
+    }
+    const Layout &L = ctx->L;
+    const Mesh &m = L.mesh;
+    if (rank > 0) {  // my first block is the upper ghost block of rank-1
+        void *p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, all[rank - 1].d, cudaIpcMemLazyEnablePeerAccess));
+        ctx->ipc_opened[ctx->n_ipc_opened++] = p;
+        const Layout Lo = make_layout(m, rank - 1, R);
+        pc.d_lo = (double *)p + Lo.own_off + Lo.nown;
+        pc.lo_count = (int)(block_start(m, L.jq0 + 1) - block_start(m, L.jq0));
+    }
+    if (rank < R - 1) {  // my last block is the lower ghost block of rank+1 (its local index 0)
+        void *p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, all[rank + 1].d, cudaIpcMemLazyEnablePeerAccess));
+        ctx->ipc_opened[ctx->n_ipc_opened++] = p;
+        pc.d_hi = (double *)p;
+        pc.hi_count = (int)(block_start(m, L.jq1) - block_start(m, L.jq1 - 1));
+    }
+    pc.enabled = 1;
+    // nobody may store into a peer before every rank has mapped everything
+    RET(allreduce(ctx, ctx->res, 1));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->pc = pc;
+    return WAVE_OK;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -656,6 +732,8 @@ int wave_create(const wave_config *cfg, wave_ctx **out) {
 void wave_destroy(wave_ctx *ctx) {
     if (!ctx) return;
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int k = 0; k < ctx->n_ipc_opened; ++k) cudaIpcCloseMemHandle(ctx->ipc_opened[k]);
+    if (ctx->mailbox) cudaFree(ctx->mailbox);
     void *ptrs[] = {ctx->dprog, ctx->rowptr, ctx->slice_ptr, ctx->row_of, ctx->slot_of, ctx->col, ctx->c2i, ctx->i2c, ctx->tmp, ctx->M, ctx->K, ctx->S1, ctx->S2, ctx->dinv1, ctx->dinv2,
                     ctx->d0, ctx->u, ctx->v, ctx->a, ctx->unew, ctx->d, ctx->rhs, ctx->fvec, ctx->g, ctx->h,
                     ctx->scratch, ctx->brow, ctx->bx, ctx->by, ctx->partials, ctx->counter, ctx->S, ctx->res,
@@ -871,6 +949,7 @@ int wave_setup(wave_ctx *ctx) {
         RET(build_system_matrix(ctx, 0.0, ctx->S2, ctx->dinv2, ctx->d0 + 1));
     }
     RET(sync_check(ctx));
+    RET(setup_peer_exchange(ctx));
     ctx->is_setup = true;
     return WAVE_OK;
 }

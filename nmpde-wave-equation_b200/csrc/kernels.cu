@@ -72,17 +72,77 @@ __device__ __forceinline__ bool grid_sum(double (&v)[NV], double *partials, unsi
 }
 
 // Last-block detection without a reduction (for scalar bookkeeping after all blocks have read it).
-__device__ __forceinline__ bool last_block_done(unsigned *counter) {
+// sys = true when the blocks wrote to peer memory: the fence then has system scope.
+__device__ __forceinline__ bool last_block_done(unsigned *counter, bool sys = false) {
     __shared__ bool s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
+        if (sys) __threadfence_system();
+        else __threadfence();
         const unsigned ticket = atomicAdd(counter, 1u);
         s_last = (ticket == gridDim.x - 1);
         if (s_last) *counter = 0u;
     }
     __syncthreads();
     return s_last;
+}
+
+// ---- peer exchange over NVLink (see PeerComm in kernels.cuh) -------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool spin_until(const unsigned long long *p, unsigned long long seq) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) < seq) {
+        if (clock64() - t0 > 6000000000LL) return false;  // ~3 s: give up instead of hanging the GPU
+    }
+    return true;
+}
+// One-shot all-reduce of NV (<= 2) doubles, executed by the first warp of one block per rank.
+// `vals` holds the local totals in lane 0 on entry and the global totals in all lanes on return.
+template <int NV>
+__device__ __forceinline__ void p2p_allreduce(const PeerComm &pc, unsigned long long seq, double (&vals)[NV]) {
+    const int lane = threadIdx.x & 31;
+    const int slot = (int)(seq & 1ull);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) vals[k] = __shfl_sync(kFull, vals[k], 0);
+    if (lane < pc.nranks) {
+        PeerMailbox *dst = pc.box[lane];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) *((volatile double *)&dst->ar_vals[slot][pc.rank][k]) = vals[k];
+        st_release_sys(&dst->ar_flag[slot][pc.rank], seq);
+    }
+    bool ok = true;
+    double mine[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) mine[k] = 0.0;
+    if (lane < pc.nranks) {
+        PeerMailbox *box = pc.box[pc.rank];
+        ok = spin_until(&box->ar_flag[slot][lane], seq);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) mine[k] = *((volatile double *)&box->ar_vals[slot][lane][k]);
+    }
+    ok = __all_sync(kFull, ok);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double t = 0.0;
+        for (int r = 0; r < pc.nranks; ++r) t += __shfl_sync(kFull, mine[k], r);  // rank order on every rank
+        vals[k] = t;
+    }
+    if (!ok && lane == 0) *pc.status = 3;
+}
+// grid_sum followed by the peer all-reduce when enabled; true in the finishing block, totals in thread 0
+template <int NV>
+__device__ __forceinline__ bool grid_sum_peers(double (&v)[NV], double *partials, unsigned *counter,
+                                               const PeerComm &pc, unsigned long long seq) {
+    const bool last = grid_sum<NV>(v, partials, counter);
+    if (last && pc.enabled && threadIdx.x < 32) p2p_allreduce<NV>(pc, seq, v);
+    return last;
 }
 
 // ---- sparsity pattern: DoFTools::make_sparsity_pattern + compress (src/WaveNewmark.cpp:33-35) ----
@@ -431,6 +491,16 @@ __device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
 template <int NT, bool TWOX, int CH, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) k_spmv(SpmvArgs a) {
     if (a.skip_flag && *a.skip_flag != 0) return;
+    if (a.halo_wait_seq) {  // ghost blocks of x are written by the neighbours' k_cg_direction
+        if (threadIdx.x == 0) {
+            bool ok = true;
+            PeerMailbox *box = a.pc.box[a.pc.rank];
+            if (a.pc.rank > 0) ok = spin_until(&box->halo_flag[0], a.halo_wait_seq) && ok;
+            if (a.pc.rank < a.pc.nranks - 1) ok = spin_until(&box->halo_flag[1], a.halo_wait_seq) && ok;
+            if (!ok) *a.pc.status = 3;
+        }
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (kThreads / 32);
     double dots[2] = {0.0, 0.0};
@@ -504,7 +574,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmv(SpmvArgs a) {
         slice = nslice; b = nb; e = ne; r = nr;
     }
     if (a.dot_mode) {
-        if (grid_sum<2>(dots, a.partials, a.counter) && threadIdx.x == 0) {
+        if (grid_sum_peers<2>(dots, a.partials, a.counter, a.pc, a.ar_seq) && threadIdx.x == 0) {
             a.result[0] = dots[0];
             if (a.dot_mode == 2) a.result[1] = dots[1];
         }
@@ -533,7 +603,7 @@ __global__ void __launch_bounds__(kThreads) k_cg_update(int n, CgScalars *S, dou
                                                         double *__restrict__ g, double *__restrict__ h,
                                                         const double *__restrict__ d,
                                                         const double *__restrict__ dinv, double *partials,
-                                                        unsigned *counter) {
+                                                        unsigned *counter, PeerComm pc, unsigned long long ar_seq) {
     if (S->status != 0) return;
     const double alpha = S->gh_old / S->dAd;
     double acc[2] = {0.0, 0.0};
@@ -547,14 +617,15 @@ __global__ void __launch_bounds__(kThreads) k_cg_update(int n, CgScalars *S, dou
         acc[0] += gi * gi;
         acc[1] += gi * hi;
     }
-    if (grid_sum<2>(acc, partials, counter) && threadIdx.x == 0) {
+    if (grid_sum_peers<2>(acc, partials, counter, pc, ar_seq) && threadIdx.x == 0) {
         S->gg = acc[0];
         S->gh_new = acc[1];
     }
 }
 // iteration_status(it, res); beta = gh'/gh ; d = beta d - h
 __global__ void __launch_bounds__(kThreads) k_cg_direction(int n, CgScalars *S, double *__restrict__ d,
-                                                           const double *__restrict__ h, unsigned *counter) {
+                                                           const double *__restrict__ h, unsigned *counter,
+                                                           PeerComm pc, unsigned long long halo_seq) {
     if (S->status != 0) return;
     const double res = sqrt(fabs(S->gg));
     const int it = S->it + 1;
@@ -564,13 +635,26 @@ __global__ void __launch_bounds__(kThreads) k_cg_direction(int n, CgScalars *S, 
     if (status == 0) {
         const double beta = S->gh_new / S->gh_old;
         const int stride = gridDim.x * blockDim.x;
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) d[i] = beta * d[i] - h[i];
+        const int hi0 = n - pc.hi_count;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            const double di = beta * d[i] - h[i];
+            d[i] = di;
+            if (pc.enabled) {  // my first / last block is the neighbours' ghost block: store it there too
+                if (pc.d_lo && i < pc.lo_count) pc.d_lo[i] = di;
+                if (pc.d_hi && i >= hi0) pc.d_hi[i - hi0] = di;
+            }
+        }
     }
-    if (last_block_done(counter) && threadIdx.x == 0) {
+    if (last_block_done(counter, pc.enabled != 0) && threadIdx.x == 0) {
         S->it = it;
         S->res = res;
         S->status = status;
         S->gh_old = S->gh_new;
+        if (pc.enabled && status == 0) {
+            __threadfence_system();
+            if (pc.rank > 0) st_release_sys(&pc.box[pc.rank - 1]->halo_flag[1], halo_seq);
+            if (pc.rank < pc.nranks - 1) st_release_sys(&pc.box[pc.rank + 1]->halo_flag[0], halo_seq);
+        }
     }
 }
 
@@ -868,11 +952,13 @@ void launch_zero_rows(const Launcher &l, int nb, const int32_t *brow, double *ve
 }
 void launch_cg_start(const Launcher &l, CgScalars *S) { WV_LAUNCH(l, k_cg_start, 1, 32, 0, S); }
 void launch_cg_update(const Launcher &l, int n, CgScalars *S, double *x, double *g, double *h, const double *d,
-                      const double *dinv, double *partials, unsigned *counter) {
-    WV_LAUNCH(l, k_cg_update, stream_blocks(n), kThreads, 0, n, S, x, g, h, d, dinv, partials, counter);
+                      const double *dinv, double *partials, unsigned *counter, const PeerComm &pc,
+                      unsigned long long ar_seq) {
+    WV_LAUNCH(l, k_cg_update, stream_blocks(n), kThreads, 0, n, S, x, g, h, d, dinv, partials, counter, pc, ar_seq);
 }
-void launch_cg_direction(const Launcher &l, int n, CgScalars *S, double *d, const double *h, unsigned *counter) {
-    WV_LAUNCH(l, k_cg_direction, stream_blocks(n), kThreads, 0, n, S, d, h, counter);
+void launch_cg_direction(const Launcher &l, int n, CgScalars *S, double *d, const double *h, unsigned *counter,
+                         const PeerComm &pc, unsigned long long halo_seq) {
+    WV_LAUNCH(l, k_cg_direction, stream_blocks(n), kThreads, 0, n, S, d, h, counter, pc, halo_seq);
 }
 void launch_newmark_predict(const Launcher &l, int n, double dt, double c1, double c2, double *u, double *v,
                             const double *a) {

@@ -64,6 +64,29 @@ struct CgScalars {
     int it, status, maxit, pad;  // status: 0 iterate, 1 success, 2 failure
 };
 
+// ---- NVLink peer exchange inside the CG kernels (nranks > 1) --------------------------------------
+// Every rank owns a small mailbox in device memory that all peers map through CUDA IPC.  The two
+// per-iteration reductions are one-shot all-reduces done by the last block of the producing kernel:
+// it stores its partial sums and a sequence number into every peer's mailbox (P2P stores over
+// NVLink), waits until all ranks' numbers arrived in its own mailbox and adds the partials in rank
+// order, so all ranks obtain bitwise identical totals without a separate collective launch.  The
+// halo of the search direction is written by k_cg_direction straight into the neighbours' ghost
+// blocks, followed by a flag the next SpMV waits on.  Sequence numbers come from the host and are
+// identical on all ranks; waits are bounded (status 3 on timeout) so a lost peer cannot hang a GPU.
+constexpr int kMaxPeers = 8;
+struct PeerMailbox {
+    double ar_vals[2][kMaxPeers][2];
+    unsigned long long ar_flag[2][kMaxPeers];
+    unsigned long long halo_flag[2];  // [0] written by the lower neighbour, [1] by the upper one
+};
+struct PeerComm {
+    int enabled, rank, nranks, pad;
+    PeerMailbox *box[kMaxPeers];  // box[rank] is the local mailbox
+    double *d_lo, *d_hi;          // where my first / last owned block lives in the neighbours' ghost regions
+    int lo_count, hi_count;
+    int *status;
+};
+
 struct SpmvTerm {
     const double *val;
     const double *xa, *xb;  // local-layout vectors; x = ca*xa + cb*xb
@@ -85,6 +108,9 @@ struct SpmvArgs {
     unsigned *counter;
     double *result;            // totals (1 or 2 doubles)
     const int *skip_flag;      // if non-null and *skip_flag != 0 the kernel returns at once
+    // peer exchange (see PeerComm): all-reduce of the dot result, wait for the neighbours' halo
+    PeerComm pc;
+    unsigned long long ar_seq, halo_wait_seq;
 };
 
 // ---- launch wrappers (defined in kernels.cu) ---------------------------------------------------
@@ -129,8 +155,10 @@ void launch_zero_rows(const Launcher &, int nb, const int32_t *brow, double *vec
 int spmv_grid_blocks(int nslices);
 void launch_cg_start(const Launcher &, CgScalars *S);
 void launch_cg_update(const Launcher &, int n, CgScalars *S, double *x, double *g, double *h, const double *d,
-                      const double *dinv, double *partials, unsigned *counter);
-void launch_cg_direction(const Launcher &, int n, CgScalars *S, double *d, const double *h, unsigned *counter);
+                      const double *dinv, double *partials, unsigned *counter, const PeerComm &pc,
+                      unsigned long long ar_seq);
+void launch_cg_direction(const Launcher &, int n, CgScalars *S, double *d, const double *h, unsigned *counter,
+                         const PeerComm &pc, unsigned long long halo_seq);
 void launch_newmark_predict(const Launcher &, int n, double dt, double c1, double c2, double *u, double *v,
                             const double *a);
 void launch_newmark_correct(const Launcher &, int n, double cu, double cv, double *u, double *v, const double *a,
