@@ -490,6 +490,8 @@ __device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
 
 template <int NT, bool TWOX, int CH, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) k_spmv(SpmvArgs a) {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
     if (a.skip_flag && *a.skip_flag != 0) return;
     if (a.halo_wait_seq) {  // ghost blocks of x are written by the neighbours' k_cg_direction
         if (threadIdx.x == 0) {
@@ -604,6 +606,8 @@ __global__ void __launch_bounds__(kThreads) k_cg_update(int n, CgScalars *S, dou
                                                         const double *__restrict__ d,
                                                         const double *__restrict__ dinv, double *partials,
                                                         unsigned *counter, PeerComm pc, unsigned long long ar_seq) {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
     if (S->status != 0) return;
     const double alpha = S->gh_old / S->dAd;
     double acc[2] = {0.0, 0.0};
@@ -626,6 +630,8 @@ __global__ void __launch_bounds__(kThreads) k_cg_update(int n, CgScalars *S, dou
 __global__ void __launch_bounds__(kThreads) k_cg_direction(int n, CgScalars *S, double *__restrict__ d,
                                                            const double *__restrict__ h, unsigned *counter,
                                                            PeerComm pc, unsigned long long halo_seq) {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
     if (S->status != 0) return;
     const double res = sqrt(fabs(S->gg));
     const int it = S->it + 1;
@@ -821,6 +827,25 @@ int reduction_blocks(int n) { return stream_blocks(n); }
         if ((l).count) ++*(l).count;                              \
     } while (0)
 
+// Launch with programmatic dependent launch: the kernel starts with cudaGridDependencySynchronize(), so
+// its blocks may be scheduled while the previous kernel of the stream drains (hides the launch gap
+// between the three short kernels of a CG iteration).
+template <class... KArgs, class... Args>
+static void launch_pdl(const Launcher &l, void (*kernel)(KArgs...), int grid, int block, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = l.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    if (l.count) ++*l.count;
+}
+
 void launch_row_lengths(const Launcher &l, const Layout &L, uint32_t *rowlen) {
     const int64_t n = slot_count(L, owned_slots(L));
     WV_LAUNCH(l, k_row_lengths, blocks_for(n, 128), 128, 0, L, rowlen);
@@ -914,7 +939,7 @@ static void launch_spmv_t(const Launcher &l, const SpmvArgs &a) {
     static int grid_cap = 0;
     if (!grid_cap) grid_cap = persistent_grid(k_spmv<NT, TWOX, CH, MINB>, 1 << 30);
     const int64_t need = blocks_for((int64_t)a.A.nslices * kSlice, kThreads);
-    WV_LAUNCH(l, (k_spmv<NT, TWOX, CH, MINB>), (int)std::min<int64_t>(need, grid_cap), kThreads, 0, a);
+    launch_pdl(l, k_spmv<NT, TWOX, CH, MINB>, (int)std::min<int64_t>(need, grid_cap), kThreads, a);
 }
 static int spmv_variant() {
     static int v = -1;
@@ -954,11 +979,11 @@ void launch_cg_start(const Launcher &l, CgScalars *S) { WV_LAUNCH(l, k_cg_start,
 void launch_cg_update(const Launcher &l, int n, CgScalars *S, double *x, double *g, double *h, const double *d,
                       const double *dinv, double *partials, unsigned *counter, const PeerComm &pc,
                       unsigned long long ar_seq) {
-    WV_LAUNCH(l, k_cg_update, stream_blocks(n), kThreads, 0, n, S, x, g, h, d, dinv, partials, counter, pc, ar_seq);
+    launch_pdl(l, k_cg_update, stream_blocks(n), kThreads, n, S, x, g, h, d, dinv, partials, counter, pc, ar_seq);
 }
 void launch_cg_direction(const Launcher &l, int n, CgScalars *S, double *d, const double *h, unsigned *counter,
                          const PeerComm &pc, unsigned long long halo_seq) {
-    WV_LAUNCH(l, k_cg_direction, stream_blocks(n), kThreads, 0, n, S, d, h, counter, pc, halo_seq);
+    launch_pdl(l, k_cg_direction, stream_blocks(n), kThreads, n, S, d, h, counter, pc, halo_seq);
 }
 void launch_newmark_predict(const Launcher &l, int n, double dt, double c1, double c2, double *u, double *v,
                             const double *a) {
