@@ -255,11 +255,12 @@ struct PhaseTimer {
     }
 };
 
-// resolve the recorded SpMV event pairs into (count, ms)
-void drain_spmv_events(wave_ctx *ctx) {
+// resolve the recorded SpMV event pairs into (count, ms).  Only the first `valid_launches` pairs are
+// counted: launches enqueued after the solve converged return at once and must not dilute the average.
+void drain_spmv_events(wave_ctx *ctx, size_t valid_launches = (size_t)-1) {
     if (!ctx->spmv_ev_used) return;
     cudaEventSynchronize(ctx->spmv_ev[ctx->spmv_ev_used - 1]);
-    for (size_t k = 0; k + 1 < ctx->spmv_ev_used; k += 2) {
+    for (size_t k = 0; k + 1 < ctx->spmv_ev_used && k / 2 < valid_launches; k += 2) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ctx->spmv_ev[k], ctx->spmv_ev[k + 1]) == cudaSuccess) {
             ctx->spmv_ms += ms;
@@ -360,6 +361,7 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     *iters = ctx->hS->it;
+    if (ctx->spmv_timing) drain_spmv_events(ctx, (size_t)ctx->hS->it);
     ctx->prev_its[slot] = ctx->hS->it;
     ctx->cg_stats[0] += 1;
     ctx->cg_stats[1] += ctx->hS->it;

@@ -941,33 +941,14 @@ static void launch_spmv_t(const Launcher &l, const SpmvArgs &a) {
     const int64_t need = blocks_for((int64_t)a.A.nslices * kSlice, kThreads);
     launch_pdl(l, k_spmv<NT, TWOX, CH, MINB>, (int)std::min<int64_t>(need, grid_cap), kThreads, a);
 }
-static int spmv_variant() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("WAVE_SPMV_VARIANT"); v = e ? atoi(e) : 0; }
-    return v;
-}
 // chunk = the dominant row length of the element: P1 rows hold 7 entries, P2 rows 19 / 9
 void launch_spmv(const Launcher &l, const SpmvArgs &a) {
     const bool two_terms = a.t[1].val != nullptr;
     const bool twox = a.t[0].xb != nullptr || (two_terms && a.t[1].xb != nullptr);
     const bool p1 = a.A.chunk <= 7;
-    if (!two_terms && !twox) {
-        if (p1) {
-            switch (spmv_variant()) {
-            case 1: launch_spmv_t<1, false, 7, 3>(l, a); break;
-            case 2: launch_spmv_t<1, false, 7, 2>(l, a); break;
-            case 3: launch_spmv_t<1, false, 7, 5>(l, a); break;
-            default: launch_spmv_t<1, false, 7, 4>(l, a);
-            }
-        } else {
-            switch (spmv_variant()) {
-            case 1: launch_spmv_t<1, false, 10, 3>(l, a); break;
-            case 2: launch_spmv_t<1, false, 10, 4>(l, a); break;
-            case 3: launch_spmv_t<1, false, 13, 2>(l, a); break;
-            default: launch_spmv_t<1, false, 10, 2>(l, a);
-            }
-        }
-    }
+    // (CH, blocks/SM) measured on B200: P1 (7, 4) -> 1.05 of the measured copy bandwidth at Nel=4096,
+    // P2 (10, 2) -> 0.97; higher occupancy with fewer loads in flight per lane was slower for both
+    if (!two_terms && !twox) { if (p1) launch_spmv_t<1, false, 7, 4>(l, a); else launch_spmv_t<1, false, 10, 2>(l, a); }
     else if (!two_terms) { if (p1) launch_spmv_t<1, true, 7, 4>(l, a); else launch_spmv_t<1, true, 10, 2>(l, a); }
     else { if (p1) launch_spmv_t<2, true, 7, 4>(l, a); else launch_spmv_t<2, true, 10, 2>(l, a); }
 }
