@@ -335,6 +335,10 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
                 a.pc = ctx->pc;
                 a.ar_seq = ++ctx->ar_seq;
                 a.halo_wait_seq = first_it ? 0ull : ctx->halo_seq;
+                a.ghost_lo_slices = ctx->cfg.rank > 0 ? ((ctx->pc.lo_count + kWindow - 1) / kWindow) * (kWindow / kSlice) : 0;
+                a.ghost_hi_slice0 = ctx->cfg.rank < ctx->cfg.nranks - 1
+                                        ? ((L.nown - ctx->pc.hi_count) / kWindow) * (kWindow / kSlice)
+                                        : ctx->nslices;
             }
             {
                 SpmvBracket br(ctx);

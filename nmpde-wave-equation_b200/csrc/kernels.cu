@@ -493,39 +493,50 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmv(SpmvArgs a) {
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
     if (a.skip_flag && *a.skip_flag != 0) return;
-    if (a.halo_wait_seq) {  // ghost blocks of x are written by the neighbours' k_cg_direction
-        if (threadIdx.x == 0) {
-            bool ok = true;
-            PeerMailbox *box = a.pc.box[a.pc.rank];
-            if (a.pc.rank > 0) ok = spin_until(&box->halo_flag[0], a.halo_wait_seq) && ok;
-            if (a.pc.rank < a.pc.nranks - 1) ok = spin_until(&box->halo_flag[1], a.halo_wait_seq) && ok;
-            if (!ok) *a.pc.status = 3;
-        }
-        __syncthreads();
-    }
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (kThreads / 32);
     double dots[2] = {0.0, 0.0};
     // Persistent warps, grid-stride over slices.  Per chunk a lane issues CH col loads and CH*NT val
     // loads back to back (unconditional: a short tail re-reads the row's last entry and is masked out
     // of the sum), then the CH dependent x gathers, then accumulates in column order.
-    int slice = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+    // The walk starts in the middle of the matrix (rotation by nslices/2): the few slices that read
+    // ghost entries sit at both ends of the row range and are reached mid-kernel, when the neighbours'
+    // halo (written by their k_cg_direction over NVLink) has long arrived -- the wait below is off
+    // the critical path.  Those slices gather through L2 (ld.global.cg): an L1 line that straddles
+    // the owned / ghost boundary may have been filled before the halo landed.
+    const int rot = a.halo_wait_seq ? a.A.nslices / 2 : 0;
+    bool halo_ready = a.halo_wait_seq == 0;
+    int it = (blockIdx.x * kThreads + threadIdx.x) >> 5;  // position in the walk
+    int slice = it + rot < a.A.nslices ? it + rot : it + rot - a.A.nslices;
     uint32_t b = 0, e = 0;
     int r = -1;
-    if (slice < a.A.nslices) {
+    if (it < a.A.nslices) {
         b = a.A.slice_ptr[slice];
         e = a.A.slice_ptr[slice + 1];
         r = a.A.row_of[slice * kSlice + lane];
     }
-    while (slice < a.A.nslices) {
+    while (it < a.A.nslices) {
         // metadata of this warp's next slice, requested before the long-latency work below
-        const int nslice = slice + nwarps;
+        const int nit = it + nwarps;
+        const int nslice = nit + rot < a.A.nslices ? nit + rot : nit + rot - a.A.nslices;
         uint32_t nb = 0, ne = 0;
         int nr = -1;
-        if (nslice < a.A.nslices) {
+        if (nit < a.A.nslices) {
             nb = a.A.slice_ptr[nslice];
             ne = a.A.slice_ptr[nslice + 1];
             nr = a.A.row_of[nslice * kSlice + lane];
+        }
+        const bool ghosty = a.pc.enabled && (slice < a.ghost_lo_slices || slice >= a.ghost_hi_slice0);
+        if (ghosty && !halo_ready) {  // warp-uniform
+            if (lane == 0) {
+                bool ok = true;
+                PeerMailbox *box = a.pc.box[a.pc.rank];
+                if (a.pc.rank > 0) ok = spin_until(&box->halo_flag[0], a.halo_wait_seq) && ok;
+                if (a.pc.rank < a.pc.nranks - 1) ok = spin_until(&box->halo_flag[1], a.halo_wait_seq) && ok;
+                if (!ok) *a.pc.status = 3;
+            }
+            __syncwarp();
+            halo_ready = true;
         }
         const int len = (int)((e - b) >> 5);
         const uint32_t base = b + lane;
@@ -545,8 +556,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmv(SpmvArgs a) {
             for (int k = 0; k < CH; ++k)
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
-                    double xv = __dmul_rn(a.t[t].ca, a.t[t].xa[c[k]]);
-                    if (TWOX && a.t[t].xb) xv = __dadd_rn(xv, __dmul_rn(a.t[t].cb, a.t[t].xb[c[k]]));
+                    const double xa = ghosty ? __ldcg(&a.t[t].xa[c[k]]) : a.t[t].xa[c[k]];
+                    double xv = __dmul_rn(a.t[t].ca, xa);
+                    if (TWOX && a.t[t].xb)
+                        xv = __dadd_rn(xv, __dmul_rn(a.t[t].cb, ghosty ? __ldcg(&a.t[t].xb[c[k]]) : a.t[t].xb[c[k]]));
                     x[t][k] = xv;
                 }
 #pragma unroll
@@ -573,7 +586,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmv(SpmvArgs a) {
             if (a.dot_mode == 1) dots[0] += s * a.dotv[r];
             else if (a.dot_mode == 2) { dots[0] += s * s; dots[1] += s * hv; }
         }
-        slice = nslice; b = nb; e = ne; r = nr;
+        it = nit; slice = nslice; b = nb; e = ne; r = nr;
     }
     if (a.dot_mode) {
         if (grid_sum_peers<2>(dots, a.partials, a.counter, a.pc, a.ar_seq) && threadIdx.x == 0) {

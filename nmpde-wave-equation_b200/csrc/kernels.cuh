@@ -111,6 +111,9 @@ struct SpmvArgs {
     // peer exchange (see PeerComm): all-reduce of the dot result, wait for the neighbours' halo
     PeerComm pc;
     unsigned long long ar_seq, halo_wait_seq;
+    // slices [0, ghost_lo_slices) and [ghost_hi_slice0, nslices) may read ghost entries of x: they wait
+    // for the halo flag (lazily, when first reached) and gather through L2 only
+    int ghost_lo_slices, ghost_hi_slice0;
 };
 
 // ---- launch wrappers (defined in kernels.cu) ---------------------------------------------------
