@@ -103,35 +103,56 @@ __device__ __forceinline__ bool spin_until(const unsigned long long *p, unsigned
     }
     return true;
 }
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 // One-shot all-reduce of NV (<= 2) doubles, executed by the first warp of one block per rank.
 // `vals` holds the local totals in lane 0 on entry and the global totals in all lanes on return.
+// Lane r stores this rank's words into rank r's mailbox (one NVLink hop, no ordering needed) and polls
+// rank r's words in the local mailbox; the sum runs in rank order on every rank (bitwise identical).
 template <int NV>
 __device__ __forceinline__ void p2p_allreduce(const PeerComm &pc, unsigned long long seq, double (&vals)[NV]) {
     const int lane = threadIdx.x & 31;
     const int slot = (int)(seq & 1ull);
+    const unsigned long long tag = (seq & 0xffffffffull) << 32;
 #pragma unroll
     for (int k = 0; k < NV; ++k) vals[k] = __shfl_sync(kFull, vals[k], 0);
-    if (lane < pc.nranks) {
-        PeerMailbox *dst = pc.box[lane];
-#pragma unroll
-        for (int k = 0; k < NV; ++k) *((volatile double *)&dst->ar_vals[slot][pc.rank][k]) = vals[k];
-        st_release_sys(&dst->ar_flag[slot][pc.rank], seq);
-    }
     bool ok = true;
-    double mine[NV];
+    double got[NV];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) mine[k] = 0.0;
+    for (int k = 0; k < NV; ++k) got[k] = 0.0;
     if (lane < pc.nranks) {
-        PeerMailbox *box = pc.box[pc.rank];
-        ok = spin_until(&box->ar_flag[slot][lane], seq);
+        unsigned long long *dst = pc.box[lane]->ll[slot][pc.rank];
 #pragma unroll
-        for (int k = 0; k < NV; ++k) mine[k] = *((volatile double *)&box->ar_vals[slot][lane][k]);
+        for (int k = 0; k < NV; ++k) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[k]);
+            st_relaxed_sys(&dst[2 * k], (bits & 0xffffffffull) | tag);
+            st_relaxed_sys(&dst[2 * k + 1], (bits >> 32) | tag);
+        }
+        const unsigned long long *src = pc.box[pc.rank]->ll[slot][lane];
+        const long long t0 = clock64();
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            unsigned long long lo, hi;
+            for (;;) {
+                lo = ld_relaxed_sys(&src[2 * k]);
+                hi = ld_relaxed_sys(&src[2 * k + 1]);
+                if ((lo & 0xffffffff00000000ull) == tag && (hi & 0xffffffff00000000ull) == tag) break;
+                if (clock64() - t0 > 6000000000LL) { ok = false; break; }  // ~3 s: give up, do not hang
+            }
+            got[k] = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+        }
     }
     ok = __all_sync(kFull, ok);
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         double t = 0.0;
-        for (int r = 0; r < pc.nranks; ++r) t += __shfl_sync(kFull, mine[k], r);  // rank order on every rank
+        for (int r = 0; r < pc.nranks; ++r) t += __shfl_sync(kFull, got[k], r);  // rank order on every rank
         vals[k] = t;
     }
     if (!ok && lane == 0) *pc.status = 3;

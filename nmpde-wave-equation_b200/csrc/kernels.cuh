@@ -75,8 +75,9 @@ struct CgScalars {
 // identical on all ranks; waits are bounded (status 3 on timeout) so a lost peer cannot hang a GPU.
 constexpr int kMaxPeers = 8;
 struct PeerMailbox {
-    double ar_vals[2][kMaxPeers][2];
-    unsigned long long ar_flag[2][kMaxPeers];
+    // all-reduce slots, "LL" style: every 8-byte word carries 4 bytes of payload and the low 32 bits of
+    // the sequence number, so a word validates itself and no fence / flag round trip is needed
+    unsigned long long ll[2][kMaxPeers][4];
     unsigned long long halo_flag[2];  // [0] written by the lower neighbour, [1] by the upper one
 };
 struct PeerComm {
