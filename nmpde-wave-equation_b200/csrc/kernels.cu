@@ -873,7 +873,8 @@ static void launch_pdl(const Launcher &l, void (*kernel)(KArgs...), int grid, in
     cfg.stream = l.stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const int pdl = std::getenv("WAVE_NO_PDL") ? 0 : 1;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
