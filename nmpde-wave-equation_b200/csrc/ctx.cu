@@ -315,7 +315,9 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
     RET(allreduce(ctx, &ctx->S->gg, 2));
     launch_cg_start(l, ctx->S);
     int enq = 0;
-    int chunk = ctx->prev_its[slot] > 6 ? ctx->prev_its[slot] - 2 : 4;
+    // iteration counts of consecutive time steps are nearly equal (warm start): enqueue as many
+    // iterations as the previous solve needed, then poll in pairs
+    int chunk = ctx->prev_its[slot] > 6 ? ctx->prev_its[slot] : 4;
     const int maxit = ctx->hS->maxit;
     for (;;) {
         for (int k = 0; k < chunk; ++k) {
@@ -358,7 +360,7 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
         CK(cudaStreamSynchronize(ctx->stream));
         if (ctx->hS->status != 0) break;
         if (enq > maxit + 8) break;
-        chunk = 4;
+        chunk = 2;
     }
     CK(cudaEventRecord(e1, ctx->stream));
     CK(cudaEventSynchronize(e1));
@@ -552,6 +554,17 @@ int own_to_canonical(wave_ctx *ctx, const double *src_own, double *dst_own) {
     const Layout &L = ctx->L;
     if (ctx->permuted) launch_gather(ctx->launcher, L.nown, ctx->c2i + L.own_off, src_own - L.own_off, dst_own);
     else CK(cudaMemcpyAsync(dst_own, src_own, sizeof(double) * L.nown, cudaMemcpyDeviceToDevice, ctx->stream));
+    return WAVE_OK;
+}
+// owned rows -> host (canonical order), asynchronous on the context stream
+int download_own_async(wave_ctx *ctx, const double *src_own, double *host_own) {
+    const Layout &L = ctx->L;
+    const double *from = src_own;
+    if (ctx->permuted) {
+        RET(own_to_canonical(ctx, src_own, ctx->tmp));
+        from = ctx->tmp;
+    }
+    CK(cudaMemcpyAsync(host_own, from, sizeof(double) * L.nown, cudaMemcpyDeviceToHost, ctx->stream));
     return WAVE_OK;
 }
 int upload_local(wave_ctx *ctx, const double *host_global, double *dst_local) {
@@ -1065,7 +1078,6 @@ int wave_step_host(wave_ctx *ctx, double t_np1, double *u, double *v, double *a,
     if (!ctx || !ctx->is_init) return fail(ctx, WAVE_ERR_STATE, "wave_step_host before wave_init");
     const size_t n = (size_t)n_dofs(ctx->L.mesh);
     const Layout &L = ctx->L;
-    (void)L;
     RET(upload_local(ctx, u, ctx->u));
     RET(upload_local(ctx, v, ctx->v));
     if (ctx->cfg.scheme == WAVE_SCHEME_NEWMARK) {
@@ -1073,6 +1085,13 @@ int wave_step_host(wave_ctx *ctx, double t_np1, double *u, double *v, double *a,
         RET(upload_local(ctx, a, ctx->a));
     }
     RET(wave_step(ctx, t_np1, iters, norms));
+    if (ctx->cfg.nranks == 1) {  // three downloads back to back, one synchronisation
+        RET(download_own_async(ctx, ctx->u + L.own_off, u));
+        RET(download_own_async(ctx, ctx->v + L.own_off, v));
+        if (ctx->cfg.scheme == WAVE_SCHEME_NEWMARK) RET(download_own_async(ctx, ctx->a + L.own_off, a));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return WAVE_OK;
+    }
     RET(wave_get_vector(ctx, WAVE_VEC_U, u, n));
     RET(wave_get_vector(ctx, WAVE_VEC_V, v, n));
     if (ctx->cfg.scheme == WAVE_SCHEME_NEWMARK) RET(wave_get_vector(ctx, WAVE_VEC_A, a, n));
