@@ -40,10 +40,16 @@ WORKLOADS = {
                                           C={"Function constants": "", "Variable names": "x, y, t",
                                              "Function expression": "1.0 + 0.25*sin(2*pi*x/3)*sin(2*pi*y/3)"}),
                                      "weak", True),
+    # the reference's own published strong-scaling configuration (BASELINE.md section 1:
+    # report/sections/8_Scalability.tex:9-18): Nel=640, R=1, Dt=8e-5, Newmark 1/4, 1/2
+    "published-newmark-640-p1": ("standing-mode-wsol", "newmark", dict(Nel="640", R="1", Dt="8e-5"), "strong", False),
     "newmark-4096-p2": ("standing-mode-wsol", "newmark", dict(Nel="4096", R="2", Dt="0.001"), "strong", False),
     "newmark-2048-p2": ("standing-mode-wsol", "newmark", dict(Nel="2048", R="2", Dt="0.002"), "strong", False),
 }
 DEFAULT = "c2-standing-newmark-1024-p1"
+# BASELINE.md publishes a number only for this workload: 410 881 DoFs x 625 steps / 296.3 s whole-process
+# wall time on one Xeon Gold 6238R core (AMG-CG); 16 ranks: 9.31 M, 32 ranks: 12.8 M DoF-steps/s
+PUBLISHED = {"published-newmark-640-p1": 0.867e6}
 
 
 def make_params(workload, n_gpus):
@@ -337,7 +343,8 @@ def main():
     line = {
         "metric": "dof_steps_per_sec", "value": value, "unit": "DoF-steps/s", "n_gpus": n_gpus, "steps": K,
         "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": scaling,
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "vs_baseline": (value / PUBLISHED[workload]) if workload in PUBLISHED else None,
+        "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload, "problem": WORKLOADS[workload][0], "scheme": scheme,
                    "Nel": params["Nel"], "R": params["R"], "Dt": params["Dt"], "n_dofs": n,
                    "nnz_per_gpu": nnz, "cg_its_per_step": its_total / K, "preconditioner": "jacobi",
