@@ -190,6 +190,8 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--no-scale-probe", action="store_true",
+                    help="skip the SpMV / CG-iteration roofline probe on matrices larger than L2")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -332,6 +334,25 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- the same kernels on matrices far larger than the 126 MB L2 (the bench workload's 88 MB matrix
+    # makes a 25 us kernel: launch ramp and tail weigh on its fraction) -------------------------------
+    at_scale = None
+    if world == 1 and not args.no_scale_probe:
+        from wavegpu.problems import problem as _problem
+
+        at_scale = []
+        for nel, r in (("4096", 1), ("2048", 2)):
+            gs = WaveSolver(_problem("standing-mode-wsol", Nel=nel, R=r, Dt="0.002"), "newmark",
+                            stream=stream.cuda_stream)
+            gs.init()
+            ms_s, by_s = gs.bench_spmv(api.MAT_SYS1, reps=10, flush_l2=True)
+            ms_c, by_c = gs.bench_cg_iter(api.MAT_SYS1, reps=2)
+            at_scale.append({"Nel": nel, "R": r, "n_dofs": gs.n, "nnz": gs.nnz_local,
+                             "spmv": {"ms": ms_s, "GB/s": by_s / ms_s / 1e6, "frac": by_s / ms_s / 1e6 / peak,
+                                      "algorithmic_bytes": by_s, "l2": "flushed before every launch"},
+                             "cg_iteration": {"ms": ms_c, "GB/s": by_c / ms_c / 1e6, "frac": by_c / ms_c / 1e6 / peak,
+                                              "algorithmic_bytes": by_c}})
+            gs.close()
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         r = time_oracle(params, scheme, budget_s=20.0, max_steps=10)
@@ -352,7 +373,7 @@ def main():
                    "l2": "flushed between steps (256 MiB write)" if flush is not None else "not flushed",
                    "setup_s": setup_s, "wall_s_timed_region": wall_s},
         "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
-        "cpu_baseline": cpu,
+        "roofline_at_scale": at_scale, "cpu_baseline": cpu,
         "cg": {"solves": cgs["solves"], "iterations": cgs["iterations"], "ms_total": cgs["ms_total"],
                "ms_per_iteration": cgs["ms_total"] / max(cgs["iterations"], 1)},
         "step_ms": {"min": min(step_ms), "max": max(step_ms)},
