@@ -91,6 +91,10 @@ struct wave_ctx {
     bool has[WAVE_EXPR_COUNT]{};
     Program *dprog = nullptr;  // WAVE_EXPR_COUNT programs
     bool forcing_active = false;
+    // F(x,y,t) = T(t) S(x,y): the load vector of S lives in fvec (assembled once), T is evaluated on the host
+    bool forcing_separable = false;
+    Program f_time{}, f_space{};
+    std::string f_text[3];  // expression, variables, constants as given to wave_set_expr
     Quadrature q_asm{}, q_err{};
 
     // SELL-32-sigma pattern shared by all matrices (owned rows, local column indices) + CSR row pointer
@@ -401,7 +405,16 @@ int upload_cg_control(wave_ctx *ctx) {
     return WAVE_OK;
 }
 
-int compute_forcing(wave_ctx *ctx, double t_np1, double t_n, double w_np1, double w_n, int two_levels) {
+// Load vector of w_np1 F(t_np1) + w_n F(t_n) as `scale * fvec`.  Separable forcing: fvec holds the load
+// vector of S and only the scalar T changes; otherwise the per-cell quadrature kernel runs.
+int compute_forcing(wave_ctx *ctx, double t_np1, double t_n, double w_np1, double w_n, int two_levels,
+                    double *scale) {
+    *scale = 1.0;
+    if (ctx->forcing_separable) {
+        const double T1 = eval(&ctx->f_time, 0.0, 0.0, t_np1);
+        *scale = two_levels ? w_np1 * T1 + w_n * eval(&ctx->f_time, 0.0, 0.0, t_n) : T1;
+        return WAVE_OK;
+    }
     launch_fill(ctx->launcher, ctx->L.nown, 0.0, ctx->fvec);
     launch_forcing(ctx->launcher, ctx->L, ctx->dprog + WAVE_EXPR_F, &ctx->q_asm, t_np1, t_n, w_np1, w_n,
                    two_levels, ctx->fvec);
@@ -428,10 +441,11 @@ int newmark_step(wave_ctx *ctx, double t, int32_t iters[2], double norms[2]) {
         launch_newmark_predict(l, L.nown, dt, dt * dt * (0.5 - beta), dt * (1.0 - gamma), ctx->u + L.own_off,
                                ctx->v + L.own_off, ctx->a + L.own_off);
         RET(halo_exchange(ctx, ctx->u));
-        if (ctx->forcing_active) RET(compute_forcing(ctx, t, 0.0, 1.0, 0.0, 0));
+        double fscale = 1.0;
+        if (ctx->forcing_active) RET(compute_forcing(ctx, t, 0.0, 1.0, 0.0, 0, &fscale));
         SpmvArgs a = spmv_base(ctx);
         a.t[0] = {ctx->K, ctx->u, nullptr, 1.0, 0.0, -1.0};
-        if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = 1.0; }
+        if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = fscale; }
         a.y = ctx->rhs;
         launch_spmv(l, a);
     }
@@ -461,16 +475,17 @@ int theta_step(wave_ctx *ctx, double t, int32_t iters[2], double norms[2]) {
     const Launcher &l = ctx->launcher;
     const double dt = ctx->cfg.dt, th = ctx->cfg.theta;
     int its_u = 0, its_v = 0;
+    double fscale = 1.0;
     {
         PhaseTimer pt(ctx, PH_RHS);
         RET(halo_exchange(ctx, ctx->u));
         RET(halo_exchange(ctx, ctx->v));
-        if (ctx->forcing_active) RET(compute_forcing(ctx, t, t - dt, th, 1.0 - th, 1));
+        if (ctx->forcing_active) RET(compute_forcing(ctx, t, t - dt, th, 1.0 - th, 1, &fscale));
         // rhs = M u + dt M v - dt^2 theta (1-theta) K u + theta dt^2 F_theta
         SpmvArgs a = spmv_base(ctx);
         a.t[0] = {ctx->M, ctx->u, ctx->v, 1.0, dt, 1.0};
         a.t[1] = {ctx->K, ctx->u, nullptr, 1.0, 0.0, -dt * dt * th * (1 - th)};
-        if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = th * dt * dt; }
+        if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = th * dt * dt * fscale; }
         a.y = ctx->rhs;
         launch_spmv(l, a);
         launch_copy(l, L.nloc, ctx->u, ctx->unew);
@@ -491,7 +506,7 @@ int theta_step(wave_ctx *ctx, double t, int32_t iters[2], double norms[2]) {
         SpmvArgs a = spmv_base(ctx);
         a.t[0] = {ctx->M, ctx->v, nullptr, 1.0, 0.0, 1.0};
         a.t[1] = {ctx->K, ctx->u, ctx->unew, 1.0 - th, th, -dt};
-        if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = dt; }
+        if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = dt * fscale; }
         a.y = ctx->rhs;
         launch_spmv(l, a);
     }
@@ -781,6 +796,11 @@ int wave_set_expr(wave_ctx *ctx, int which, const char *expression, const char *
         return fail(ctx, WAVE_ERR_EXPR, e.what());
     }
     ctx->has[which] = true;
+    if (which == WAVE_EXPR_F) {
+        ctx->f_text[0] = expression;
+        ctx->f_text[1] = variable_names ? variable_names : "";
+        ctx->f_text[2] = constants ? constants : "";
+    }
     CK(cudaMemcpyAsync(ctx->dprog + which, &ctx->hprog[which], sizeof(Program), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return WAVE_OK;
@@ -952,6 +972,25 @@ int wave_setup(wave_ctx *ctx) {
     CK(cudaMallocHost((void **)&ctx->hres, 8 * sizeof(double)));
     RET(upload_cg_control(ctx));
 
+    // ---- separable forcing F = T(t) S(x,y): assemble the load vector of S once ---------------------
+    if (ctx->forcing_active && !(ctx->cfg.flags & WAVE_FLAG_FORCING_EVERY_STEP) && !ctx->f_text[0].empty()) {
+        try {
+            ctx->forcing_separable =
+                compile_separable(ctx->f_text[0], ctx->f_text[1], ctx->f_text[2], &ctx->f_time, &ctx->f_space);
+        } catch (const std::exception &) {
+            ctx->forcing_separable = false;
+        }
+        if (ctx->forcing_separable) {
+            Program *dS = nullptr;
+            RET(dev_alloc(ctx, &dS, 1, false));
+            CK(cudaMemcpyAsync(dS, &ctx->f_space, sizeof(Program), cudaMemcpyHostToDevice, ctx->stream));
+            launch_fill(l, L.nown, 0.0, ctx->fvec);
+            launch_forcing(l, L, dS, &ctx->q_asm, 0.0, 0.0, 1.0, 0.0, 0, ctx->fvec);
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaFree(dS));
+        }
+    }
+
     // ---- scheme matrices (src/WaveNewmark.cpp:110-112, :372-374; src/WaveTheta.cpp:110-115) -----
     RET(dev_alloc(ctx, &ctx->S1, (size_t)ctx->nnz_pad, false));
     RET(dev_alloc(ctx, &ctx->dinv1, (size_t)L.nown, false));
@@ -985,10 +1024,11 @@ int wave_init(wave_ctx *ctx) {
         if (ctx->is_init)  // SYS1 must again be the BC-modified mass matrix
             RET(build_system_matrix(ctx, 0.0, ctx->S1, ctx->dinv1, ctx->d0));
         // M a0 = F(0) - K u0 with a0 = second difference of g on the boundary (src/WaveNewmark.cpp:300-385)
-        if (ctx->forcing_active) RET(compute_forcing(ctx, 0.0, 0.0, 1.0, 0.0, 0));
+        double fscale = 1.0;
+        if (ctx->forcing_active) RET(compute_forcing(ctx, 0.0, 0.0, 1.0, 0.0, 0, &fscale));
         SpmvArgs a = spmv_base(ctx);
         a.t[0] = {ctx->K, ctx->u, nullptr, 1.0, 0.0, -1.0};
-        if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = 1.0; }
+        if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = fscale; }
         a.y = ctx->rhs;
         launch_spmv(l, a);
         launch_fill(l, L.nloc, 0.0, ctx->a);
@@ -1259,8 +1299,8 @@ int wave_cg(wave_ctx *ctx, int which, double *x, const double *b, size_t n, int3
         return fail(ctx, WAVE_ERR_ARG, "wave_cg: single rank, n = n_dofs, SYS1 or SYS2");
     const double *dinv = which == WAVE_MAT_SYS1 ? ctx->dinv1 : ctx->dinv2;
     RET(upload_local(ctx, x, ctx->unew));
-    RET(upload_local(ctx, b, ctx->fvec));  // single rank: nloc == nown
-    CK(cudaMemcpyAsync(ctx->rhs, ctx->fvec, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    RET(upload_local(ctx, b, ctx->g));  // single rank: nloc == nown; g is scratch until the solve starts
+    CK(cudaMemcpyAsync(ctx->rhs, ctx->g, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
     int its = 0;
     ctx->prev_its[0] = 0;
     const int rc = cg_solve(ctx, val, dinv, ctx->unew, ctx->rhs, 0, &its);

@@ -325,6 +325,82 @@ Program compile_expression(const std::string &expression, const std::string &var
     return p;
 }
 
+namespace {
+
+// which variables a subtree reads: bit 0 = space (x or y), bit 1 = time
+int dependence(const Ast &a) {
+    int d = 0;
+    if (a.op == OP_VAR) d = a.arg == 2 ? 2 : 1;
+    for (const auto &k : a.kids) d |= dependence(*k);
+    return d;
+}
+AstP clone(const Ast &a) {
+    auto n = std::make_unique<Ast>();
+    n->op = a.op;
+    n->arg = a.arg;
+    n->val = a.val;
+    for (const auto &k : a.kids) n->kids.push_back(clone(*k));
+    return n;
+}
+// flatten a chain of * and / (and unary minus) into (factor, is_divisor) pairs
+void factors(const Ast &a, bool inverse, std::vector<std::pair<const Ast *, bool>> &out, double &sign) {
+    if (a.op == OP_MUL) {
+        factors(*a.kids[0], inverse, out, sign);
+        factors(*a.kids[1], inverse, out, sign);
+    } else if (a.op == OP_DIV) {
+        factors(*a.kids[0], inverse, out, sign);
+        factors(*a.kids[1], !inverse, out, sign);
+    } else if (a.op == OP_NEG) {
+        sign = -sign;
+        factors(*a.kids[0], inverse, out, sign);
+    } else
+        out.emplace_back(&a, inverse);
+}
+AstP product(AstP acc, AstP f, bool inverse) {
+    return node(inverse ? OP_DIV : OP_MUL, 0, std::move(acc), std::move(f));
+}
+
+}  // namespace
+
+bool compile_separable(const std::string &expression, const std::string &variables, const std::string &constants,
+                       Program *time_part, Program *space_part) {
+    auto consts = parse_constants(constants);
+    consts["pi"] = M_PI;
+    std::vector<std::string> vars;
+    {
+        std::stringstream ss(variables);
+        std::string item;
+        while (std::getline(ss, item, ',')) {
+            item = trimmed(item);
+            if (!item.empty()) vars.push_back(item);
+        }
+    }
+    if (vars.size() != 3) return false;  // no time variable: nothing to separate
+    Parser ps(expression, vars, consts);
+    AstP root = ps.parse();
+    std::vector<std::pair<const Ast *, bool>> fs;
+    double sign = 1.0;
+    factors(*root, false, fs, sign);
+    AstP t = leaf(sign), s = leaf(1.0);
+    for (const auto &f : fs) {
+        const int d = dependence(*f.first);
+        if (d == 3) return false;  // a factor mixes space and time
+        if (d == 2) t = product(std::move(t), clone(*f.first), f.second);
+        else s = product(std::move(s), clone(*f.first), f.second);
+    }
+    fold(t);
+    fold(s);
+    auto finish = [](AstP &r, Program *p, int td) {
+        *p = Program{};
+        p->time_dependent = td;
+        int depth = 0, maxdepth = 0;
+        emit(*r, *p, depth, maxdepth);
+    };
+    finish(t, time_part, 1);
+    finish(s, space_part, 1);
+    return true;
+}
+
 bool is_constant(const Program &p, double *value) {
     if (p.len == 1 && p.code[0].op == OP_CONST) {
         if (value) *value = p.code[0].val;
