@@ -76,6 +76,19 @@ enum Phase { PH_RHS = 0, PH_BC, PH_CG, PH_UPDATE, PH_ENERGY, PH_OTHER, PH_COUNT 
 
 }  // namespace
 
+// one level of the multigrid hierarchy (WAVE_PRECOND_MG); level 0 is the solver context itself
+struct MgLevel {
+    wave_ctx *c = nullptr;
+    const double *S = nullptr, *dinv = nullptr;
+    double *x = nullptr, *x2 = nullptr, *b = nullptr, *r = nullptr;
+    double omega = 0.8;
+};
+struct Mg {
+    int nlev = 0, nu = 2, nu_coarse = 8;
+    MgLevel lev[16];
+    double s = 0.0;
+};
+
 struct wave_ctx {
     wave_config cfg{};
     Layout L{};
@@ -133,6 +146,10 @@ struct wave_ctx {
     double *res = nullptr;    // device scalars [8]
     double *hres = nullptr;   // pinned [8]
     int prev_its[2] = {0, 0};
+
+    // multigrid preconditioner
+    Mg *mg = nullptr;
+    double *mg_buf[3] = {nullptr, nullptr, nullptr};  // level-0 work vectors
 
     // NCCL + NVLink peer exchange
     Nccl::comm_t comm = nullptr;
@@ -299,10 +316,67 @@ SpmvArgs spmv_base(wave_ctx *ctx) {
 
 // SolverCG::solve (src/WaveNewmark.cpp:256-261): Jacobi-PCG on the BC-modified matrix `Sval`,
 // start vector x (local layout), right-hand side b (row-indexed).
+// V-cycle on level l: lev.x <- approximate solution of S x = lev.b from x = 0 (all launches asynchronous)
+void mg_smooth(wave_ctx *ctx, MgLevel &lv, int sweeps, bool x_is_zero) {
+    wave_ctx *c = lv.c;
+    const int *skip = &ctx->S->status;
+    for (int sw = 0; sw < sweeps; ++sw) {
+        if (sw == 0 && x_is_zero) {
+            launch_scale_rows(ctx->launcher, c->L.nown, lv.omega, lv.dinv, lv.b, lv.x, skip);
+            continue;
+        }
+        SpmvArgs a = spmv_base(c);
+        a.partials = ctx->partials;
+        a.counter = ctx->counter;
+        a.t[0] = {lv.S, lv.x, nullptr, 1.0, 0.0, -1.0};
+        a.add0 = lv.b; a.addc0 = 1.0;
+        a.dinv = lv.dinv; a.jac_x = lv.x; a.jac_omega = lv.omega;
+        a.y = lv.x2;
+        a.skip_flag = skip;
+        launch_spmv(ctx->launcher, a);
+        std::swap(lv.x, lv.x2);
+    }
+}
+void mg_vcycle(wave_ctx *ctx, int l) {
+    Mg &m = *ctx->mg;
+    MgLevel &lv = m.lev[l];
+    const int *skip = &ctx->S->status;
+    if (l == m.nlev - 1) { mg_smooth(ctx, lv, m.nu_coarse, true); return; }
+    mg_smooth(ctx, lv, m.nu, true);
+    {   // r = b - S x
+        SpmvArgs a = spmv_base(lv.c);
+        a.partials = ctx->partials;
+        a.counter = ctx->counter;
+        a.t[0] = {lv.S, lv.x, nullptr, 1.0, 0.0, -1.0};
+        a.add0 = lv.b; a.addc0 = 1.0;
+        a.y = lv.r;
+        a.skip_flag = skip;
+        launch_spmv(ctx->launcher, a);
+    }
+    MgLevel &cv = m.lev[l + 1];
+    const bool p_coarsening = lv.c->L.mesh.r == 2;
+    if (p_coarsening) launch_restrict_p2p1(ctx->launcher, lv.c->L, cv.c->L, lv.r, cv.b, skip);
+    else launch_restrict_p1(ctx->launcher, lv.c->L, cv.c->L, lv.r, cv.b, skip);
+    mg_vcycle(ctx, l + 1);
+    if (p_coarsening) launch_prolong_add_p2p1(ctx->launcher, lv.c->L, cv.c->L, cv.x, lv.x, skip);
+    else launch_prolong_add_p1(ctx->launcher, lv.c->L, cv.c->L, cv.x, lv.x, skip);
+    mg_smooth(ctx, lv, m.nu, false);
+}
+// z = V-cycle(g) on the fine level; returns the vector holding z
+const double *mg_apply(wave_ctx *ctx, const double *Sval, const double *dinv, const double *g) {
+    MgLevel &f = ctx->mg->lev[0];
+    f.S = Sval;
+    f.dinv = dinv;
+    f.b = const_cast<double *>(g);
+    mg_vcycle(ctx, 0);
+    return f.x;
+}
+
 int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, const double *b, int slot,
-             int *iters) {
+             int *iters, bool use_mg = false) {
     const Layout &L = ctx->L;
     const Launcher &l = ctx->launcher;
+    use_mg = use_mg && ctx->mg != nullptr;
     cudaEvent_t e0 = ctx->ev[2 * PH_COUNT], e1 = ctx->ev[2 * PH_COUNT + 1];
     CK(cudaEventRecord(e0, ctx->stream));
     RET(halo_exchange(ctx, x));
@@ -311,10 +385,14 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
         a.t[0] = {Sval, x, nullptr, 1.0, 0.0, 1.0};
         a.add0 = b; a.addc0 = -1.0;
         a.y = ctx->g;
-        a.dinv = dinv; a.h_out = ctx->h; a.d_out = ctx->d + L.own_off;
+        if (!use_mg) { a.dinv = dinv; a.h_out = ctx->h; a.d_out = ctx->d + L.own_off; }
         a.dot_mode = 2;
         a.result = &ctx->S->gg;
         launch_spmv(l, a);
+    }
+    if (use_mg) {  // h = V-cycle(g) ; d = -h ; gh = g.h
+        const double *z = mg_apply(ctx, Sval, dinv, ctx->g);
+        launch_dot_gz(l, L.nown, ctx->g, z, ctx->d + L.own_off, ctx->partials, ctx->counter, &ctx->S->gh_new, nullptr);
     }
     RET(allreduce(ctx, &ctx->S->gg, 2));
     launch_cg_start(l, ctx->S);
@@ -352,11 +430,17 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
             }
             if (!p2p) RET(allreduce(ctx, &ctx->S->dAd, 1));
             const unsigned long long seq_b = p2p ? ++ctx->ar_seq : 0ull;
-            launch_cg_update(l, L.nown, ctx->S, x + L.own_off, ctx->g, ctx->h, ctx->d + L.own_off, dinv,
-                             ctx->partials, ctx->counter, p2p ? ctx->pc : PeerComm{}, seq_b);
+            launch_cg_update(l, L.nown, ctx->S, x + L.own_off, ctx->g, ctx->h, ctx->d + L.own_off,
+                             use_mg ? nullptr : dinv, ctx->partials, ctx->counter, p2p ? ctx->pc : PeerComm{}, seq_b);
+            const double *z = ctx->h;
+            if (use_mg) {  // h' = V-cycle(g) ; gh' = g.h'
+                z = mg_apply(ctx, Sval, dinv, ctx->g);
+                launch_dot_gz(l, L.nown, ctx->g, z, nullptr, ctx->partials, ctx->counter, &ctx->S->gh_new,
+                              &ctx->S->status);
+            }
             if (!p2p) RET(allreduce(ctx, &ctx->S->gg, 2));
             const unsigned long long seq_h = p2p ? ++ctx->halo_seq : 0ull;
-            launch_cg_direction(l, L.nown, ctx->S, ctx->d + L.own_off, ctx->h, ctx->counter,
+            launch_cg_direction(l, L.nown, ctx->S, ctx->d + L.own_off, z, ctx->counter,
                                 p2p ? ctx->pc : PeerComm{}, seq_h);
         }
         enq += chunk;
@@ -457,7 +541,7 @@ int newmark_step(wave_ctx *ctx, double t, int32_t iters[2], double norms[2]) {
     }
     {
         PhaseTimer pt(ctx, PH_CG);
-        RET(cg_solve(ctx, ctx->S1, ctx->dinv1, ctx->a, ctx->rhs, 0, &its));
+        RET(cg_solve(ctx, ctx->S1, ctx->dinv1, ctx->a, ctx->rhs, 0, &its, true));
     }
     {
         PhaseTimer pt(ctx, PH_UPDATE);
@@ -497,7 +581,7 @@ int theta_step(wave_ctx *ctx, double t, int32_t iters[2], double norms[2]) {
     }
     {
         PhaseTimer pt(ctx, PH_CG);
-        RET(cg_solve(ctx, ctx->S1, ctx->dinv1, ctx->unew, ctx->rhs, 0, &its_u));
+        RET(cg_solve(ctx, ctx->S1, ctx->dinv1, ctx->unew, ctx->rhs, 0, &its_u, true));
     }
     {
         PhaseTimer pt(ctx, PH_RHS);
@@ -613,6 +697,81 @@ int dev_alloc(wave_ctx *ctx, T **p, size_t count, bool zero = true) {
     return WAVE_OK;
 }
 
+// Build the multigrid hierarchy for the scheme matrix bc(M + s K): [P2 on the mesh ->] P1 on the mesh ->
+// P1 on Nel/2, Nel/4, ... while the stiffness part still matters (s c^2 / (dx dy) > 1/4) and the mesh
+// halves evenly.  Every coarse level is a child context (pattern, rediscretised M and K, Dirichlet rows,
+// Jacobi diagonal) running on the parent's stream; its u / unew / rhs / g vectors serve as x / x2 / b / r.
+int mg_setup(wave_ctx *ctx, double s) {
+    if (ctx->mg && ctx->mg->s == s) return WAVE_OK;
+    if (ctx->mg) {
+        for (int l = 1; l < ctx->mg->nlev; ++l) wave_destroy(ctx->mg->lev[l].c);
+        delete ctx->mg;
+        ctx->mg = nullptr;
+    }
+    Mg *m = new Mg();
+    m->s = s;
+    const Layout &L = ctx->L;
+    for (int k = 0; k < 3; ++k)
+        if (!ctx->mg_buf[k]) RET(dev_alloc(ctx, &ctx->mg_buf[k], (size_t)L.nloc));
+    m->lev[0].c = ctx;
+    m->lev[0].x = ctx->mg_buf[0];
+    m->lev[0].x2 = ctx->mg_buf[1];
+    m->lev[0].r = ctx->mg_buf[2];
+    m->lev[0].omega = L.mesh.r == 2 ? 0.5 : 0.8;
+    m->nlev = 1;
+    const double cx = 0.5 * (ctx->cfg.x0 + ctx->cfg.x1), cy = 0.5 * (ctx->cfg.y0 + ctx->cfg.y1);
+    const double c0 = eval(&ctx->hprog[WAVE_EXPR_C], cx, cy, 0.0);
+    int nx = L.mesh.nx, ny = L.mesh.ny, r = L.mesh.r;
+    for (;;) {
+        int nnx = nx, nny = ny;
+        if (r == 1) {
+            const double dx = (ctx->cfg.x1 - ctx->cfg.x0) / nx, dy = (ctx->cfg.y1 - ctx->cfg.y0) / ny;
+            const bool matters = s * c0 * c0 / (dx * dy) > 0.25;
+            if (!(matters && nx % 2 == 0 && ny % 2 == 0 && std::min(nx, ny) / 2 >= 2)) break;
+            nnx = nx / 2;
+            nny = ny / 2;
+        }
+        if (m->nlev >= 12) break;
+        wave_config cfg = ctx->cfg;
+        cfg.nx = nnx; cfg.ny = nny; cfg.r = 1;
+        cfg.scheme = WAVE_SCHEME_NEWMARK;
+        cfg.rank = 0; cfg.nranks = 1; cfg.nccl_unique_id = nullptr; cfg.device = -1;
+        cfg.precond = WAVE_PRECOND_JACOBI;
+        cfg.flags = 0;
+        cfg.stream = ctx->stream;
+        wave_ctx *c = nullptr;
+        if (wave_create(&cfg, &c) != WAVE_OK) { delete m; return fail(ctx, WAVE_ERR_CUDA, wave_last_error(nullptr)); }
+        const Program zero = compile_expression("0.0", "x, y, t", "");
+        for (int k = 0; k < WAVE_EXPR_SOLUTION; ++k) {
+            c->hprog[k] = k == WAVE_EXPR_C ? ctx->hprog[k] : zero;
+            c->has[k] = true;
+        }
+        cudaMemcpyAsync(c->dprog, c->hprog, sizeof(Program) * WAVE_EXPR_COUNT, cudaMemcpyHostToDevice, c->stream);
+        int rc = wave_setup(c);
+        if (rc == WAVE_OK) rc = build_system_matrix(c, s, c->S1, c->dinv1, c->d0);
+        if (rc != WAVE_OK) {
+            const std::string msg = std::string("multigrid level setup: ") + wave_last_error(c);
+            wave_destroy(c);
+            delete m;
+            return fail(ctx, rc, msg);
+        }
+        MgLevel &lv = m->lev[m->nlev++];
+        lv.c = c;
+        lv.S = c->S1;
+        lv.dinv = c->dinv1;
+        lv.x = c->u;
+        lv.x2 = c->unew;
+        lv.b = c->rhs;
+        lv.r = c->g;
+        lv.omega = 0.8;
+        ctx->launches += c->launches;
+        nx = nnx; ny = nny; r = 1;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->mg = m;
+    return WAVE_OK;
+}
+
 // Map every rank's mailbox and the neighbours' search-direction vectors through CUDA IPC; the 64-byte
 // handles travel over NCCL broadcasts.  Disabled (NCCL collectives stay) for nranks > kMaxPeers or
 // when WAVE_NO_P2P is set.
@@ -710,6 +869,8 @@ int wave_create(const wave_config *cfg, wave_ctx **out) {
     if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks)
         return fail(nullptr, WAVE_ERR_ARG, "bad rank / nranks");
     if (cfg->ny < cfg->nranks) return fail(nullptr, WAVE_ERR_ARG, "need at least one quad row per rank");
+    if (cfg->precond == WAVE_PRECOND_MG && cfg->nranks > 1)
+        return fail(nullptr, WAVE_ERR_UNSUPPORTED, "the multigrid preconditioner runs on a single rank");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(nullptr, WAVE_ERR_CUDA, "no CUDA device: libwavegpu has no CPU fallback");
@@ -766,6 +927,12 @@ int wave_create(const wave_config *cfg, wave_ctx **out) {
 void wave_destroy(wave_ctx *ctx) {
     if (!ctx) return;
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->mg) {
+        for (int l = 1; l < ctx->mg->nlev; ++l) wave_destroy(ctx->mg->lev[l].c);
+        delete ctx->mg;
+    }
+    for (double *b : ctx->mg_buf)
+        if (b) cudaFree(b);
     for (int k = 0; k < ctx->n_ipc_opened; ++k) cudaIpcCloseMemHandle(ctx->ipc_opened[k]);
     if (ctx->mailbox) cudaFree(ctx->mailbox);
     void *ptrs[] = {ctx->dprog, ctx->rowptr, ctx->slice_ptr, ctx->row_of, ctx->slot_of, ctx->col, ctx->c2i, ctx->i2c, ctx->tmp, ctx->M, ctx->K, ctx->S1, ctx->S2, ctx->dinv1, ctx->dinv2,
@@ -1040,6 +1207,12 @@ int wave_init(wave_ctx *ctx) {
         RET(halo_exchange(ctx, ctx->a));
         RET(build_system_matrix(ctx, beta * dt * dt, ctx->S1, ctx->dinv1, ctx->d0));
         ctx->prev_its[0] = 0;
+    }
+    if (ctx->cfg.precond == WAVE_PRECOND_MG) {
+        const double dt = ctx->cfg.dt;
+        const double s = ctx->cfg.scheme == WAVE_SCHEME_NEWMARK ? ctx->cfg.beta * dt * dt
+                                                                : (ctx->cfg.theta * dt) * (ctx->cfg.theta * dt);
+        if (s > 0.0) RET(mg_setup(ctx, s));
     }
     RET(sync_check(ctx));
     ctx->is_init = true;

@@ -597,6 +597,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmv(SpmvArgs a) {
         if (r >= 0) {
             if (a.add0) s += a.addc0 * a.add0[r];
             if (a.add1) s += a.addc1 * a.add1[r];
+            if (a.jac_x) s = a.jac_x[r] + a.jac_omega * (a.dinv[r] * s);
             if (a.y) a.y[r] = s;
             double hv = 0.0;
             if (a.h_out) {
@@ -649,15 +650,17 @@ __global__ void __launch_bounds__(kThreads) k_cg_update(int n, CgScalars *S, dou
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         x[i] += alpha * d[i];
         const double gi = g[i] + alpha * h[i];
-        const double hi = dinv[i] * gi;
         g[i] = gi;
-        h[i] = hi;
         acc[0] += gi * gi;
-        acc[1] += gi * hi;
+        if (dinv) {  // Jacobi fused here; with the multigrid preconditioner h is produced by the V-cycle
+            const double hi = dinv[i] * gi;
+            h[i] = hi;
+            acc[1] += gi * hi;
+        }
     }
     if (grid_sum_peers<2>(acc, partials, counter, pc, ar_seq) && threadIdx.x == 0) {
         S->gg = acc[0];
-        S->gh_new = acc[1];
+        if (dinv) S->gh_new = acc[1];
     }
 }
 // iteration_status(it, res); beta = gh'/gh ; d = beta d - h
@@ -696,6 +699,89 @@ __global__ void __launch_bounds__(kThreads) k_cg_direction(int n, CgScalars *S, 
             if (pc.rank < pc.nranks - 1) st_release_sys(&pc.box[pc.rank + 1]->halo_flag[0], halo_seq);
         }
     }
+}
+
+// ---- multigrid V-cycle pieces -----------------------------------------------------------------------
+// Transfers are FE interpolation between nested spaces, written as closed-form stencils: a fine P1
+// vertex is a coarse vertex (weight 1) or the midpoint of a coarse edge -- horizontal, vertical or the
+// diagonal (i+1,j)-(i,j+1) of the structured triangulation (weights 1/2, 1/2); a P2 edge DoF is the
+// midpoint of its edge.  Restriction is the transpose, with Dirichlet rows of the coarse level zeroed.
+__global__ void k_scale_rows(int n, double omega, const double *__restrict__ dinv, const double *__restrict__ b,
+                             double *__restrict__ x, const int *skip_flag) {
+    if (skip_flag && *skip_flag != 0) return;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = omega * (dinv[i] * b[i]);
+}
+__global__ void k_prolong_add_p1(Mesh mf, Mesh mc, const double *__restrict__ ec, double *__restrict__ xf,
+                                 const int *skip_flag) {
+    if (skip_flag && *skip_flag != 0) return;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)(mf.nx + 1) * (mf.ny + 1)) return;
+    const int I = (int)(t % (mf.nx + 1)), J = (int)(t / (mf.nx + 1));
+    double v;
+    if (!(I & 1) && !(J & 1)) v = ec[dof_V(mc, I / 2, J / 2)];
+    else if ((I & 1) && !(J & 1)) v = 0.5 * (ec[dof_V(mc, (I - 1) / 2, J / 2)] + ec[dof_V(mc, (I + 1) / 2, J / 2)]);
+    else if (!(I & 1)) v = 0.5 * (ec[dof_V(mc, I / 2, (J - 1) / 2)] + ec[dof_V(mc, I / 2, (J + 1) / 2)]);
+    else v = 0.5 * (ec[dof_V(mc, (I + 1) / 2, (J - 1) / 2)] + ec[dof_V(mc, (I - 1) / 2, (J + 1) / 2)]);
+    xf[dof_V(mf, I, J)] += v;
+}
+__global__ void k_restrict_p1(Mesh mf, Mesh mc, const double *__restrict__ rf, double *__restrict__ bc,
+                              const int *skip_flag) {
+    if (skip_flag && *skip_flag != 0) return;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)(mc.nx + 1) * (mc.ny + 1)) return;
+    const int i = (int)(t % (mc.nx + 1)), j = (int)(t / (mc.nx + 1));
+    double s = 0.0;
+    if (i > 0 && i < mc.nx && j > 0 && j < mc.ny) {
+        const int I = 2 * i, J = 2 * j;
+        s = rf[dof_V(mf, I, J)] +
+            0.5 * (rf[dof_V(mf, I - 1, J)] + rf[dof_V(mf, I + 1, J)] + rf[dof_V(mf, I, J - 1)] +
+                   rf[dof_V(mf, I, J + 1)] + rf[dof_V(mf, I + 1, J - 1)] + rf[dof_V(mf, I - 1, J + 1)]);
+    }
+    bc[dof_V(mc, i, j)] = s;
+}
+__global__ void k_prolong_add_p2p1(Mesh mf, Mesh mc, const double *__restrict__ ec, double *__restrict__ xf,
+                                   const int *skip_flag) {
+    if (skip_flag && *skip_flag != 0) return;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 4LL * (mf.nx + 1) * (mf.ny + 1)) return;
+    const int kind = (int)(t & 3);
+    const int64_t q = t >> 2;
+    const int i = (int)(q % (mf.nx + 1)), j = (int)(q / (mf.nx + 1));
+    const int64_t dof = entity_dof_internal(mf, i, j, kind);
+    if (dof < 0) return;
+    double v;
+    if (kind == 0) v = ec[dof_V(mc, i, j)];
+    else if (kind == 1) v = 0.5 * (ec[dof_V(mc, i, j)] + ec[dof_V(mc, i + 1, j)]);
+    else if (kind == 2) v = 0.5 * (ec[dof_V(mc, i, j)] + ec[dof_V(mc, i, j + 1)]);
+    else v = 0.5 * (ec[dof_V(mc, i + 1, j)] + ec[dof_V(mc, i, j + 1)]);
+    xf[dof] += v;
+}
+__global__ void k_restrict_p2p1(Mesh mf, Mesh mc, const double *__restrict__ rf, double *__restrict__ bc,
+                                const int *skip_flag) {
+    if (skip_flag && *skip_flag != 0) return;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)(mc.nx + 1) * (mc.ny + 1)) return;
+    const int i = (int)(t % (mc.nx + 1)), j = (int)(t / (mc.nx + 1));
+    double s = 0.0;
+    if (i > 0 && i < mc.nx && j > 0 && j < mc.ny)
+        s = rf[idof_V(mf, i, j)] +
+            0.5 * (rf[idof_B(mf, i - 1, j)] + rf[idof_B(mf, i, j)] + rf[idof_L(mf, i, j - 1)] + rf[idof_L(mf, i, j)] +
+                   rf[idof_D(mf, i - 1, j)] + rf[idof_D(mf, i, j - 1)]);
+    bc[dof_V(mc, i, j)] = s;
+}
+__global__ void __launch_bounds__(kThreads) k_dot_gz(int n, const double *__restrict__ g, const double *__restrict__ z,
+                                                     double *d, double *partials, unsigned *counter, double *result,
+                                                     const int *skip_flag) {
+    if (skip_flag && *skip_flag != 0) return;
+    double acc[1] = {0.0};
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double zi = z[i];
+        acc[0] += g[i] * zi;
+        if (d) d[i] = -zi;
+    }
+    if (grid_sum<1>(acc, partials, counter) && threadIdx.x == 0) result[0] = acc[0];
 }
 
 // ---- K7: fused Newmark vector updates (src/WaveNewmark.cpp:121-126, :264-278, :429-430) --------------
@@ -992,6 +1078,34 @@ void launch_zero_rows(const Launcher &l, int nb, const int32_t *brow, double *ve
     WV_LAUNCH(l, k_zero_rows, blocks_for(nb, 128), 128, 0, nb, brow, vec);
 }
 void launch_cg_start(const Launcher &l, CgScalars *S) { WV_LAUNCH(l, k_cg_start, 1, 32, 0, S); }
+void launch_scale_rows(const Launcher &l, int n, double omega, const double *dinv, const double *b, double *x,
+                       const int *skip_flag) {
+    WV_LAUNCH(l, k_scale_rows, stream_blocks(n), kThreads, 0, n, omega, dinv, b, x, skip_flag);
+}
+void launch_prolong_add_p1(const Launcher &l, const Layout &Lf, const Layout &Lc, const double *ec, double *xf,
+                           const int *skip_flag) {
+    const int64_t n = (int64_t)(Lf.mesh.nx + 1) * (Lf.mesh.ny + 1);
+    WV_LAUNCH(l, k_prolong_add_p1, blocks_for(n, kThreads), kThreads, 0, Lf.mesh, Lc.mesh, ec, xf, skip_flag);
+}
+void launch_restrict_p1(const Launcher &l, const Layout &Lf, const Layout &Lc, const double *rf, double *bc,
+                        const int *skip_flag) {
+    const int64_t n = (int64_t)(Lc.mesh.nx + 1) * (Lc.mesh.ny + 1);
+    WV_LAUNCH(l, k_restrict_p1, blocks_for(n, kThreads), kThreads, 0, Lf.mesh, Lc.mesh, rf, bc, skip_flag);
+}
+void launch_prolong_add_p2p1(const Launcher &l, const Layout &Lf, const Layout &Lc, const double *ec, double *xf,
+                             const int *skip_flag) {
+    const int64_t n = 4LL * (Lf.mesh.nx + 1) * (Lf.mesh.ny + 1);
+    WV_LAUNCH(l, k_prolong_add_p2p1, blocks_for(n, kThreads), kThreads, 0, Lf.mesh, Lc.mesh, ec, xf, skip_flag);
+}
+void launch_restrict_p2p1(const Launcher &l, const Layout &Lf, const Layout &Lc, const double *rf, double *bc,
+                          const int *skip_flag) {
+    const int64_t n = (int64_t)(Lc.mesh.nx + 1) * (Lc.mesh.ny + 1);
+    WV_LAUNCH(l, k_restrict_p2p1, blocks_for(n, kThreads), kThreads, 0, Lf.mesh, Lc.mesh, rf, bc, skip_flag);
+}
+void launch_dot_gz(const Launcher &l, int n, const double *g, const double *z, double *d_or_null, double *partials,
+                   unsigned *counter, double *result, const int *skip_flag) {
+    WV_LAUNCH(l, k_dot_gz, stream_blocks(n), kThreads, 0, n, g, z, d_or_null, partials, counter, result, skip_flag);
+}
 void launch_cg_update(const Launcher &l, int n, CgScalars *S, double *x, double *g, double *h, const double *d,
                       const double *dinv, double *partials, unsigned *counter, const PeerComm &pc,
                       unsigned long long ar_seq) {

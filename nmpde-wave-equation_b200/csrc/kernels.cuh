@@ -102,6 +102,9 @@ struct SpmvArgs {
     // residual epilogue (CG start): h = dinv*y, d = -h
     const double *dinv;
     double *h_out, *d_out;
+    // damped-Jacobi epilogue (multigrid smoother): y_r = jac_x_r + jac_omega * dinv_r * s_r
+    const double *jac_x;
+    double jac_omega;
     // fused dots: mode 0 none, 1 sum y_i*dotv_i, 2 {sum y_i^2, sum y_i*h_i}
     int dot_mode;
     const double *dotv;
@@ -158,6 +161,23 @@ void launch_spmv(const Launcher &, const SpmvArgs &);
 void launch_zero_rows(const Launcher &, int nb, const int32_t *brow, double *vec);
 int spmv_grid_blocks(int nslices);
 void launch_cg_start(const Launcher &, CgScalars *S);
+// ---- multigrid V-cycle pieces (preconditioner WAVE_PRECOND_MG) -----------------------------------
+// x = omega * dinv * b
+void launch_scale_rows(const Launcher &, int n, double omega, const double *dinv, const double *b, double *x,
+                       const int *skip_flag);
+// P1 on mesh Lc (Nel/2) <-> P1 on mesh Lf: x_f += P e_c ; b_c = P^T r_f with Dirichlet rows zeroed
+void launch_prolong_add_p1(const Launcher &, const Layout &Lf, const Layout &Lc, const double *ec, double *xf,
+                           const int *skip_flag);
+void launch_restrict_p1(const Launcher &, const Layout &Lf, const Layout &Lc, const double *rf, double *bc,
+                        const int *skip_flag);
+// P1 <-> P2 on the same mesh (Lf: r = 2, storage numbering; Lc: r = 1)
+void launch_prolong_add_p2p1(const Launcher &, const Layout &Lf, const Layout &Lc, const double *ec, double *xf,
+                             const int *skip_flag);
+void launch_restrict_p2p1(const Launcher &, const Layout &Lf, const Layout &Lc, const double *rf, double *bc,
+                          const int *skip_flag);
+// result[0] = g.z ; optionally d = -z (CG start)
+void launch_dot_gz(const Launcher &, int n, const double *g, const double *z, double *d_or_null, double *partials,
+                   unsigned *counter, double *result, const int *skip_flag);
 void launch_cg_update(const Launcher &, int n, CgScalars *S, double *x, double *g, double *h, const double *d,
                       const double *dinv, double *partials, unsigned *counter, const PeerComm &pc,
                       unsigned long long ar_seq);

@@ -438,6 +438,7 @@ typedef struct {
     double xi[16], eta[16], w[16];
 } quadrule_t;
 
+struct mg_t;
 typedef struct oracle_problem {
     int Nx, Ny, r;
     double x0, x1, y0, y1;
@@ -471,7 +472,9 @@ typedef struct oracle_problem {
     int cg_maxit;
     double cg_tol, cg_reduce;
     int last_its[2];
-    int precond; /* 0 = Jacobi (north-star replacement of AMG), 1 = identity */
+    int precond; /* 0 = Jacobi (north-star replacement of AMG), 1 = identity, 2 = multigrid V-cycle */
+    struct mg_t *mg;   /* hierarchy for precond == 2 (built by the scheme init) */
+    int borrowed_expr; /* coarse-level problems share the fine problem's expression trees */
     int forcing_every_step; /* 1 = as the reference (assemble F even if zero) */
 } oracle_problem;
 
@@ -969,17 +972,198 @@ static void apply_bc(oracle_problem *p, double *Sval, const double *bval, double
     }
 }
 
+/* ------------------------------------------------------------------------- */
+/* Geometric multigrid V-cycle preconditioner (precond == 2).                   */
+/* Stands in for TrilinosWrappers::PreconditionAMG (ML smoothed aggregation,     */
+/* Chebyshev smoother, src/WaveNewmark.cpp:246-251) -- "next" row (f).1 of       */
+/* SURVEY section 8.  Hierarchy: [P2 on the mesh ->] P1 on the mesh -> P1 on the */
+/* meshes with Nel/2, Nel/4, ...; coarse operators by rediscretisation           */
+/* bc(M_l + s K_l); transfers = FE interpolation (P[i][j] = phi_j^coarse at the  */
+/* fine support point i) and its transpose; smoother = damped Jacobi, nu pre and */
+/* nu post sweeps (symmetric, so the V-cycle is an SPD preconditioner for CG).   */
+/* ------------------------------------------------------------------------- */
+typedef struct mg_level {
+    oracle_problem *prob; /* level 0: the fine problem itself (not owned) */
+    double *S, *dinv, *x, *b, *r, *t;
+    int64_t *Pptr; /* prolongation from the next coarser level onto this one (rows = this level) */
+    int *Pcol;
+    double *Pval;
+    double omega;
+} mg_level;
+typedef struct mg_t {
+    int nlev, nu, nu_coarse;
+    mg_level lev[16];
+} mg_t;
+
+int oracle_setup(oracle_problem *p);
+int oracle_assemble(oracle_problem *p);
+static void apply_bc(oracle_problem *p, double *Sval, const double *bval, double *x, double *rhs);
+
+static void mg_build_prolongation(const oracle_problem *f, const oracle_problem *c, mg_level *L) {
+    const double dxc = (c->x1 - c->x0) / c->Nx, dyc = (c->y1 - c->y0) / c->Ny;
+    L->Pptr = (int64_t *)malloc(sizeof(int64_t) * (f->n + 1));
+    L->Pcol = (int *)malloc(sizeof(int) * 6 * f->n);
+    L->Pval = (double *)malloc(sizeof(double) * 6 * f->n);
+    int64_t k = 0;
+    for (int64_t i = 0; i < f->n; ++i) {
+        L->Pptr[i] = k;
+        const double x = f->sx[i], y = f->sy[i];
+        int ic = (int)floor((x - c->x0) / dxc + 1e-9), jc = (int)floor((y - c->y0) / dyc + 1e-9);
+        if (ic >= c->Nx) ic = c->Nx - 1;
+        if (jc >= c->Ny) jc = c->Ny - 1;
+        const double a = (x - (c->x0 + ic * dxc)) / dxc, b = (y - (c->y0 + jc * dyc)) / dyc;
+        const int t1 = a + b > 1.0 + 1e-9;
+        const int64_t cell = 2 * ((int64_t)jc * c->Nx + ic) + t1;
+        const double xi = t1 ? 1.0 - a : a, eta = t1 ? 1.0 - b : b;
+        double phi[6], d1[6], d2[6];
+        shape(c->r, xi, eta, phi, d1, d2);
+        for (int q = 0; q < c->dpc; ++q) {
+            const double w = rint(phi[q] * 1024.0) / 1024.0; /* weights are exact dyadic numbers */
+            if (w != 0.0) { L->Pcol[k] = c->cell_dof[c->dpc * cell + q]; L->Pval[k] = w; ++k; }
+        }
+    }
+    L->Pptr[f->n] = k;
+}
+
+static void mg_free(mg_t *m);
+static void oracle_destroy_internal(oracle_problem *p);
+
+/* s: the scheme matrix is M + s K; fineS: the fine level's BC-modified system matrix (borrowed) */
+static int mg_setup(oracle_problem *p, double s, double *fineS) {
+    if (p->mg) { mg_free(p->mg); p->mg = NULL; }
+    mg_t *m = (mg_t *)calloc(1, sizeof(mg_t));
+    m->nu = 2;
+    m->nu_coarse = 8;
+    m->lev[0].prob = p;
+    m->lev[0].S = fineS;
+    m->nlev = 1;
+    int Nx = p->Nx, Ny = p->Ny, r = p->r;
+    /* h-coarsening continues while the stiffness part still matters on the current level:
+       s c^2 / (dx dy) > 1/4 with c taken at the centre of the domain */
+    const double c0 = ev(p, EX_C, 0.5 * (p->x0 + p->x1), 0.5 * (p->y0 + p->y1), 0.0);
+    for (;;) {
+        int nNx = Nx, nNy = Ny, nr = 1;
+        if (r == 2) nr = 1; /* p-coarsening first: same mesh, P1 */
+        else {
+            const double dx = (p->x1 - p->x0) / Nx, dy = (p->y1 - p->y0) / Ny;
+            const int matters = s * c0 * c0 / (dx * dy) > 0.25;
+            if (matters && Nx % 2 == 0 && Ny % 2 == 0 && (Nx / 2 < Ny / 2 ? Nx / 2 : Ny / 2) >= 2) { nNx = Nx / 2; nNy = Ny / 2; }
+            else break;
+        }
+        if (m->nlev >= 12) break;
+        oracle_problem *q = oracle_create(nNx, nNy, p->x0, p->x1, p->y0, p->y1, nr);
+        q->ex[EX_C] = p->ex[EX_C];
+        q->borrowed_expr = 1;
+        oracle_setup(q);
+        oracle_assemble(q);
+        mg_level *L = &m->lev[m->nlev];
+        L->prob = q;
+        L->S = (double *)malloc(sizeof(double) * q->nnz);
+        for (int64_t k = 0; k < q->nnz; ++k) L->S[k] = q->M[k] + s * q->K[k];
+        double *zero = (double *)calloc(q->nb ? q->nb : 1, sizeof(double));
+        apply_bc(q, L->S, zero, q->t1, q->t2);
+        free(zero);
+        mg_build_prolongation(m->lev[m->nlev - 1].prob, q, &m->lev[m->nlev - 1]);
+        m->nlev++;
+        Nx = nNx; Ny = nNy; r = nr;
+    }
+    for (int l = 0; l < m->nlev; ++l) {
+        mg_level *L = &m->lev[l];
+        const oracle_problem *q = L->prob;
+        L->omega = q->r == 2 ? 0.5 : 0.8;
+        L->dinv = (double *)malloc(sizeof(double) * q->n);
+        L->x = (double *)calloc(q->n, sizeof(double));
+        L->b = (double *)calloc(q->n, sizeof(double));
+        L->r = (double *)calloc(q->n, sizeof(double));
+        L->t = (double *)calloc(q->n, sizeof(double));
+        if (l > 0)
+            for (int64_t i = 0; i < q->n; ++i) L->dinv[i] = 1.0 / L->S[csr_find(q, (int)i, (int)i)];
+    }
+    {   /* fine level: p->S is rebuilt every step (copy + apply_boundary_values); its diagonal is that
+           of bc(M + s K), formed here once */
+        mg_level *L = &m->lev[0];
+        double *tmpS = (double *)malloc(sizeof(double) * p->nnz);
+        for (int64_t k = 0; k < p->nnz; ++k) tmpS[k] = p->M[k] + s * p->K[k];
+        double *zero = (double *)calloc(p->nb ? p->nb : 1, sizeof(double));
+        apply_bc(p, tmpS, zero, L->t, L->r);
+        for (int64_t i = 0; i < p->n; ++i) L->dinv[i] = 1.0 / tmpS[csr_find(p, (int)i, (int)i)];
+        memset(L->t, 0, sizeof(double) * p->n);
+        memset(L->r, 0, sizeof(double) * p->n);
+        free(zero);
+        free(tmpS);
+    }
+    p->mg = m;
+    return m->nlev;
+}
+
+/* x <- x + omega D^-1 (b - S x), `sweeps` times; the first sweep from x = 0 is x = omega D^-1 b */
+static void mg_smooth(mg_level *L, int sweeps, int x_is_zero) {
+    const oracle_problem *q = L->prob;
+    for (int sw = 0; sw < sweeps; ++sw) {
+        if (sw == 0 && x_is_zero) {
+            for (int64_t i = 0; i < q->n; ++i) L->x[i] = L->omega * (L->dinv[i] * L->b[i]);
+            continue;
+        }
+        spmv(q, L->S, L->x, L->t);
+        for (int64_t i = 0; i < q->n; ++i) L->x[i] = L->x[i] + L->omega * (L->dinv[i] * (L->b[i] - L->t[i]));
+    }
+}
+static void mg_vcycle(mg_t *m, int l) {
+    mg_level *L = &m->lev[l];
+    const oracle_problem *q = L->prob;
+    if (l == m->nlev - 1) { mg_smooth(L, m->nu_coarse, 1); return; }
+    mg_smooth(L, m->nu, 1);
+    spmv(q, L->S, L->x, L->t);
+    for (int64_t i = 0; i < q->n; ++i) L->r[i] = L->b[i] - L->t[i];
+    /* restriction = transpose of the prolongation; Dirichlet rows of the coarse level get 0 */
+    mg_level *C = &m->lev[l + 1];
+    const oracle_problem *qc = C->prob;
+    memset(C->b, 0, sizeof(double) * qc->n);
+    for (int64_t i = 0; i < q->n; ++i)
+        for (int64_t k = L->Pptr[i]; k < L->Pptr[i + 1]; ++k) C->b[L->Pcol[k]] += L->Pval[k] * L->r[i];
+    for (int64_t b = 0; b < qc->nb; ++b) C->b[qc->bdof[b]] = 0.0;
+    mg_vcycle(m, l + 1);
+    for (int64_t i = 0; i < q->n; ++i) {
+        double e = 0.0;
+        for (int64_t k = L->Pptr[i]; k < L->Pptr[i + 1]; ++k) e += L->Pval[k] * C->x[L->Pcol[k]];
+        L->x[i] += e;
+    }
+    mg_smooth(L, m->nu, 0);
+}
+/* h = V-cycle(g) on the fine level */
+static void mg_apply(oracle_problem *p, const double *g, double *h) {
+    mg_t *m = p->mg;
+    memcpy(m->lev[0].b, g, sizeof(double) * p->n);
+    mg_vcycle(m, 0);
+    memcpy(h, m->lev[0].x, sizeof(double) * p->n);
+}
+static void mg_free(mg_t *m) {
+    for (int l = 0; l < m->nlev; ++l) {
+        mg_level *L = &m->lev[l];
+        free(L->dinv); free(L->x); free(L->b); free(L->r); free(L->t);
+        free(L->Pptr); free(L->Pcol); free(L->Pval);
+        if (l > 0) { free(L->S); oracle_destroy_internal(L->prob); }
+    }
+    free(m);
+}
+int oracle_mg_levels(oracle_problem *p) { return p->mg ? p->mg->nlev : 0; }
+
 /* [deal.II] SolverCG::solve + ReductionControl (src/WaveNewmark.cpp:256-261).
    Preconditioner: Jacobi (north-star replacement of PreconditionAMG/SSOR). */
+static int cg_solve_ex(oracle_problem *p, const double *Aval, double *x, const double *b, int use_mg);
 static int cg_solve(oracle_problem *p, const double *Aval, double *x, const double *b) {
+    return cg_solve_ex(p, Aval, x, b, 0);
+}
+static int cg_solve_ex(oracle_problem *p, const double *Aval, double *x, const double *b, int use_mg) {
     double *g = p->cg_g, *d = p->cg_d, *h = p->cg_h;
     const int64_t n = p->n;
+    use_mg = use_mg && p->precond == 2 && p->mg != NULL;
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) {
         double dg = 1.0;
         for (int64_t k = p->rowptr[i]; k < p->rowptr[i + 1]; ++k)
             if (p->col[k] == i) dg = Aval[k];
-        p->dinv[i] = p->precond == 0 ? 1.0 / dg : 1.0;
+        p->dinv[i] = p->precond == 1 ? 1.0 : 1.0 / dg;
     }
     spmv(p, Aval, x, g);
     axpy(p, -1.0, b, g);
@@ -987,8 +1171,13 @@ static int cg_solve(oracle_problem *p, const double *Aval, double *x, const doub
     const double reduced_tol = res * p->cg_reduce;
     int it = 0;
     if (res <= reduced_tol || res <= p->cg_tol) return 0;
+    if (use_mg) {
+        mg_apply(p, g, h);
+        for (int64_t i = 0; i < n; ++i) d[i] = -h[i];
+    } else {
 #pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < n; ++i) { h[i] = p->dinv[i] * g[i]; d[i] = -h[i]; }
+        for (int64_t i = 0; i < n; ++i) { h[i] = p->dinv[i] * g[i]; d[i] = -h[i]; }
+    }
     double gh = dot(p, g, h);
     for (;;) {
         it++;
@@ -999,8 +1188,12 @@ static int cg_solve(oracle_problem *p, const double *Aval, double *x, const doub
         res = sqrt(fabs(dot(p, g, g)));
         if (res <= reduced_tol || res <= p->cg_tol) return it;
         if (it >= p->cg_maxit || isnan(res)) return -it;
+        if (use_mg)
+            mg_apply(p, g, h);
+        else {
 #pragma omp parallel for schedule(static)
-        for (int64_t i = 0; i < n; ++i) h[i] = p->dinv[i] * g[i];
+            for (int64_t i = 0; i < n; ++i) h[i] = p->dinv[i] * g[i];
+        }
         double beta = gh;
         gh = dot(p, g, h);
         beta = gh / beta;
@@ -1052,6 +1245,7 @@ int oracle_newmark_init(oracle_problem *p, double dt, double beta, double gamma)
     vcopy(p, p->oa, p->a);
     p->last_its[0] = its; p->last_its[1] = 0;
     free(bv);
+    if (p->precond == 2 && beta * dt * dt > 0.0) mg_setup(p, beta * dt * dt, p->S);
     return its < 0 ? -1 : 0;
 }
 
@@ -1093,7 +1287,7 @@ int oracle_newmark_step(oracle_problem *p) {
     }
     apply_bc(p, p->S, bv, p->a, p->rhs);
     free(bv);
-    int its = cg_solve(p, p->S, p->a, p->rhs);
+    int its = cg_solve_ex(p, p->S, p->a, p->rhs, 1);
     p->last_its[0] = its; p->last_its[1] = 0;
     /* update_u_v :264-278 */
     vcopy(p, p->ou, p->u);
@@ -1123,6 +1317,7 @@ int oracle_theta_init(oracle_problem *p, double dt, double theta) {
     interp(p, EX_V0, 0.0, p->ov);
     vcopy(p, p->ou, p->u);
     vcopy(p, p->ov, p->v);
+    if (p->precond == 2 && theta * dt > 0.0) mg_setup(p, (theta * dt) * (theta * dt), p->S);
     return 0;
 }
 
@@ -1149,7 +1344,7 @@ int oracle_theta_step(oracle_problem *p) {
         bv[b] = ev(p, EX_G, p->sx[i], p->sy[i], p->time);
     }
     apply_bc(p, p->S, bv, p->u, p->rhs);
-    int its_u = cg_solve(p, p->S, p->u, p->rhs);
+    int its_u = cg_solve_ex(p, p->S, p->u, p->rhs, 1);
     /* assemble_rhs_v :188-249 */
     spmv(p, p->M, p->ov, p->rhs);
     spmv(p, p->K, p->ou, tmp);
@@ -1258,6 +1453,7 @@ double oracle_probe(oracle_problem *p) {
 /* ------------------------------------------------------------------------- */
 /* accessors                                                                  */
 /* ------------------------------------------------------------------------- */
+void oracle_destroy(oracle_problem *p);
 int64_t oracle_n(oracle_problem *p) { return p->n; }
 int64_t oracle_nnz(oracle_problem *p) { return p->nnz; }
 int64_t oracle_nb(oracle_problem *p) { return p->nb; }
@@ -1319,9 +1515,12 @@ int oracle_num_threads(void) {
     return 1;
 #endif
 }
+static void oracle_destroy_internal(oracle_problem *p) { oracle_destroy(p); }
 void oracle_destroy(oracle_problem *p) {
     if (!p) return;
-    for (int i = 0; i < EX_COUNT; ++i) free_node(p->ex[i].root);
+    if (p->mg) mg_free(p->mg);
+    if (!p->borrowed_expr)
+        for (int i = 0; i < EX_COUNT; ++i) free_node(p->ex[i].root);
     free(p->vx); free(p->vy); free(p->cell_v); free(p->cell_dof); free(p->sx); free(p->sy);
     free(p->bdof); free(p->is_b); free(p->rowptr); free(p->col);
     free(p->M); free(p->K); free(p->A); free(p->A2); free(p->S);
