@@ -127,13 +127,14 @@ def hbm_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def time_oracle(params, scheme, budget_s, max_steps, warmup=1):
+def time_oracle(params, scheme, budget_s, max_steps, warmup=1, precond=0):
     """The CPU path: oracle/wave_oracle.c (C restatement of the reference, OpenMP over all host
     threads) stepping the same workload for a bounded number of steps."""
     from oracle import oracle as O
 
     t0 = time.time()
     o = O.Oracle.from_params(params)
+    o.set_cg(precond=precond)
     dt = float(params["Dt"])
     if scheme == "newmark":
         o.newmark_init(dt, float(params["Beta"]), float(params["Gamma"]))
@@ -189,6 +190,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precond", default="jacobi", choices=["jacobi", "mg"],
+                    help="CG preconditioner: jacobi (north-star default) or the multigrid V-cycle (single GPU)")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-scale-probe", action="store_true",
                     help="skip the SpMV / CG-iteration roofline probe on matrices larger than L2")
@@ -226,8 +229,9 @@ def main():
     K = args.steps
 
     t_setup0 = time.time()
+    cg_opts = dict(precond=2) if args.precond == "mg" else None
     g = WaveSolver(params, scheme, rank=rank, nranks=world, nccl_id=nccl_id, device=local_rank,
-                   stream=stream.cuda_stream)
+                   stream=stream.cuda_stream, cg=cg_opts)
     g.init()
     setup_s = time.time() - t_setup0
     n = g.n
@@ -355,7 +359,7 @@ def main():
             gs.close()
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = time_oracle(params, scheme, budget_s=20.0, max_steps=10)
+        r = time_oracle(params, scheme, budget_s=20.0, max_steps=10, precond=2 if args.precond == "mg" else 0)
         cpu = {"value": r["n"] * r["steps"] / r["seconds"], "unit": "DoF-steps/s", "cores": r["threads"],
                "kind": "port", "cg_its_per_step": r["cg_its_per_step"],
                "sample": f"{r['steps']} time steps of the same workload on the host "
@@ -368,7 +372,7 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload, "problem": WORKLOADS[workload][0], "scheme": scheme,
                    "Nel": params["Nel"], "R": params["R"], "Dt": params["Dt"], "n_dofs": n,
-                   "nnz_per_gpu": nnz, "cg_its_per_step": its_total / K, "preconditioner": "jacobi",
+                   "nnz_per_gpu": nnz, "cg_its_per_step": its_total / K, "preconditioner": args.precond,
                    "cg_stop": "ReductionControl(10000, 1e-12, 1e-6)", "parallelism": f"strips{n_gpus}",
                    "l2": "flushed between steps (256 MiB write)" if flush is not None else "not flushed",
                    "setup_s": setup_s, "wall_s_timed_region": wall_s},

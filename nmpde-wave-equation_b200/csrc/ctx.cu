@@ -379,6 +379,8 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
     use_mg = use_mg && ctx->mg != nullptr;
     cudaEvent_t e0 = ctx->ev[2 * PH_COUNT], e1 = ctx->ev[2 * PH_COUNT + 1];
     CK(cudaEventRecord(e0, ctx->stream));
+    // the status of the previous solve must not gate the kernels of this one (V-cycle before k_cg_start)
+    CK(cudaMemsetAsync(&ctx->S->status, 0, sizeof(int), ctx->stream));
     RET(halo_exchange(ctx, x));
     {   // g = A x - b ; h = D^-1 g ; d = -h ; gg, gh
         SpmvArgs a = spmv_base(ctx);
