@@ -357,6 +357,30 @@ def main():
                              "cg_iteration": {"ms": ms_c, "GB/s": by_c / ms_c / 1e6, "frac": by_c / ms_c / 1e6 / peak,
                                               "algorithmic_bytes": by_c}})
             gs.close()
+    # ---- the same workload with the multigrid V-cycle preconditioner (single GPU; the default `value`
+    # keeps the north star's Jacobi so that every N runs the same algorithm) ---------------------------
+    multigrid = None
+    if world == 1 and args.precond == "jacobi" and not args.no_scale_probe:
+        gm = WaveSolver(params, scheme, stream=stream.cuda_stream, cg=dict(precond=2))
+        gm.init()
+        for _ in range(W):
+            gm.step()
+        torch.cuda.synchronize()
+        evm = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        its_m = 0
+        for k in range(K):
+            if flush is not None:
+                flush.fill_(k & 0xFF)
+            evm[k][0].record(stream)
+            it_m, _ = gm.step()
+            evm[k][1].record(stream)
+            its_m += it_m[0] + it_m[1]
+        torch.cuda.synchronize()
+        ms_m = float(sum(a.elapsed_time(b) for a, b in evm))
+        multigrid = {"value": n * K / (ms_m * 1e-3), "unit": "DoF-steps/s", "ms_per_step": ms_m / K,
+                     "cg_its_per_step": its_m / K,
+                     "preconditioner": "geometric multigrid V(2,2), damped Jacobi smoothing (WAVE_PRECOND_MG)"}
+        gm.close()
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         r = time_oracle(params, scheme, budget_s=20.0, max_steps=10, precond=2 if args.precond == "mg" else 0)
@@ -377,7 +401,7 @@ def main():
                    "l2": "flushed between steps (256 MiB write)" if flush is not None else "not flushed",
                    "setup_s": setup_s, "wall_s_timed_region": wall_s},
         "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
-        "roofline_at_scale": at_scale, "cpu_baseline": cpu,
+        "roofline_at_scale": at_scale, "multigrid": multigrid, "cpu_baseline": cpu,
         "cg": {"solves": cgs["solves"], "iterations": cgs["iterations"], "ms_total": cgs["ms_total"],
                "ms_per_iteration": cgs["ms_total"] / max(cgs["iterations"], 1)},
         "step_ms": {"min": min(step_ms), "max": max(step_ms)},
