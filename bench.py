@@ -43,6 +43,12 @@ WORKLOADS = {
     # the reference's own published strong-scaling configuration (BASELINE.md section 1:
     # report/sections/8_Scalability.tex:9-18): Nel=640, R=1, Dt=8e-5, Newmark 1/4, 1/2
     "published-newmark-640-p1": ("standing-mode-wsol", "newmark", dict(Nel="640", R="1", Dt="8e-5"), "strong", False),
+    # BASELINE configs[4] at its full size (268 M DoFs, 3.09 G nnz): needs >= 2 GPUs
+    "c5-traveling-newmark-8192-p2": ("traveling-square-bump", "newmark",
+                                     dict(Nel="8192", R="2", Geometry="[0.0, 3.0] x [0.0, 3.0]",
+                                          C={"Function constants": "", "Variable names": "x, y, t",
+                                             "Function expression": "1.0 + 0.25*sin(2*pi*x/3)*sin(2*pi*y/3)"}),
+                                     "strong", False),
     "newmark-4096-p2": ("standing-mode-wsol", "newmark", dict(Nel="4096", R="2", Dt="0.001"), "strong", False),
     "newmark-2048-p2": ("standing-mode-wsol", "newmark", dict(Nel="2048", R="2", Dt="0.002"), "strong", False),
 }
