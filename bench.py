@@ -63,6 +63,8 @@ def make_params(workload, n_gpus):
 
     name, scheme, over, scaling, weak_y = WORKLOADS[workload]
     over = dict(over)
+    if os.environ.get("WAVE_BENCH_NEL"):  # debugging aid: same problem on another mesh
+        over["Nel"] = os.environ["WAVE_BENCH_NEL"]
     p = problem(name, **over)
     if scaling == "weak" and n_gpus > 1 and weak_y:
         from wavegpu.api import parse_geometry, parse_nel
