@@ -58,10 +58,10 @@ def build(force=False, verbose=False):
     if force or jobs or not LIB.exists():
         _run([NVCC, "-shared", *ARCH, "-o", LIB, *objs, "-ldl"])
     # host executables (same names as the reference's CMake targets)
-    if HOST.exists() and all((HOST / s).exists() for s in HOST_SOURCES):
+    if HOST.exists() and all((HOST / s).exists() for s in HOST_SOURCES):  # + host_selftest (CPU-only checks)
         BIN.mkdir(exist_ok=True)
         hdeps = list(HOST.glob("*.hpp")) + list(HOST.glob("*.cpp")) + [HERE.parent / "include" / "wavegpu.h"]
-        for exe in ("main-newmark", "main-theta"):
+        for exe in ("main-newmark", "main-theta", "host_selftest"):
             target = BIN / exe
             if force or _newer(target, hdeps + [LIB]):
                 _run(["g++", *CXXFLAGS, "-I", HERE.parent / "include", "-o", target, HOST / (exe + ".cpp"),

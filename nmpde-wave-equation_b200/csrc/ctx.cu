@@ -1378,13 +1378,17 @@ int64_t wave_local_rows(const wave_ctx *ctx, int64_t *first_row) {
     return ctx->L.nown;
 }
 int64_t wave_local_nnz(const wave_ctx *ctx) { return ctx ? ctx->nnz : 0; }
-int64_t wave_nnz(const wave_ctx *ctx) {
-    if (!ctx) return 0;
-    const int64_t N = ctx->L.mesh.nx, Ny = ctx->L.mesh.ny;
-    if (ctx->cfg.nranks == 1) return ctx->nnz;
-    // closed forms hold for square meshes; general: count on the fly
-    (void)N; (void)Ny;
-    return -1;
+int64_t wave_nnz(const wave_ctx *cctx) {
+    if (!cctx) return 0;
+    if (cctx->cfg.nranks == 1) return cctx->nnz;
+    // sum of the ranks' owned entries (collective; exact in a double up to 2^53)
+    wave_ctx *ctx = const_cast<wave_ctx *>(cctx);
+    ctx->hres[0] = (double)ctx->nnz;
+    if (cudaMemcpyAsync(ctx->res, ctx->hres, sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return -1;
+    if (allreduce(ctx, ctx->res, 1) != WAVE_OK) return -1;
+    if (cudaMemcpyAsync(ctx->hres, ctx->res, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+    return (int64_t)ctx->hres[0];
 }
 
 int wave_get_csr(wave_ctx *ctx, int which, int64_t *rowptr, int32_t *col, double *val) {

@@ -86,6 +86,16 @@ void WaveEquationBase::create_context(int scheme, double theta, double beta, dou
     cfg.theta = theta;
     cfg.beta = beta;
     cfg.gamma = gamma;
+    // solver options without a field in the JSON schema come through the environment, like NMPDE_*:
+    // WAVE_PRECOND=mg selects the multigrid V-cycle instead of Jacobi
+    if (const char* pc = std::getenv("WAVE_PRECOND"))
+    {
+        const std::string v(pc);
+        if (v == "mg" || v == "MG" || v == "2")
+            cfg.precond = WAVE_PRECOND_MG;
+        else if (v == "none" || v == "1")
+            cfg.precond = WAVE_PRECOND_NONE;
+    }
     if (wave_create(&cfg, &ctx) != WAVE_OK)
         throw std::runtime_error(std::string("wave_create: ") + wave_last_error(nullptr));
 

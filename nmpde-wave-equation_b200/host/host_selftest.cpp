@@ -1,0 +1,148 @@
+// host_selftest.cpp -- CPU-only checks of the host mirror (no device needed): clean_double, the
+// ParameterHandler JSON reader and pattern checks, ParameterReader::get_nel / get_geometry / constants,
+// FunctionParser over the library's expression handles.  Run by tests/test_host_cpu.py; prints one
+// "ok <name>" line per check and exits non-zero on the first failure.
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <functional>
+#include <iostream>
+
+#include "ParameterReader.hpp"
+#include "WaveEquationBase.hpp"
+
+namespace
+{
+int failures = 0;
+void check(bool cond, const char* name)
+{
+    std::cout << (cond ? "ok " : "FAIL ") << name << std::endl;
+    if (!cond)
+        ++failures;
+}
+template <class E>
+bool throws(const std::function<void()>& f)
+{
+    try
+    {
+        f();
+    }
+    catch (const E&)
+    {
+        return true;
+    }
+    catch (...)
+    {
+        return false;
+    }
+    return false;
+}
+} // namespace
+
+int main(int argc, char** argv)
+{
+    const std::string dir = argc > 1 ? argv[1] : ".";
+
+    // clean_double: src/WaveEquationBase.cpp:433-452 and scripts/dissipation_dispersion_sweep.py:333-357
+    check(clean_double(0.05) == "0_05", "clean_double 0.05");
+    check(clean_double(1.0) == "1", "clean_double 1.0");
+    check(clean_double(10.0) == "10", "clean_double 10 keeps the integer zero");
+    check(clean_double(0.015625) == "0_015625", "clean_double 1/64");
+    check(clean_double(8e-5) == "0_00008", "clean_double 8e-5");
+    check(clean_double(1e-7) == "0", "clean_double below 6 decimals");
+    check(clean_double(0.25) == "0_25" && clean_double(0.5) == "0_5", "clean_double beta gamma");
+    check(clean_double(-1.0, 2) == "-1", "clean_double negative, precision 2");
+
+    // constants with pi: src/ParameterReader.cpp:237-294
+    check(std::fabs(parse_value_with_pi(" pi ") - M_PI) < 1e-15, "constant pi");
+    check(std::fabs(parse_value_with_pi("4.0*pi") - 4 * M_PI) < 1e-15, "constant 4.0*pi");
+    check(std::fabs(parse_value_with_pi(" 2 * PI") - 2 * M_PI) < 1e-15, "constant 2 * PI");
+    check(parse_value_with_pi("1e-3") == 1e-3, "plain number");
+    check(throws<std::invalid_argument>([] { parse_value_with_pi("abc"); }), "bad constant throws invalid_argument");
+    {
+        auto m = parse_constants_with_pi_and_multiplication("TT=0.5, XX=0.5, ya=0.333, k=4.0*pi");
+        check(m.size() == 4 && m["TT"] == 0.5 && std::fabs(m["k"] - 4 * M_PI) < 1e-15, "constant list");
+    }
+
+    // JSON parameter file with string, numeric and boolean literals (scripts/convergence_sweep.py:175-177)
+    const std::string file = dir + "/selftest.json";
+    {
+        std::ofstream f(file);
+        f << "{\n \"Geometry\": \"[-1.0, 1.0] x [0.0, 3.5]\", \"Nel\": \"180, 60\", \"R\": 2, \"T\": \"1.5\",\n"
+             " \"Dt\": 0.005, \"Save Solution\": false, \"Enable Logging\": \"true\", \"Log Every\": 0,\n"
+             " \"U0\": {\"Function constants\": \"A=2.0\", \"Function expression\": \"A*sin(pi*x)*y\", \"Variable "
+             "names\": \"x, y\"},\n"
+             " \"G\": {\"Function constants\": \"\", \"Function expression\": \"if(t<=0.5 && x<0.1, sin(t), 0.0)\", "
+             "\"Variable names\": \"x, y, t\"},\n"
+             " \"C\": {\"Function expression\": \"1.0\", \"Variable names\": \"x, y, t\"},\n"
+             " \"F\": {\"Function expression\": \"0.0\", \"Variable names\": \"x, y, t\"},\n"
+             " \"V0\": {\"Function expression\": \"0.0\", \"Variable names\": \"x, y\"},\n"
+             " \"DGDT\": {\"Function expression\": \"0.0\", \"Variable names\": \"x, y, t\"}\n}\n";
+    }
+    ParameterHandler prm;
+    ParameterReader reader(prm);
+    const std::vector<std::string> names{ "C", "F", "U0", "V0", "G", "DGDT", "Solution" };
+    reader.declare(names);
+    reader.parse(file);
+    check(prm.get_integer("R") == 2 && prm.get_double("Dt") == 0.005 && prm.get_double("T") == 1.5, "scalars");
+    check(prm.get_double("Theta") == 0.5 && prm.get_double("Beta") == 0.25 && prm.get_integer("Print Every") == 10,
+          "defaults of undeclared-in-file entries");
+    check(!prm.get_bool("Save Solution") && prm.get_bool("Enable Logging") && prm.get_integer("Log Every") == 0,
+          "bool / int literals");
+    const auto nel = reader.get_nel();
+    check(nel.first == 180 && nel.second == 60, "get_nel two values");
+    const auto geo = reader.get_geometry();
+    check(geo.first[0] == -1.0 && geo.second[0] == 1.0 && geo.first[1] == 0.0 && geo.second[1] == 3.5, "get_geometry");
+    FunctionParser<2> c, f, u0, v0, g, dgdt, sol;
+    reader.load_functions(names, { &c, &f, &u0, &v0, &g, &dgdt, &sol });
+    check(!sol.is_initialized() && u0.is_initialized(), "Solution block optional");
+    check(std::fabs(u0.value(Point<2>(0.5, 3.0)) - 6.0) < 1e-14, "U0 value with constant");
+    g.set_time(0.25);
+    check(std::fabs(g.value(Point<2>(0.05, 0.0)) - std::sin(0.25)) < 1e-15, "G inside the window");
+    g.set_time(0.75);
+    check(g.value(Point<2>(0.05, 0.0)) == 0.0, "G after the window");
+
+    // error behaviour
+    check(throws<std::invalid_argument>([&] {
+              ParameterHandler p2;
+              ParameterReader r2(p2);
+              r2.declare(names);
+              std::ofstream(dir + "/bad.json") << "{\"R\": \"0\"}";
+              r2.parse(dir + "/bad.json");
+          }),
+          "R = 0 violates Patterns::Integer(1)");
+    check(throws<std::runtime_error>([&] {
+              ParameterHandler p2;
+              ParameterReader r2(p2);
+              r2.declare(names);
+              std::ofstream(dir + "/bad2.json") << "{\"Unknown Key\": \"1\"}";
+              r2.parse(dir + "/bad2.json");
+          }),
+          "undeclared entry is an error");
+    check(throws<std::invalid_argument>([&] {
+              ParameterHandler p2;
+              ParameterReader r2(p2);
+              r2.declare(names);
+              std::ofstream(dir + "/bad3.json") << "{\"Geometry\": \"0,1,0,1\"}";
+              r2.parse(dir + "/bad3.json");
+              r2.get_geometry();
+          }),
+          "malformed Geometry");
+    check(throws<std::invalid_argument>([&] {
+              FunctionParser<2> bad;
+              bad.initialize("x, y", "sin(pi*x", {}, false);
+          }),
+          "unparsable expression throws invalid_argument");
+    check(throws<std::invalid_argument>([&] {
+              ParameterHandler p2;
+              ParameterReader r2(p2);
+              r2.declare(names);
+              std::ofstream(dir + "/bad4.json") << "{\"C\": {\"Function expression\": \"\"}}";
+              r2.parse(dir + "/bad4.json");
+              FunctionParser<2> a1, a2, a3, a4, a5, a6, a7;
+              r2.load_functions(names, { &a1, &a2, &a3, &a4, &a5, &a6, &a7 });
+          }),
+          "missing expression for C");
+    std::cout << (failures ? "FAILED" : "ALL OK") << std::endl;
+    return failures ? 1 : 0;
+}

@@ -152,3 +152,17 @@ def test_cli_error_behaviour(exe, tmp_path):
     assert r.returncode == 1
     r = _run(exe, "../parameters/missing.json", tmp_path / "build")
     assert r.returncode == 1 and "Unexpected error while parsing parameters" in r.stdout
+
+
+def test_host_selftest_binary(tmp_path):
+    """clean_double, JSON reader, get_nel/get_geometry, constants, FunctionParser: C++ checks, CPU only."""
+    r = subprocess.run([str(BIN / "host_selftest"), str(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ALL OK" in r.stdout and "FAIL " not in r.stdout
+
+
+def test_mpirun_shim_drops_mpi_options():
+    shim = ROOT / "tools" / "mpirun-shim"
+    r = subprocess.run([str(shim), "-np", "16", "--bind-to", "core", "--map-by", "socket", "--hostfile", "/tmp/x",
+                        "echo", "binary", "params.json"], capture_output=True, text=True, timeout=30)
+    assert r.returncode == 0 and r.stdout.split() == ["binary", "params.json"]
