@@ -50,6 +50,13 @@ def lib():
     """Load libwavegpu.so.  Fails loudly when it has not been built: there is no fallback."""
     global _lib
     if _lib is None:
+        if not _LIB.exists():  # build in-tree (nvcc cross-compiles sm_100a without a GPU); never falls back to CPU code
+            import importlib.util
+
+            spec = importlib.util.spec_from_file_location("wave_build", _PKG / "build.py")
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
         if not _LIB.exists():
             raise FileNotFoundError(f"{_LIB} missing: run python nmpde-wave-equation_b200/build.py")
         L = C.CDLL(str(_LIB))
