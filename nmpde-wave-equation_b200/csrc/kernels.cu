@@ -708,12 +708,16 @@ __global__ void __launch_bounds__(kThreads) k_cg_direction(int n, CgScalars *S, 
 // midpoint of its edge.  Restriction is the transpose, with Dirichlet rows of the coarse level zeroed.
 __global__ void k_scale_rows(int n, double omega, const double *__restrict__ dinv, const double *__restrict__ b,
                              double *__restrict__ x, const int *skip_flag) {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
     if (skip_flag && *skip_flag != 0) return;
     const int stride = gridDim.x * blockDim.x;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = omega * (dinv[i] * b[i]);
 }
 __global__ void k_prolong_add_p1(Mesh mf, Mesh mc, const double *__restrict__ ec, double *__restrict__ xf,
                                  const int *skip_flag) {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
     if (skip_flag && *skip_flag != 0) return;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)(mf.nx + 1) * (mf.ny + 1)) return;
@@ -727,6 +731,8 @@ __global__ void k_prolong_add_p1(Mesh mf, Mesh mc, const double *__restrict__ ec
 }
 __global__ void k_restrict_p1(Mesh mf, Mesh mc, const double *__restrict__ rf, double *__restrict__ bc,
                               const int *skip_flag) {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
     if (skip_flag && *skip_flag != 0) return;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)(mc.nx + 1) * (mc.ny + 1)) return;
@@ -742,6 +748,8 @@ __global__ void k_restrict_p1(Mesh mf, Mesh mc, const double *__restrict__ rf, d
 }
 __global__ void k_prolong_add_p2p1(Mesh mf, Mesh mc, const double *__restrict__ ec, double *__restrict__ xf,
                                    const int *skip_flag) {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
     if (skip_flag && *skip_flag != 0) return;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 4LL * (mf.nx + 1) * (mf.ny + 1)) return;
@@ -759,6 +767,8 @@ __global__ void k_prolong_add_p2p1(Mesh mf, Mesh mc, const double *__restrict__ 
 }
 __global__ void k_restrict_p2p1(Mesh mf, Mesh mc, const double *__restrict__ rf, double *__restrict__ bc,
                                 const int *skip_flag) {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
     if (skip_flag && *skip_flag != 0) return;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)(mc.nx + 1) * (mc.ny + 1)) return;
@@ -773,6 +783,8 @@ __global__ void k_restrict_p2p1(Mesh mf, Mesh mc, const double *__restrict__ rf,
 __global__ void __launch_bounds__(kThreads) k_dot_gz(int n, const double *__restrict__ g, const double *__restrict__ z,
                                                      double *d, double *partials, unsigned *counter, double *result,
                                                      const int *skip_flag) {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
     if (skip_flag && *skip_flag != 0) return;
     double acc[1] = {0.0};
     const int stride = gridDim.x * blockDim.x;
@@ -1080,31 +1092,31 @@ void launch_zero_rows(const Launcher &l, int nb, const int32_t *brow, double *ve
 void launch_cg_start(const Launcher &l, CgScalars *S) { WV_LAUNCH(l, k_cg_start, 1, 32, 0, S); }
 void launch_scale_rows(const Launcher &l, int n, double omega, const double *dinv, const double *b, double *x,
                        const int *skip_flag) {
-    WV_LAUNCH(l, k_scale_rows, stream_blocks(n), kThreads, 0, n, omega, dinv, b, x, skip_flag);
+    launch_pdl(l, k_scale_rows, stream_blocks(n), kThreads, n, omega, dinv, b, x, skip_flag);
 }
 void launch_prolong_add_p1(const Launcher &l, const Layout &Lf, const Layout &Lc, const double *ec, double *xf,
                            const int *skip_flag) {
     const int64_t n = (int64_t)(Lf.mesh.nx + 1) * (Lf.mesh.ny + 1);
-    WV_LAUNCH(l, k_prolong_add_p1, blocks_for(n, kThreads), kThreads, 0, Lf.mesh, Lc.mesh, ec, xf, skip_flag);
+    launch_pdl(l, k_prolong_add_p1, blocks_for(n, kThreads), kThreads, Lf.mesh, Lc.mesh, ec, xf, skip_flag);
 }
 void launch_restrict_p1(const Launcher &l, const Layout &Lf, const Layout &Lc, const double *rf, double *bc,
                         const int *skip_flag) {
     const int64_t n = (int64_t)(Lc.mesh.nx + 1) * (Lc.mesh.ny + 1);
-    WV_LAUNCH(l, k_restrict_p1, blocks_for(n, kThreads), kThreads, 0, Lf.mesh, Lc.mesh, rf, bc, skip_flag);
+    launch_pdl(l, k_restrict_p1, blocks_for(n, kThreads), kThreads, Lf.mesh, Lc.mesh, rf, bc, skip_flag);
 }
 void launch_prolong_add_p2p1(const Launcher &l, const Layout &Lf, const Layout &Lc, const double *ec, double *xf,
                              const int *skip_flag) {
     const int64_t n = 4LL * (Lf.mesh.nx + 1) * (Lf.mesh.ny + 1);
-    WV_LAUNCH(l, k_prolong_add_p2p1, blocks_for(n, kThreads), kThreads, 0, Lf.mesh, Lc.mesh, ec, xf, skip_flag);
+    launch_pdl(l, k_prolong_add_p2p1, blocks_for(n, kThreads), kThreads, Lf.mesh, Lc.mesh, ec, xf, skip_flag);
 }
 void launch_restrict_p2p1(const Launcher &l, const Layout &Lf, const Layout &Lc, const double *rf, double *bc,
                           const int *skip_flag) {
     const int64_t n = (int64_t)(Lc.mesh.nx + 1) * (Lc.mesh.ny + 1);
-    WV_LAUNCH(l, k_restrict_p2p1, blocks_for(n, kThreads), kThreads, 0, Lf.mesh, Lc.mesh, rf, bc, skip_flag);
+    launch_pdl(l, k_restrict_p2p1, blocks_for(n, kThreads), kThreads, Lf.mesh, Lc.mesh, rf, bc, skip_flag);
 }
 void launch_dot_gz(const Launcher &l, int n, const double *g, const double *z, double *d_or_null, double *partials,
                    unsigned *counter, double *result, const int *skip_flag) {
-    WV_LAUNCH(l, k_dot_gz, stream_blocks(n), kThreads, 0, n, g, z, d_or_null, partials, counter, result, skip_flag);
+    launch_pdl(l, k_dot_gz, stream_blocks(n), kThreads, n, g, z, d_or_null, partials, counter, result, skip_flag);
 }
 void launch_cg_update(const Launcher &l, int n, CgScalars *S, double *x, double *g, double *h, const double *d,
                       const double *dinv, double *partials, unsigned *counter, const PeerComm &pc,

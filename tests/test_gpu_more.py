@@ -143,3 +143,31 @@ def test_set_vector_roundtrip_and_norms():
     nu, nv = g.norms()
     assert nu == pytest.approx(np.linalg.norm(u), rel=1e-13) and nv == pytest.approx(np.linalg.norm(v), rel=1e-13)
     g.close()
+
+
+def test_reference_default_case_full_run():
+    """BASELINE configs[0]: parameters/sine-membrane.json as shipped (theta = 0.5, Nel 180 x 60 on
+    [0,3]x[0,1], Dt = 0.05, T = 60: 1201 steps, inhomogeneous time-dependent Dirichlet data) -- the whole
+    run on the GPU against the whole run of the oracle: energy series, iteration counts, final vectors."""
+    p = problem("sine-membrane")
+    out = O.run(p, "theta", log_every=50)
+    assert out["steps"] == 1201
+    g = WaveSolver(p, "theta")
+    g.init()
+    k, same_its, total = 0, 0, 0
+    t = 0.0
+    for step in range(1, out["steps"] + 1):
+        its, _ = g.step()
+        if step % 50 == 0:
+            s, tt, E = out["energy"][k]
+            assert s == step
+            assert abs(g.energy() - E) <= 1e-8 * abs(E)
+            oi = out["iterations"][k][2:]
+            same_its += int(tuple(its) == tuple(oi))
+            total += 1
+            k += 1
+    assert same_its >= total - 1  # round-off may move a stopping iteration by one, very rarely
+    o = out["oracle"]
+    assert rel(g.vector(api.VEC_U), o.vector(O.Oracle.U)) < 1e-8
+    assert rel(g.vector(api.VEC_V), o.vector(O.Oracle.V)) < 1e-8
+    g.close()
