@@ -432,8 +432,8 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
             }
             if (!p2p) RET(allreduce(ctx, &ctx->S->dAd, 1));
             const unsigned long long seq_b = p2p ? ++ctx->ar_seq : 0ull;
-            launch_cg_update(l, L.nown, ctx->S, x + L.own_off, ctx->g, ctx->h, ctx->d + L.own_off,
-                             use_mg ? nullptr : dinv, ctx->partials, ctx->counter, p2p ? ctx->pc : PeerComm{}, seq_b);
+            launch_cg_update(l, L.nown, ctx->S, ctx->g, ctx->h, use_mg ? nullptr : dinv, ctx->partials, ctx->counter,
+                             p2p ? ctx->pc : PeerComm{}, seq_b);
             const double *z = ctx->h;
             if (use_mg) {  // h' = V-cycle(g) ; gh' = g.h'
                 z = mg_apply(ctx, Sval, dinv, ctx->g);
@@ -442,7 +442,7 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
             }
             if (!p2p) RET(allreduce(ctx, &ctx->S->gg, 2));
             const unsigned long long seq_h = p2p ? ++ctx->halo_seq : 0ull;
-            launch_cg_direction(l, L.nown, ctx->S, ctx->d + L.own_off, z, ctx->counter,
+            launch_cg_direction(l, L.nown, ctx->S, x + L.own_off, ctx->d + L.own_off, z, ctx->counter,
                                 p2p ? ctx->pc : PeerComm{}, seq_h);
         }
         enq += chunk;

@@ -635,12 +635,12 @@ __global__ void k_cg_start(CgScalars *S) {
     S->gh_old = S->gh_new;
     S->status = (res0 <= S->reduced_tol || res0 <= S->tol) ? 1 : 0;
 }
-// x += alpha d ; g += alpha h ; res^2 = g.g ; h = D^-1 g ; gh' = g.h   (one pass, 5 reads 3 writes)
-__global__ void __launch_bounds__(kThreads) k_cg_update(int n, CgScalars *S, double *__restrict__ x,
-                                                        double *__restrict__ g, double *__restrict__ h,
-                                                        const double *__restrict__ d,
-                                                        const double *__restrict__ dinv, double *partials,
-                                                        unsigned *counter, PeerComm pc, unsigned long long ar_seq) {
+// g += alpha h ; res^2 = g.g ; h = D^-1 g ; gh' = g.h   (one pass: 3 reads, 2 writes).  The x update of
+// this iteration (x += alpha d) is done by k_cg_direction, which reads d anyway.
+__global__ void __launch_bounds__(kThreads) k_cg_update(int n, CgScalars *S, double *__restrict__ g,
+                                                        double *__restrict__ h, const double *__restrict__ dinv,
+                                                        double *partials, unsigned *counter, PeerComm pc,
+                                                        unsigned long long ar_seq) {
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
     if (S->status != 0) return;
@@ -648,7 +648,6 @@ __global__ void __launch_bounds__(kThreads) k_cg_update(int n, CgScalars *S, dou
     double acc[2] = {0.0, 0.0};
     const int stride = gridDim.x * blockDim.x;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        x[i] += alpha * d[i];
         const double gi = g[i] + alpha * h[i];
         g[i] = gi;
         acc[0] += gi * gi;
@@ -663,24 +662,28 @@ __global__ void __launch_bounds__(kThreads) k_cg_update(int n, CgScalars *S, dou
         if (dinv) S->gh_new = acc[1];
     }
 }
-// iteration_status(it, res); beta = gh'/gh ; d = beta d - h
-__global__ void __launch_bounds__(kThreads) k_cg_direction(int n, CgScalars *S, double *__restrict__ d,
-                                                           const double *__restrict__ h, unsigned *counter,
-                                                           PeerComm pc, unsigned long long halo_seq) {
+// x += alpha d ; iteration_status(it, res) ; beta = gh'/gh ; d = beta d - h   (3 reads, 2 writes)
+__global__ void __launch_bounds__(kThreads) k_cg_direction(int n, CgScalars *S, double *__restrict__ x,
+                                                           double *__restrict__ d, const double *__restrict__ h,
+                                                           unsigned *counter, PeerComm pc,
+                                                           unsigned long long halo_seq) {
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
     if (S->status != 0) return;
+    const double alpha = S->gh_old / S->dAd;  // the step length of this iteration (set before k_cg_update)
     const double res = sqrt(fabs(S->gg));
     const int it = S->it + 1;
     int status = 0;
     if (res <= S->reduced_tol || res <= S->tol) status = 1;
     else if (it >= S->maxit || isnan(res)) status = 2;
-    if (status == 0) {
-        const double beta = S->gh_new / S->gh_old;
-        const int stride = gridDim.x * blockDim.x;
-        const int hi0 = n - pc.hi_count;
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-            const double di = beta * d[i] - h[i];
+    const double beta = S->gh_new / S->gh_old;
+    const int stride = gridDim.x * blockDim.x;
+    const int hi0 = n - pc.hi_count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double dold = d[i];
+        x[i] += alpha * dold;
+        if (status == 0) {
+            const double di = beta * dold - h[i];
             d[i] = di;
             if (pc.enabled) {  // my first / last block is the neighbours' ghost block: store it there too
                 if (pc.d_lo && i < pc.lo_count) pc.d_lo[i] = di;
@@ -1118,14 +1121,13 @@ void launch_dot_gz(const Launcher &l, int n, const double *g, const double *z, d
                    unsigned *counter, double *result, const int *skip_flag) {
     launch_pdl(l, k_dot_gz, stream_blocks(n), kThreads, n, g, z, d_or_null, partials, counter, result, skip_flag);
 }
-void launch_cg_update(const Launcher &l, int n, CgScalars *S, double *x, double *g, double *h, const double *d,
-                      const double *dinv, double *partials, unsigned *counter, const PeerComm &pc,
-                      unsigned long long ar_seq) {
-    launch_pdl(l, k_cg_update, stream_blocks(n), kThreads, n, S, x, g, h, d, dinv, partials, counter, pc, ar_seq);
+void launch_cg_update(const Launcher &l, int n, CgScalars *S, double *g, double *h, const double *dinv,
+                      double *partials, unsigned *counter, const PeerComm &pc, unsigned long long ar_seq) {
+    launch_pdl(l, k_cg_update, stream_blocks(n), kThreads, n, S, g, h, dinv, partials, counter, pc, ar_seq);
 }
-void launch_cg_direction(const Launcher &l, int n, CgScalars *S, double *d, const double *h, unsigned *counter,
-                         const PeerComm &pc, unsigned long long halo_seq) {
-    launch_pdl(l, k_cg_direction, stream_blocks(n), kThreads, n, S, d, h, counter, pc, halo_seq);
+void launch_cg_direction(const Launcher &l, int n, CgScalars *S, double *x, double *d, const double *h,
+                         unsigned *counter, const PeerComm &pc, unsigned long long halo_seq) {
+    launch_pdl(l, k_cg_direction, stream_blocks(n), kThreads, n, S, x, d, h, counter, pc, halo_seq);
 }
 void launch_newmark_predict(const Launcher &l, int n, double dt, double c1, double c2, double *u, double *v,
                             const double *a) {

@@ -178,11 +178,10 @@ void launch_restrict_p2p1(const Launcher &, const Layout &Lf, const Layout &Lc, 
 // result[0] = g.z ; optionally d = -z (CG start)
 void launch_dot_gz(const Launcher &, int n, const double *g, const double *z, double *d_or_null, double *partials,
                    unsigned *counter, double *result, const int *skip_flag);
-void launch_cg_update(const Launcher &, int n, CgScalars *S, double *x, double *g, double *h, const double *d,
-                      const double *dinv, double *partials, unsigned *counter, const PeerComm &pc,
-                      unsigned long long ar_seq);
-void launch_cg_direction(const Launcher &, int n, CgScalars *S, double *d, const double *h, unsigned *counter,
-                         const PeerComm &pc, unsigned long long halo_seq);
+void launch_cg_update(const Launcher &, int n, CgScalars *S, double *g, double *h, const double *dinv,
+                      double *partials, unsigned *counter, const PeerComm &pc, unsigned long long ar_seq);
+void launch_cg_direction(const Launcher &, int n, CgScalars *S, double *x, double *d, const double *h,
+                         unsigned *counter, const PeerComm &pc, unsigned long long halo_seq);
 void launch_newmark_predict(const Launcher &, int n, double dt, double c1, double c2, double *u, double *v,
                             const double *a);
 void launch_newmark_correct(const Launcher &, int n, double cu, double cv, double *u, double *v, const double *a,
