@@ -178,7 +178,7 @@ int wave_cg(wave_ctx *ctx, int which, double *x, const double *b, size_t n, int3
 /* Time `reps` back-to-back launches of the SpMV kernel on device-resident data; returns the
    average launch duration in ms and the algorithmic bytes per launch (12 nnz + 20 n). */
 int wave_bench_spmv(wave_ctx *ctx, int which, int reps, int flush_l2, double *ms_avg, double *bytes);
-/* Same for one Jacobi-PCG iteration (algorithmic bytes 12 nnz + 108 n). */
+/* Same for one Jacobi-PCG iteration (algorithmic bytes 12 nnz + 100 n). */
 int wave_bench_cg_iter(wave_ctx *ctx, int which, int reps, double *ms_avg, double *bytes);
 
 /* ---- instrumentation ------------------------------------------------------------------ */

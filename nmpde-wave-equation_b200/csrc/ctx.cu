@@ -1562,7 +1562,7 @@ int wave_bench_cg_iter(wave_ctx *ctx, int which, int reps, double *ms_avg, doubl
     }
     ctx->prev_its[0] = 0;
     if (ms_avg) *ms_avg = its_total > 0 ? ms_total / its_total : 0.0;
-    if (bytes) *bytes = 12.0 * (double)ctx->nnz + 108.0 * (double)L.nown;
+    if (bytes) *bytes = 12.0 * (double)ctx->nnz + 100.0 * (double)L.nown;
     return WAVE_OK;
 }
 
