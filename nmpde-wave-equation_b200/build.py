@@ -22,7 +22,7 @@ NVFLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", *ARCH]
 CXXFLAGS = ["-std=c++17", "-O2", "-fPIC", "-Wall"]
 
 LIB_SOURCES = ["kernels.cu", "ctx.cu", "expr.cpp", "quadrature.cpp"]
-HOST_SOURCES = ["ParameterReader.cpp", "WaveEquationBase.cpp", "WaveNewmark.cpp", "WaveTheta.cpp"]
+HOST_SOURCES = ["ParameterReader.cpp", "WaveEquationBase.cpp", "WaveNewmark.cpp", "WaveTheta.cpp", "cli.cpp"]
 
 
 def _newer(target: Path, deps) -> bool:

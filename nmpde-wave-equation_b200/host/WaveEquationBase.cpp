@@ -186,76 +186,58 @@ void WaveEquationBase::prepare_output_filename(const std::string& method_params)
     }
 }
 
+// energy.csv: E = 1/2 (v^T M v + u^T K u) from the device, default stream formatting (6 significant
+// digits) for time and energy (src/WaveEquationBase.cpp:148-168)
 void WaveEquationBase::compute_and_log_energy()
 {
     check(wave_energy(ctx, &current_energy), "wave_energy");
-    if (mpi_rank == 0)
-    {
-        if (!energy_log_file.is_open())
-        {
-            energy_log_file.open(output_folder + "energy.csv");
-            if (energy_log_file.is_open())
-                energy_log_file << "timestep,time,energy" << std::endl;
-        }
-        if (energy_log_file.is_open())
-            energy_log_file << timestep_number << "," << time << "," << current_energy << std::endl;
-    }
+    if (mpi_rank != 0)
+        return;
+    auto& out = energy_log.rows(output_folder + "energy.csv", "timestep,time,energy");
+    if (out)
+        out << timestep_number << ',' << time << ',' << current_energy << std::endl;
 }
 
+// probe.csv: u_h at the centre of the box, scientific with 10 digits (src/WaveEquationBase.cpp:170-222)
 void WaveEquationBase::log_point_probe()
 {
-    const double px = 0.5 * (geometry.first[0] + geometry.second[0]);
-    const double py = 0.5 * (geometry.first[1] + geometry.second[1]);
     double u_probe = 0.0;
-    check(wave_probe(ctx, px, py, &u_probe), "wave_probe");
-    if (mpi_rank == 0)
-    {
-        if (!point_probe_log_file.is_open())
-        {
-            point_probe_log_file.open(output_folder + "probe.csv");
-            if (point_probe_log_file.is_open())
-                point_probe_log_file << "timestep,time,u_probe" << std::endl;
-        }
-        if (point_probe_log_file.is_open())
-            point_probe_log_file << timestep_number << "," << time << "," << std::scientific
-                                 << std::setprecision(10) << u_probe << std::endl;
-    }
+    check(wave_probe(ctx, 0.5 * (geometry.first[0] + geometry.second[0]),
+                     0.5 * (geometry.first[1] + geometry.second[1]), &u_probe),
+          "wave_probe");
+    if (mpi_rank != 0)
+        return;
+    auto& out = probe_log.rows(output_folder + "probe.csv", "timestep,time,u_probe");
+    if (out)
+        out << timestep_number << ',' << time << ',' << std::scientific << std::setprecision(10) << u_probe
+            << std::endl;
 }
 
+// iterations.csv: CG iterations of the one (Newmark) or two (theta) solves of the step (:224-239)
 void WaveEquationBase::log_iterations(const unsigned int n_iterations_1, const unsigned int n_iterations_2)
 {
-    if (mpi_rank == 0)
-    {
-        if (!iterations_log_file.is_open())
-        {
-            iterations_log_file.open(output_folder + "iterations.csv");
-            if (iterations_log_file.is_open())
-                iterations_log_file << "timestep,time,iterations_1,iterations_2" << std::endl;
-        }
-        if (iterations_log_file.is_open())
-            iterations_log_file << timestep_number << "," << time << "," << n_iterations_1 << "," << n_iterations_2
-                                << std::endl;
-    }
+    if (mpi_rank != 0)
+        return;
+    auto& out = iterations_log.rows(output_folder + "iterations.csv", "timestep,time,iterations_1,iterations_2");
+    if (out)
+        out << timestep_number << ',' << time << ',' << n_iterations_1 << ',' << n_iterations_2 << std::endl;
 }
 
+// error.csv: L2 / H1 errors against the Solution expression and their relative versions, scientific
+// with 6 digits (:241-272); nothing is written for problems without an exact solution
 void WaveEquationBase::compute_and_log_error()
 {
     if (exact_solution == nullptr)
         return;
     double e[4];
     check(wave_errors(ctx, time, e), "wave_errors");
-    if (mpi_rank == 0)
-    {
-        if (!error_log_file.is_open())
-        {
-            error_log_file.open(output_folder + "error.csv");
-            if (error_log_file.is_open())
-                error_log_file << "timestep,time,L2_error,H1_error,rel_L2_error,rel_H1_error" << std::endl;
-        }
-        if (error_log_file.is_open())
-            error_log_file << timestep_number << "," << time << "," << std::scientific << std::setprecision(6) << e[0]
-                           << "," << e[1] << "," << e[2] << "," << e[3] << std::endl;
-    }
+    if (mpi_rank != 0)
+        return;
+    auto& out = error_log.rows(output_folder + "error.csv",
+                               "timestep,time,L2_error,H1_error,rel_L2_error,rel_H1_error");
+    if (out)
+        out << timestep_number << ',' << time << ',' << std::scientific << std::setprecision(6) << e[0] << ',' << e[1]
+            << ',' << e[2] << ',' << e[3] << std::endl;
 }
 
 void WaveEquationBase::compute_final_errors() { compute_final_errors("", "", ""); }
@@ -317,19 +299,12 @@ bool WaveEquationBase::check_divergence(const double nu, const double nv, const 
 
 void WaveEquationBase::close_logs()
 {
-    if (mpi_rank == 0)
-    {
-        if (energy_log_file.is_open())
-            energy_log_file.close();
-        if (error_log_file.is_open())
-            error_log_file.close();
-        if (convergence_file.is_open())
-            convergence_file.close();
-        if (iterations_log_file.is_open())
-            iterations_log_file.close();
-        if (point_probe_log_file.is_open())
-            point_probe_log_file.close();
-    }
+    if (mpi_rank != 0)
+        return;
+    for (LazyCsv* log : { &energy_log, &error_log, &iterations_log, &probe_log })
+        log->close();
+    if (convergence_file.is_open())
+        convergence_file.close();
 }
 
 std::string clean_double(double x, int precision)

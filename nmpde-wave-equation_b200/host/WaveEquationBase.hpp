@@ -16,6 +16,34 @@
 
 #include "wave_types.hpp"
 
+/// A CSV time series that is created (with its header line) on the first row: runs with
+/// log_every = 0 leave no files behind, as in the reference.
+class LazyCsv
+{
+  public:
+    /// Stream positioned after the header; opens `path` on first use.  Formatting flags set on the
+    /// stream persist between rows (the reference's sticky std::scientific).
+    std::ofstream& rows(const std::string& path, const char* header)
+    {
+        if (!file.is_open())
+        {
+            file.open(path);
+            if (file.is_open())
+                file << header << std::endl;
+        }
+        return file;
+    }
+    bool is_open() const { return file.is_open(); }
+    void close()
+    {
+        if (file.is_open())
+            file.close();
+    }
+
+  private:
+    std::ofstream file;
+};
+
 class WaveEquationBase
 {
   public:
@@ -66,11 +94,8 @@ class WaveEquationBase
     // ---- Problem description --------------------------------------------------------------------
     const std::string problem_name;
     std::string output_folder;
-    std::ofstream energy_log_file;
-    std::ofstream error_log_file;
-    std::ofstream convergence_file;
-    std::ofstream iterations_log_file;
-    std::ofstream point_probe_log_file;
+    LazyCsv energy_log, error_log, iterations_log, probe_log; // per-run series in output_folder
+    std::ofstream convergence_file;                           // one row per run, shared across runs
 
     std::pair<unsigned int, unsigned int> N_el;
     const std::pair<Point<dim>, Point<dim>> geometry;
