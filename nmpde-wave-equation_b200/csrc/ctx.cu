@@ -401,7 +401,7 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
     int enq = 0;
     // iteration counts of consecutive time steps are nearly equal (warm start): enqueue as many
     // iterations as the previous solve needed, then poll in pairs
-    int chunk = ctx->prev_its[slot] > 6 ? ctx->prev_its[slot] : 4;
+    int chunk = ctx->prev_its[slot] > 0 ? ctx->prev_its[slot] : 4;
     const int maxit = ctx->hS->maxit;
     for (;;) {
         for (int k = 0; k < chunk; ++k) {
@@ -450,7 +450,7 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
         CK(cudaStreamSynchronize(ctx->stream));
         if (ctx->hS->status != 0) break;
         if (enq > maxit + 8) break;
-        chunk = 2;
+        chunk = use_mg ? 1 : 2;  // a skipped multigrid iteration still costs ~50 no-op launches
     }
     CK(cudaEventRecord(e1, ctx->stream));
     CK(cudaEventSynchronize(e1));
