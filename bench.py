@@ -138,6 +138,12 @@ def hbm_peak():
 def time_oracle(params, scheme, budget_s, max_steps, warmup=1, precond=0):
     """The CPU path: oracle/wave_oracle.c (C restatement of the reference, OpenMP over all host
     threads) stepping the same workload for a bounded number of steps."""
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU path is meant to use every host core
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(ncores)
     from oracle import oracle as O
 
     t0 = time.time()
