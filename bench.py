@@ -146,6 +146,7 @@ def time_oracle(params, scheme, budget_s, max_steps, warmup=1, precond=0):
     os.environ["OMP_NUM_THREADS"] = str(ncores)
     from oracle import oracle as O
 
+    O.lib().oracle_set_num_threads(ncores)  # in case the OpenMP runtime was initialised before
     t0 = time.time()
     o = O.Oracle.from_params(params)
     o.set_cg(precond=precond)

@@ -84,6 +84,7 @@ def lib():
         L.oracle_norm.argtypes = [vp, C.c_int]
         L.oracle_get_quadrature.argtypes = [C.c_int, dp, dp, dp]
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_set_num_threads.argtypes = [C.c_int]
         L.oracle_destroy.argtypes = [vp]
         _lib = L
     return _lib

@@ -1508,6 +1508,13 @@ double oracle_norm(oracle_problem *p, int which) {
     const double *src[] = {p->u, p->v, p->a, p->rhs};
     return sqrt(dot(p, src[which], src[which]));
 }
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
