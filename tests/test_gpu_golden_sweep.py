@@ -1,0 +1,22 @@
+"""Every known-answer row of the reference's result tables through libwavegpu (121 convergence rows,
+15 dissipation rows; about 40 s on a B200)."""
+import importlib.util
+import json
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_all_golden_rows_on_the_gpu(capsys):
+    spec = importlib.util.spec_from_file_location("golden_sweep_gpu", ROOT / "tools" / "golden_sweep_gpu.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main()
+    out = json.loads(capsys.readouterr().out)
+    assert out["convergence_rows"] == 121 and out["dissdisp_rows"] == 15
+    assert out["worst_rel_dev_r1"]["rel_L2"] < 2e-6 and out["worst_rel_dev_r1"]["rel_H1"] < 2e-6
+    assert out["worst_rel_dev_r2"]["rel_L2"] < 6e-5 and out["worst_rel_dev_r2"]["rel_H1"] < 2e-5
+    assert out["energy_ratio_bit_identical_rows"] >= 14 and out["worst_energy_ratio_dev"] < 5e-6
