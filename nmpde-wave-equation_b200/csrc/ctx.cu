@@ -96,6 +96,7 @@ struct wave_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     long long launches = 0;
+    cudaError_t launch_error = cudaSuccess;
     Launcher launcher{};
     bool is_setup = false, is_init = false;
 
@@ -222,10 +223,18 @@ Layout make_layout(const Mesh &m, int rank, int nranks) {
     return L;
 }
 
+int launch_check(wave_ctx *ctx) {
+    if (ctx->launch_error != cudaSuccess) {
+        ctx->err = std::string("kernel launch failed: ") + cudaGetErrorString(ctx->launch_error);
+        ctx->launch_error = cudaSuccess;
+        return WAVE_ERR_CUDA;
+    }
+    return WAVE_OK;
+}
 int sync_check(wave_ctx *ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
-    return WAVE_OK;
+    return launch_check(ctx);
 }
 
 // ---- multi-GPU plumbing: contiguous halo blocks and small all-reduces over NCCL -------------------
@@ -448,6 +457,7 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
         enq += chunk;
         CK(cudaMemcpyAsync(ctx->hS, ctx->S, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        RET(launch_check(ctx));
         if (ctx->hS->status != 0) break;
         if (enq > maxit + 8) break;
         chunk = use_mg ? 1 : 2;  // a skipped multigrid iteration still costs ~50 no-op launches
@@ -692,6 +702,16 @@ int gather_global(wave_ctx *ctx, const double *own_src) {
     return WAVE_OK;
 }
 
+// temporary device allocation released on every exit path
+template <class T>
+struct DevTmp {
+    T *p = nullptr;
+    ~DevTmp() { if (p) cudaFree(p); }
+    DevTmp() = default;
+    DevTmp(const DevTmp &) = delete;
+    DevTmp &operator=(const DevTmp &) = delete;
+};
+
 template <class T>
 int dev_alloc(wave_ctx *ctx, T **p, size_t count, bool zero = true) {
     CK(cudaMalloc((void **)p, sizeof(T) * (count ? count : 1)));
@@ -895,7 +915,7 @@ int wave_create(const wave_config *cfg, wave_ctx **out) {
         }
         ctx->own_stream = true;
     }
-    ctx->launcher = Launcher{ctx->stream, &ctx->launches};
+    ctx->launcher = Launcher{ctx->stream, &ctx->launches, &ctx->launch_error};
     for (auto &e : ctx->ev)
         if (cudaEventCreate(&e) != cudaSuccess) { ctx->err = "cudaEventCreate failed"; return bail(WAVE_ERR_CUDA); }
     Mesh m{};
@@ -1397,55 +1417,48 @@ int wave_get_csr(wave_ctx *ctx, int which, int64_t *rowptr, int32_t *col, double
     const double *src = mat_ptr(ctx, which);
     if (val && !src) return fail(ctx, WAVE_ERR_ARG, "matrix not available for this scheme");
     // canonical row pointer: lengths of the storage rows in canonical row order, then a scan
-    uint32_t *len_c = nullptr, *rp_c = nullptr;
-    RET(dev_alloc(ctx, &len_c, (size_t)L.nown + 1));
-    RET(dev_alloc(ctx, &rp_c, (size_t)L.nown + 1));
-    launch_canonical_lengths(ctx->launcher, L, ctx->A, ctx->c2i, len_c);
+    DevTmp<uint32_t> len_c, rp_c;
+    DevTmp<char> scan_tmp;
+    RET(dev_alloc(ctx, &len_c.p, (size_t)L.nown + 1));
+    RET(dev_alloc(ctx, &rp_c.p, (size_t)L.nown + 1));
+    launch_canonical_lengths(ctx->launcher, L, ctx->A, ctx->c2i, len_c.p);
     {
-        void *tmp = nullptr;
         size_t bytes = 0;
-        CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, len_c, rp_c, L.nown + 1, ctx->stream));
-        CK(cudaMalloc(&tmp, bytes));
-        CK(cub::DeviceScan::ExclusiveSum(tmp, bytes, len_c, rp_c, L.nown + 1, ctx->stream));
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, len_c.p, rp_c.p, L.nown + 1, ctx->stream));
+        CK(cudaMalloc((void **)&scan_tmp.p, bytes));
+        CK(cub::DeviceScan::ExclusiveSum(scan_tmp.p, bytes, len_c.p, rp_c.p, L.nown + 1, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        CK(cudaFree(tmp));
     }
     if (rowptr) {
         std::vector<uint32_t> rp((size_t)L.nown + 1);
-        CK(cudaMemcpy(rp.data(), rp_c, sizeof(uint32_t) * rp.size(), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(rp.data(), rp_c.p, sizeof(uint32_t) * rp.size(), cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < rp.size(); ++i) rowptr[i] = rp[i];
     }
     if (col || val) {
-        double *dval = nullptr;
-        int32_t *dcol = nullptr;
-        if (val) RET(dev_alloc(ctx, &dval, (size_t)ctx->nnz, false));
-        if (col) RET(dev_alloc(ctx, &dcol, (size_t)ctx->nnz, false));
-        launch_export_csr(ctx->launcher, L, ctx->A, ctx->c2i, ctx->i2c, rp_c, src ? src : ctx->M, dval, dcol);
-        if (val) CK(cudaMemcpyAsync(val, dval, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost, ctx->stream));
-        if (col) CK(cudaMemcpyAsync(col, dcol, sizeof(int32_t) * ctx->nnz, cudaMemcpyDeviceToHost, ctx->stream));
+        DevTmp<double> dval;
+        DevTmp<int32_t> dcol;
+        if (val) RET(dev_alloc(ctx, &dval.p, (size_t)ctx->nnz, false));
+        if (col) RET(dev_alloc(ctx, &dcol.p, (size_t)ctx->nnz, false));
+        launch_export_csr(ctx->launcher, L, ctx->A, ctx->c2i, ctx->i2c, rp_c.p, src ? src : ctx->M, dval.p, dcol.p);
+        if (val) CK(cudaMemcpyAsync(val, dval.p, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost, ctx->stream));
+        if (col) CK(cudaMemcpyAsync(col, dcol.p, sizeof(int32_t) * ctx->nnz, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        if (dval) cudaFree(dval);
-        if (dcol) cudaFree(dcol);
     }
-    cudaFree(len_c);
-    cudaFree(rp_c);
-    return WAVE_OK;
+    return launch_check(ctx);
 }
 
 int wave_get_support_points(wave_ctx *ctx, double *x, double *y, size_t n) {
     if (!ctx || !ctx->is_setup) return fail(ctx, WAVE_ERR_STATE, "before wave_setup");
     if (ctx->cfg.nranks != 1 || (int64_t)n != n_dofs(ctx->L.mesh))
         return fail(ctx, WAVE_ERR_ARG, "support points: single rank, n = n_dofs");
-    double *dx = nullptr, *dy = nullptr;
-    RET(dev_alloc(ctx, &dx, n));
-    RET(dev_alloc(ctx, &dy, n));
-    launch_interpolate(ctx->launcher, ctx->L, ctx->dprog, 0.0, nullptr, dx, dy);
-    CK(cudaMemcpyAsync(x, dx, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(y, dy, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    DevTmp<double> dx, dy;
+    RET(dev_alloc(ctx, &dx.p, n));
+    RET(dev_alloc(ctx, &dy.p, n));
+    launch_interpolate(ctx->launcher, ctx->L, ctx->dprog, 0.0, nullptr, dx.p, dy.p);
+    CK(cudaMemcpyAsync(x, dx.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(y, dy.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(dx);
-    cudaFree(dy);
-    return WAVE_OK;
+    return launch_check(ctx);
 }
 
 int64_t wave_n_boundary_dofs(const wave_ctx *ctx) { return ctx ? ctx->nb_global : 0; }

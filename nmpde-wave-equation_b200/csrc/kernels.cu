@@ -956,10 +956,14 @@ inline int stream_blocks(int64_t n) {
 
 int reduction_blocks(int n) { return stream_blocks(n); }
 
-#define WV_LAUNCH(l, kernel, grid, block, smem, ...)              \
-    do {                                                          \
+static inline void note_launch(const Launcher &l) {
+    if (l.count) ++*l.count;
+    if (l.error && *l.error == cudaSuccess) *l.error = cudaPeekAtLastError();
+}
+#define WV_LAUNCH(l, kernel, grid, block, smem, ...)                  \
+    do {                                                              \
         kernel<<<(grid), (block), (smem), (l).stream>>>(__VA_ARGS__); \
-        if ((l).count) ++*(l).count;                              \
+        note_launch(l);                                               \
     } while (0)
 
 // Launch with programmatic dependent launch: the kernel starts with cudaGridDependencySynchronize(), so
@@ -978,8 +982,9 @@ static void launch_pdl(const Launcher &l, void (*kernel)(KArgs...), int grid, in
     attr[0].val.programmaticStreamSerializationAllowed = pdl;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
     if (l.count) ++*l.count;
+    if (l.error && *l.error == cudaSuccess) *l.error = e != cudaSuccess ? e : cudaPeekAtLastError();
 }
 
 void launch_row_lengths(const Launcher &l, const Layout &L, uint32_t *rowlen) {

@@ -123,7 +123,8 @@ struct SpmvArgs {
 // ---- launch wrappers (defined in kernels.cu) ---------------------------------------------------
 struct Launcher {
     cudaStream_t stream;
-    long long *count;  // kernels launched
+    long long *count;    // kernels launched
+    cudaError_t *error;  // first launch error seen (sticky; reported at the next synchronisation point)
 };
 
 void launch_row_lengths(const Launcher &, const Layout &, uint32_t *rowlen);
