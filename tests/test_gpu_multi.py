@@ -50,10 +50,17 @@ CASES = [
 ]
 
 
+def _world_sizes():
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    return [w for w in (2, 4, 8) if w <= n] or [2]
+
+
+@pytest.mark.parametrize("world", _world_sizes())
 @pytest.mark.parametrize("name,scheme,over", CASES)
-def test_two_ranks_match_one_rank(name, scheme, over):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+def test_ranks_match_one_rank(name, scheme, over, world):
+    """2 ranks exercise the end strips; 4 and 8 ranks also the strips with two neighbours."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
 
     from wavegpu import WaveSolver, api, problem
@@ -72,7 +79,8 @@ def test_two_ranks_match_one_rank(name, scheme, over):
     nccl_id = api.comm_unique_id()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(rk, 2, nccl_id, name, scheme, over, nsteps, q)) for rk in range(2)]
+    procs = [ctx.Process(target=_worker, args=(rk, world, nccl_id, name, scheme, over, nsteps, q))
+             for rk in range(world)]
     for p in procs:
         p.start()
     u2, v2, e2, err2, its2, nrm2 = q.get(timeout=300)
