@@ -85,7 +85,6 @@ typedef struct {
 } wave_config;
 
 #define WAVE_FLAG_FORCING_EVERY_STEP 1u /* assemble F even when it folds to 0 (as the reference) */
-#define WAVE_FLAG_NO_PERSISTENT_CG 2u   /* force the multi-launch CG driver on one GPU */
 
 /* ---- life cycle ---------------------------------------------------------------------- */
 /* Fills a config with the reference's declared defaults (src/ParameterReader.cpp:39-105). */

@@ -4,10 +4,11 @@
 // ids follow SURVEY.md section 2.1:
 //   K1  per-cell quadrature M_e, K_e + CSR scatter          (assemble_matrices)
 //   K2  A = M + s K on the shared pattern, Dirichlet rows    (copy_from/add + apply_boundary_values)
-//   K3  CSR-stream SpMV with fused epilogues                 (SparseMatrix::vmult)
+//   K3  SELL-32 SpMV (warp per slice) with fused epilogues   (SparseMatrix::vmult)
 //   K4  per-cell load vector with the compiled f(x,y,t)      (forcing loops)
 //   K5  boundary values -> rhs / start vector                (interpolate_boundary_values)
-//   K6  PCG pieces with device-resident scalars              (SolverCG::solve)
+//   K6  PCG pieces with device-resident scalars, optional    (SolverCG::solve, PreconditionAMG)
+//       multigrid V-cycle, NVLink peer all-reduce / halo
 //   K7  fused Newmark predictor / corrector + norms          (assemble_rhs z, update_u_v)
 //   K8  energy (SpMV + fused dot)                            (compute_and_log_energy)
 //   K9  interpolation of u0 / v0 at support points           (VectorTools::interpolate)

@@ -13,7 +13,8 @@ EXPR_NAMES = ("C", "F", "U0", "V0", "G", "DGDT", "Solution")
 VEC_U, VEC_V, VEC_A, VEC_RHS = 0, 1, 2, 3
 MAT_M, MAT_K, MAT_SYS1, MAT_SYS2 = 0, 1, 2, 3
 SCHEME_NEWMARK, SCHEME_THETA = 0, 1
-FLAG_FORCING_EVERY_STEP, FLAG_NO_PERSISTENT_CG = 1, 2
+FLAG_FORCING_EVERY_STEP = 1
+PRECOND_JACOBI, PRECOND_NONE, PRECOND_MG = 0, 1, 2
 
 STATUS = {0: "WAVE_OK", -1: "WAVE_ERR_ARG", -2: "WAVE_ERR_EXPR", -3: "WAVE_ERR_CUDA", -4: "WAVE_ERR_STATE",
           -5: "WAVE_ERR_NOCONV", -6: "WAVE_ERR_DIVERGED", -7: "WAVE_ERR_UNSUPPORTED"}
