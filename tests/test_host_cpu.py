@@ -166,3 +166,26 @@ def test_mpirun_shim_drops_mpi_options():
     r = subprocess.run([str(shim), "-np", "16", "--bind-to", "core", "--map-by", "socket", "--hostfile", "/tmp/x",
                         "echo", "binary", "params.json"], capture_output=True, text=True, timeout=30)
     assert r.returncode == 0 and r.stdout.split() == ["binary", "params.json"]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times): one JSON line with the contract keys."""
+    import json
+    import os
+    import sys
+
+    env = dict(os.environ, WAVE_BENCH_NEL="48", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "dof_steps_per_sec" and line["unit"] == "DoF-steps/s"
+    assert line["value"] > 0 and line["steps"] == 2 and line["higher_is_better"] is True
+    assert line["e2e"] == {"value": line["value"], "unit": "DoF-steps/s", "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["config"]["workload"] == "c2-standing-newmark-1024-p1" and line["config"]["n_dofs"] == 49 * 49
+    # ranks other than 0 print nothing and exit 0 (torchrun launch of the reference arm)
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1"],
+                       capture_output=True, text=True, timeout=60, env=dict(env, RANK="1", WORLD_SIZE="2"))
+    assert r.returncode == 0 and r.stdout.strip() == ""
