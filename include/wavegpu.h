@@ -136,7 +136,8 @@ int wave_run(wave_ctx *ctx, double t_start, int32_t n_steps, double *t_end, int3
              int32_t iters[2], double norms[2], int64_t *total_iters);
 /* Stateless form for callers that keep their vectors in host memory (the reference keeps them in
    Trilinos vectors): uploads u, v, (a) in canonical numbering, performs one step, downloads the
-   new u, v, (a).  a may be NULL for the theta scheme. */
+   new u, v, (a).  a may be NULL for the theta scheme.  With several ranks the arrays have global
+   length and every rank reads / refreshes its own rows (plus read-only ghost rows). */
 int wave_step_host(wave_ctx *ctx, double t_np1, double *u, double *v, double *a, int32_t iters[2],
                    double norms[2]);
 

@@ -1320,16 +1320,13 @@ int wave_step_host(wave_ctx *ctx, double t_np1, double *u, double *v, double *a,
         RET(upload_local(ctx, a, ctx->a));
     }
     RET(wave_step(ctx, t_np1, iters, norms));
-    if (ctx->cfg.nranks == 1) {  // three downloads back to back, one synchronisation
-        RET(download_own_async(ctx, ctx->u + L.own_off, u));
-        RET(download_own_async(ctx, ctx->v + L.own_off, v));
-        if (ctx->cfg.scheme == WAVE_SCHEME_NEWMARK) RET(download_own_async(ctx, ctx->a + L.own_off, a));
-        CK(cudaStreamSynchronize(ctx->stream));
-        return WAVE_OK;
-    }
-    RET(wave_get_vector(ctx, WAVE_VEC_U, u, n));
-    RET(wave_get_vector(ctx, WAVE_VEC_V, v, n));
-    if (ctx->cfg.scheme == WAVE_SCHEME_NEWMARK) RET(wave_get_vector(ctx, WAVE_VEC_A, a, n));
+    // three downloads back to back, one synchronisation.  With several ranks every rank refreshes its
+    // owned rows of the caller's arrays (the ghost parts are re-exchanged on the device each step).
+    RET(download_own_async(ctx, ctx->u + L.own_off, u + L.row0));
+    RET(download_own_async(ctx, ctx->v + L.own_off, v + L.row0));
+    if (ctx->cfg.scheme == WAVE_SCHEME_NEWMARK) RET(download_own_async(ctx, ctx->a + L.own_off, a + L.row0));
+    CK(cudaStreamSynchronize(ctx->stream));
+    (void)n;
     return WAVE_OK;
 }
 

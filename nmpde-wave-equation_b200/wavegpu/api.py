@@ -284,6 +284,12 @@ class WaveSolver:
         self._ck(self.L.wave_get_vector(self.h, which, _dp(v), v.size))
         return v
 
+    def vector_owned(self, which):
+        """This rank's owned rows only (canonical order), for multi-rank contexts."""
+        v = np.empty(self.nown)
+        self._ck(self.L.wave_get_vector(self.h, which, _dp(v), v.size))
+        return v
+
     def set_vector(self, which, arr):
         arr = np.ascontiguousarray(arr, dtype=np.float64)
         self._ck(self.L.wave_set_vector(self.h, which, _dp(arr), arr.size))
