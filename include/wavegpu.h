@@ -168,6 +168,9 @@ int64_t wave_n_boundary_dofs(const wave_ctx *ctx);
 int wave_get_boundary_dofs(wave_ctx *ctx, int32_t *out, size_t n);
 /* Closed-form cell -> DoF map (distribute_dofs numbering), dpc entries per cell; host only. */
 int wave_cell_dofs(int32_t nx, int32_t ny, int32_t r, int64_t cell, int32_t *out);
+/* The same cell's DoFs in the internal storage numbering (kind-major inside each block for R = 2,
+   identical to the canonical numbering for R = 1); host only, for tests of the permutation. */
+int wave_cell_dofs_storage(int32_t nx, int32_t ny, int32_t r, int64_t cell, int32_t *out);
 
 /* ---- kernel-level entry points (parity tests, roofline measurement) ------------------- */
 /* y = A x on the device path (TrilinosWrappers::SparseMatrix::vmult); host vectors, canonical

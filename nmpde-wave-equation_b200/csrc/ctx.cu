@@ -1624,6 +1624,16 @@ int wave_cell_dofs(int32_t nx, int32_t ny, int32_t r, int64_t cell, int32_t *out
     return WAVE_OK;
 }
 
+int wave_cell_dofs_storage(int32_t nx, int32_t ny, int32_t r, int64_t cell, int32_t *out) {
+    if (nx < 1 || ny < 1 || (r != 1 && r != 2) || cell < 0 || cell >= 2LL * nx * ny || !out) return WAVE_ERR_ARG;
+    Mesh m{};
+    m.nx = nx; m.ny = ny; m.r = r;
+    int64_t d[6];
+    cell_dofs_internal(m, cell, d);
+    for (int k = 0; k < dofs_per_cell(r); ++k) out[k] = (int32_t)d[k];
+    return WAVE_OK;
+}
+
 int wave_partition_plan(int32_t nx, int32_t ny, int32_t r, int32_t rank, int32_t nranks, wave_partition *out) {
     if (nx < 1 || ny < 1 || (r != 1 && r != 2) || nranks < 1 || rank < 0 || rank >= nranks || ny < nranks || !out)
         return WAVE_ERR_ARG;

@@ -93,6 +93,7 @@ def lib():
         L.wave_get_support_points.argtypes = [vp, dp, dp, C.c_size_t]
         L.wave_get_boundary_dofs.argtypes = [vp, ip, C.c_size_t]
         L.wave_cell_dofs.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, ip]
+        L.wave_cell_dofs_storage.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, ip]
         L.wave_spmv.argtypes = [vp, C.c_int, dp, dp, C.c_size_t]
         L.wave_cg.argtypes = [vp, C.c_int, dp, dp, C.c_size_t, ip]
         L.wave_bench_spmv.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp]
@@ -147,6 +148,17 @@ def cell_dofs(nx, ny, r):
     L = lib()
     for c in range(ncells):
         L.wave_cell_dofs(nx, ny, r, c, _ip(out[c]))
+    return out
+
+
+def cell_dofs_storage(nx, ny, r):
+    """Cell->DoF table in the internal storage numbering (host only)."""
+    dpc = 3 if r == 1 else 6
+    ncells = 2 * nx * ny
+    out = np.empty((ncells, dpc), dtype=np.int32)
+    L = lib()
+    for c in range(ncells):
+        L.wave_cell_dofs_storage(nx, ny, r, c, _ip(out[c]))
     return out
 
 

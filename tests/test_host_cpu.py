@@ -189,3 +189,22 @@ def test_bench_reference_arm_contract():
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1"],
                        capture_output=True, text=True, timeout=60, env=dict(env, RANK="1", WORLD_SIZE="2"))
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+@pytest.mark.parametrize("nx,ny,r", [(1, 1, 2), (3, 2, 2), (5, 7, 2), (8, 4, 1), (16, 5, 2)])
+def test_storage_numbering_is_a_blockwise_permutation(nx, ny, r):
+    """The internal (kind-major) numbering permutes DoFs only inside a block [block_start(j),
+    block_start(j+1)): strips and halos are the same index ranges in both numberings."""
+    canon = cell_dofs(nx, ny, r)
+    stor = api.cell_dofs_storage(nx, ny, r)
+    n = (nx + 1) * (ny + 1) if r == 1 else (2 * nx + 1) * (2 * ny + 1)
+    c2s = np.full(n, -1, dtype=np.int64)
+    for c, s in zip(canon.ravel(), stor.ravel()):
+        assert c2s[c] in (-1, s)  # one storage index per canonical DoF, the same in every cell
+        c2s[c] = s
+    assert sorted(c2s.tolist()) == list(range(n))  # a permutation of all DoFs
+    if r == 1:
+        assert np.array_equal(c2s, np.arange(n))
+    starts = [partition_plan(nx, ny, r, k, ny).row_begin for k in range(ny)] + [n]  # one block per quad row
+    for b0, b1 in zip(starts[:-1], starts[1:]):
+        assert sorted(c2s[b0:b1].tolist()) == list(range(b0, b1))
