@@ -239,7 +239,10 @@ def main():
     n_gpus = world
     workload = args.workload or DEFAULT
     params, scheme, scaling = make_params(workload, n_gpus)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the library runs on the stream it is given, so the events below are
+    # recorded on the very stream the kernels are launched on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     W = max(args.warmup, 3)
     K = args.steps
 
