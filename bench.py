@@ -261,12 +261,14 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(W):
-        g.step()
-    # ---- timed region: K steps, device timed on the context stream -------------------------------
+    # clocks / throttle reasons are sampled from the warm-up through the timed and the bracketed pass
+    # (the timed region alone lasts only tens of milliseconds at 100 ms sampling)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(W):
+        g.step()
+    # ---- timed region: K steps, device timed on the context stream -------------------------------
     g.cg_stats(reset=True)
     launches0 = g.launch_count()
     barrier()
@@ -286,7 +288,6 @@ def main():
     total_ms = float(sum(step_ms))
     launches = g.launch_count() - launches0
     cgs = g.cg_stats()
-    clocks = sampler.stop() if rank == 0 else None
     # second pass over further steps of the same run with every CG SpMV launch bracketed by events on
     # the context stream (kept out of the pass above: the brackets cost ~1 us per launch)
     g.spmv_timing(True)
@@ -301,6 +302,7 @@ def main():
     barrier()
     spmv_launches, spmv_ms = g.spmv_timing(False)
     bracketed_ms = float(sum(a.elapsed_time(b) for a, b in ev2))
+    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
