@@ -171,6 +171,11 @@ int wave_cell_dofs(int32_t nx, int32_t ny, int32_t r, int64_t cell, int32_t *out
 /* The same cell's DoFs in the internal storage numbering (kind-major inside each block for R = 2,
    identical to the canonical numbering for R = 1); host only, for tests of the permutation. */
 int wave_cell_dofs_storage(int32_t nx, int32_t ny, int32_t r, int64_t cell, int32_t *out);
+/* [deal.II] QGaussSimplex<2>(n_points_1d) as the library integrates with it: n = r+1 for assembly and
+   forcing (src/WaveEquationBase.cpp:82), n = r+2 for the error norms (:371,405).  Fills up to 16
+   reference-triangle points and weights (sum 1/2) and returns their number (< 0: unsupported n);
+   host only. */
+int wave_quadrature(int32_t n_points_1d, double *xi, double *eta, double *w);
 
 /* ---- kernel-level entry points (parity tests, roofline measurement) ------------------- */
 /* y = A x on the device path (TrilinosWrappers::SparseMatrix::vmult); host vectors, canonical

@@ -1634,6 +1634,17 @@ int wave_cell_dofs_storage(int32_t nx, int32_t ny, int32_t r, int64_t cell, int3
     return WAVE_OK;
 }
 
+int wave_quadrature(int32_t n_points_1d, double *xi, double *eta, double *w) {
+    if (!xi || !eta || !w) return WAVE_ERR_ARG;
+    try {
+        const Quadrature q = make_quadrature(n_points_1d);
+        for (int k = 0; k < q.nq; ++k) { xi[k] = q.xi[k]; eta[k] = q.eta[k]; w[k] = q.w[k]; }
+        return q.nq;
+    } catch (const std::exception &) {
+        return WAVE_ERR_ARG;
+    }
+}
+
 int wave_partition_plan(int32_t nx, int32_t ny, int32_t r, int32_t rank, int32_t nranks, wave_partition *out) {
     if (nx < 1 || ny < 1 || (r != 1 && r != 2) || nranks < 1 || rank < 0 || rank >= nranks || ny < nranks || !out)
         return WAVE_ERR_ARG;

@@ -223,8 +223,9 @@ WV_HD void shape_grads(int r, double xi, double eta, double *dxi, double *deta) 
 }
 
 // ---- quadrature ([deal.II] QGaussSimplex<2>(n), weights sum to 1/2) -----------------------
-// n=2: 3 points, degree 2.  n=3: 7 points, degree 5 (Radon).  n=4: 16-point degree-7 collapsed
-// Gauss-Legendre x Gauss-Jacobi(1,0) rule (filled on the host, see quadrature.cpp).
+// deal.II >= 9.4 tables: n=2: 4 points, degree 3 (Hillion).  n=3: 7 points, degree 5
+// (Hammer-Marlowe-Stroud).  n=4: 15 points, degree 7 (Witherden-Vincent).  Filled on the host,
+// see quadrature.cpp.
 struct Quadrature {
     int nq;
     double xi[16], eta[16], w[16];

@@ -1,7 +1,18 @@
 // quadrature.cpp -- simplex quadrature tables of the product (host side; copied to the device
 // as plain data).  [deal.II] QGaussSimplex<2>(n) at the reference's call sites
-// src/WaveEquationBase.cpp:82 (n = r+1, assembly) and :371,405 (n = r+2, error norms).
+// src/WaveEquationBase.cpp:82 (n = r+1, assembly and forcing) and :371,405 (n = r+2, error norms).
+//
+// The tables are those of deal.II >= 9.4 (9.3 has no n = 4 rule in two dimensions, and the
+// reference's own P2 error tables, analysis/data/convergence-results.csv, are reproduced to their
+// 7 printed digits only by the 15-point Witherden-Vincent rule):
+//   n = 2   4 points, degree 3   Hillion's scheme: 2x2 Gauss x Gauss-Jacobi(1,0), collapsed
+//   n = 3   7 points, degree 5   Hammer-Marlowe-Stroud (Radon)
+//   n = 4  15 points, degree 7   Witherden-Vincent
+// Weights sum to 1/2.  The n = 2 rule is not invariant under vertex permutations, so the cell's
+// vertex order (mesh.h cell_geometry: xi along v0->v1, eta along v0->v2) is part of the result
+// whenever the integrand is not a cubic (forcing vectors, variable c).
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <stdexcept>
 
@@ -10,117 +21,72 @@
 namespace wv {
 namespace {
 
-// Legendre P_n(x) and P_n'(x)
-void legendre(int n, double x, double &p, double &dp) {
-    double p0 = 1.0, p1 = x;
-    if (n == 0) { p = 1.0; dp = 0.0; return; }
-    for (int k = 2; k <= n; ++k) {
-        const double pk = ((2.0 * k - 1.0) * x * p1 - (k - 1.0) * p0) / k;
-        p0 = p1; p1 = pk;
+struct Builder {
+    Quadrature q{};
+    void add(double xi, double eta, double w) {
+        if (q.nq >= 16) throw std::logic_error("quadrature table overflow");
+        q.xi[q.nq] = xi;
+        q.eta[q.nq] = eta;
+        q.w[q.nq] = w;
+        ++q.nq;
     }
-    p = p1;
-    dp = n * (x * p1 - p0) / (x * x - 1.0);
+    // every distinct arrangement of the barycentric triple, ascending lexicographic order; the
+    // Cartesian point is the first two coordinates
+    void add_orbit(std::array<double, 3> b, double w) {
+        std::sort(b.begin(), b.end());
+        do add(b[0], b[1], w);
+        while (std::next_permutation(b.begin(), b.end()));
+    }
+};
+
+Quadrature hillion4() {
+    Builder B;
+    // eta: Gauss-Jacobi(1,0) nodes (4 -+ sqrt 6)/10 on [0,1]; xi = (1 - eta)(1 -+ 1/sqrt 3)/2
+    const double wl = 0.31804138174397717, wh = 0.18195861825602283;  // (9 +- sqrt 6)/36
+    B.add(0.17855872826361643, 0.1550510257216822, 0.5 * wl);
+    B.add(0.07503111022260812, 0.6449489742783178, 0.5 * wh);
+    B.add(0.6663902460147014, 0.1550510257216822, 0.5 * wl);
+    B.add(0.28001991549907407, 0.6449489742783178, 0.5 * wh);
+    return B.q;
 }
 
-void gauss_legendre(int n, double *x, double *w) {
-    for (int k = 0; k < n; ++k) {
-        double z = -std::cos(M_PI * (k + 0.75) / (n + 0.5));
-        for (int it = 0; it < 100; ++it) {
-            double p, dp;
-            legendre(n, z, p, dp);
-            const double dz = p / dp;
-            z -= dz;
-            if (std::fabs(dz) < 1e-16) break;
-        }
-        double p, dp;
-        legendre(n, z, p, dp);
-        x[k] = z;
-        w[k] = 2.0 / ((1.0 - z * z) * dp * dp);
-    }
+Quadrature hammer_marlowe_stroud7() {
+    Builder B;
+    const double r = std::sqrt(15.0);
+    const double lo = 2.0 / 7.0 - r / 21.0, hi = 2.0 / 7.0 + r / 21.0;
+    const double lo_c = 3.0 / 7.0 + 2.0 * r / 21.0, hi_c = 3.0 / 7.0 - 2.0 * r / 21.0;  // 1 - 2 lo, 1 - 2 hi
+    const double w_lo = 0.5 * (31.0 / 240.0 - r / 1200.0), w_hi = 0.5 * (31.0 / 240.0 + r / 1200.0);
+    B.add(1.0 / 3.0, 1.0 / 3.0, 0.5 * (9.0 / 40.0));
+    B.add(lo_c, lo, w_lo);
+    B.add(lo, lo_c, w_lo);
+    B.add(lo, lo, w_lo);
+    B.add(hi_c, hi, w_hi);
+    B.add(hi, hi_c, w_hi);
+    B.add(hi, hi, w_hi);
+    return B.q;
 }
 
-// n-point Gauss rule for the weight (1-x) on [-1,1]: nodes are the zeros of
-// (P_n(x) - P_{n+1}(x)) / (1 - x); weights from the moment equations.
-void gauss_jacobi10(int n, double *x, double *w) {
-    auto f = [&](double z, double &v, double &dv) {
-        double pa, da, pb, db;
-        legendre(n, z, pa, da);
-        legendre(n + 1, z, pb, db);
-        v = pa - pb;
-        dv = da - db;
-    };
-    for (int k = 0; k < n; ++k) {
-        double z = -std::cos(M_PI * (k + 0.5) / (n + 0.5));
-        for (int it = 0; it < 200; ++it) {
-            double v, dv, s = 1.0 / (z - 1.0);  // deflate the root at x = 1 and the found ones
-            f(z, v, dv);
-            for (int m = 0; m < k; ++m) s += 1.0 / (z - x[m]);
-            const double dz = v / (dv - v * s);
-            z -= dz;
-            if (std::fabs(dz) < 1e-16) break;
-        }
-        x[k] = z;
-    }
-    std::sort(x, x + n);
-    // moments  int_{-1}^{1} (1-x) x^m dx
-    double A[8][9];
-    for (int m = 0; m < n; ++m) {
-        for (int k = 0; k < n; ++k) A[m][k] = std::pow(x[k], m);
-        const double a = (m % 2 == 0) ? 2.0 / (m + 1) : 0.0;        // int x^m
-        const double b = ((m + 1) % 2 == 0) ? 2.0 / (m + 2) : 0.0;  // int x^(m+1)
-        A[m][n] = a - b;
-    }
-    for (int c = 0; c < n; ++c) {  // Gaussian elimination with partial pivoting
-        int piv = c;
-        for (int r = c + 1; r < n; ++r)
-            if (std::fabs(A[r][c]) > std::fabs(A[piv][c])) piv = r;
-        for (int k = 0; k <= n; ++k) std::swap(A[c][k], A[piv][k]);
-        for (int r = c + 1; r < n; ++r) {
-            const double fct = A[r][c] / A[c][c];
-            for (int k = c; k <= n; ++k) A[r][k] -= fct * A[c][k];
-        }
-    }
-    for (int r = n - 1; r >= 0; --r) {
-        double s = A[r][n];
-        for (int k = r + 1; k < n; ++k) s -= A[r][k] * w[k];
-        w[r] = s / A[r][r];
-    }
+Quadrature witherden_vincent15() {
+    Builder B;
+    struct S21 { double a, w; };
+    const S21 s21[3] = {{0.03373064855458785, 0.016545050110792132},
+                        {0.24157738259540357, 0.12794417123015558},
+                        {0.47430969250471822, 0.07708664618598607}};
+    for (const S21 &o : s21) B.add_orbit({o.a, o.a, 1.0 - 2.0 * o.a}, 0.5 * o.w);
+    const double b1 = 0.047036644652595234, b2 = 0.19868331479735159;
+    B.add_orbit({b1, b2, 1.0 - b1 - b2}, 0.5 * 0.05587873290319978);
+    return B.q;
 }
 
 }  // namespace
 
 Quadrature make_quadrature(int n1d) {
-    Quadrature q{};
-    if (n1d == 2) {
-        q.nq = 3;
-        const double pts[3][2] = {{1.0 / 6, 1.0 / 6}, {2.0 / 3, 1.0 / 6}, {1.0 / 6, 2.0 / 3}};
-        for (int k = 0; k < 3; ++k) { q.xi[k] = pts[k][0]; q.eta[k] = pts[k][1]; q.w[k] = 1.0 / 6; }
-    } else if (n1d == 3) {
-        q.nq = 7;
-        const double s15 = std::sqrt(15.0);
-        const double a = (6.0 - s15) / 21.0, b = (6.0 + s15) / 21.0;
-        const double wa = (155.0 - s15) / 2400.0, wb = (155.0 + s15) / 2400.0;
-        const double pts[7][3] = {{1.0 / 3, 1.0 / 3, 9.0 / 80}, {a, a, wa}, {1 - 2 * a, a, wa},
-                                  {a, 1 - 2 * a, wa},           {b, b, wb}, {1 - 2 * b, b, wb},
-                                  {b, 1 - 2 * b, wb}};
-        for (int k = 0; k < 7; ++k) { q.xi[k] = pts[k][0]; q.eta[k] = pts[k][1]; q.w[k] = pts[k][2]; }
-    } else if (n1d == 4) {
-        const int n = 4;
-        double gx[8], gw[8], jx[8], jw[8];
-        gauss_legendre(n, gx, gw);
-        gauss_jacobi10(n, jx, jw);
-        q.nq = n * n;
-        int k = 0;
-        for (int a = 0; a < n; ++a)
-            for (int b = 0; b < n; ++b) {
-                q.xi[k] = 0.5 * (1.0 + jx[a]);
-                q.eta[k] = 0.25 * (1.0 - jx[a]) * (1.0 + gx[b]);
-                q.w[k] = jw[a] * gw[b] / 8.0;
-                ++k;
-            }
-    } else
-        throw std::invalid_argument("unsupported quadrature order");
-    return q;
+    switch (n1d) {
+        case 2: return hillion4();
+        case 3: return hammer_marlowe_stroud7();
+        case 4: return witherden_vincent15();
+        default: throw std::invalid_argument("unsupported quadrature order");
+    }
 }
 
 }  // namespace wv

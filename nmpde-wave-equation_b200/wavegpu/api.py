@@ -94,6 +94,7 @@ def lib():
         L.wave_get_boundary_dofs.argtypes = [vp, ip, C.c_size_t]
         L.wave_cell_dofs.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, ip]
         L.wave_cell_dofs_storage.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, ip]
+        L.wave_quadrature.argtypes = [C.c_int32, dp, dp, dp]
         L.wave_spmv.argtypes = [vp, C.c_int, dp, dp, C.c_size_t]
         L.wave_cg.argtypes = [vp, C.c_int, dp, dp, C.c_size_t, ip]
         L.wave_bench_spmv.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp]
@@ -160,6 +161,15 @@ def cell_dofs_storage(nx, ny, r):
     for c in range(ncells):
         L.wave_cell_dofs_storage(nx, ny, r, c, _ip(out[c]))
     return out
+
+
+def quadrature(n1d):
+    """(xi, eta, w) of the library's QGaussSimplex<2>(n1d) table (host only)."""
+    xi, eta, w = np.zeros(16), np.zeros(16), np.zeros(16)
+    nq = lib().wave_quadrature(n1d, _dp(xi), _dp(eta), _dp(w))
+    if nq < 0:
+        raise WaveError(nq, "unsupported quadrature order")
+    return xi[:nq].copy(), eta[:nq].copy(), w[:nq].copy()
 
 
 def comm_unique_id() -> bytes:

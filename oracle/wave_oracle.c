@@ -561,81 +561,66 @@ double oracle_eval(oracle_problem *p, int which, double x, double y, double t) {
 }
 
 /* ------------------------------------------------------------------------- */
-/* Quadrature [deal.II QGaussSimplex<2>(n), deal.II 9.3 tables]               */
-/* n=2: 3-point degree 2; n=3: 7-point degree 5 (Radon); n=4: reference uses a */
-/* 15-point rule -- restated here as the 16-point degree-7 collapsed           */
-/* Gauss-Legendre x Gauss-Jacobi(1,0) rule (unpinned choice). */
+/* Quadrature [deal.II QGaussSimplex<2>(n), deal.II >= 9.4 tables]            */
+/* Call sites: src/WaveEquationBase.cpp:82 (n = r+1) and :371,405 (n = r+2).  */
+/* n=2: 4 points, degree 3 (Hillion's scheme = 2x2 Gauss x Gauss-Jacobi(1,0)  */
+/*      collapsed onto the triangle; not symmetric under vertex permutation); */
+/* n=3: 7 points, degree 5 (Hammer-Marlowe-Stroud / Radon);                   */
+/* n=4: 15 points, degree 7 (Witherden-Vincent).                              */
+/* Which release the reference was built with is pinned by its own results:   */
+/* the P2 rows of analysis/data/convergence-results.csv (error norms through  */
+/* n=4) reproduce to the 7 printed digits with the Witherden-Vincent rule and */
+/* only to 5e-5 with other degree-7 rules; deal.II 9.3 has no n=4 rule in 2-D.*/
 /* Weights sum to 1/2 (reference triangle area).                              */
 /* ------------------------------------------------------------------------- */
-/* P_n^{(a,0)}(z) and its derivative by the three-term recurrence */
-static void jacobi_eval(int n, double a, double z, double *pv, double *dv) {
-    const double b = 0.0;
-    double pkm1 = 1.0, pk = 0.5 * (a - b + (a + b + 2.0) * z);
-    if (n == 0) { *pv = 1.0; *dv = 0.0; return; }
-    for (int j = 2; j <= n; ++j) {
-        const double t = 2.0 * j + a + b;
-        const double c1 = 2.0 * j * (j + a + b) * (t - 2.0);
-        const double c2 = (t - 1.0) * (a * a - b * b + t * (t - 2.0) * z);
-        const double c3 = 2.0 * (j - 1.0 + a) * (j - 1.0 + b) * t;
-        const double pn = (c2 * pk - c3 * pkm1) / c1;
-        pkm1 = pk; pk = pn;
-    }
-    const double t = 2.0 * n + a + b;
-    *pv = pk;
-    *dv = (n * (a - b - t * z) * pk + 2.0 * (n + a) * (n + b) * pkm1) / (t * (1.0 - z * z));
+static void put_point(quadrule_t *q, double xi, double eta, double w) {
+    q->xi[q->nq] = xi; q->eta[q->nq] = eta; q->w[q->nq] = w; q->nq++;
 }
-/* n-point Gauss-Jacobi rule for weight (1-x)^a on [-1,1]: Newton with deflation */
-static void gauss_jacobi(int n, double a, double *x, double *w) {
-    for (int k = 0; k < n; ++k) {
-        double z = -cos(M_PI * (k + 0.5) / n);
-        for (int it = 0; it < 200; ++it) {
-            double pv, dv, s = 0.0;
-            jacobi_eval(n, a, z, &pv, &dv);
-            for (int m = 0; m < k; ++m) s += 1.0 / (z - x[m]);
-            const double dz = pv / (dv - pv * s);
-            z -= dz;
-            if (fabs(dz) < 1e-16) break;
-        }
-        x[k] = z;
-    }
-    const double g = pow(2.0, a + 1.0) * tgamma(n + a + 1.0) * tgamma(n + 1.0) /
-                     (tgamma(n + a + 1.0) * tgamma(n + 1.0));
-    for (int k = 0; k < n; ++k) {
-        double pv, dv;
-        jacobi_eval(n, a, x[k], &pv, &dv);
-        w[k] = g / ((1.0 - x[k] * x[k]) * dv * dv);
+/* first two barycentric coordinates of every distinct permutation of (b0,b1,b2), in
+   lexicographic order of the sorted triple */
+static void put_orbit(quadrule_t *q, double b0, double b1, double b2, double w) {
+    double b[3] = {b0, b1, b2};
+    for (int i = 0; i < 3; ++i)
+        for (int j = i + 1; j < 3; ++j)
+            if (b[j] < b[i]) { double t = b[i]; b[i] = b[j]; b[j] = t; }
+    static const int perm[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+    double seen[6][2];
+    int ns = 0;
+    for (int p = 0; p < 6; ++p) {
+        const double x = b[perm[p][0]], y = b[perm[p][1]];
+        int dup = 0;
+        for (int k = 0; k < ns; ++k) dup |= (seen[k][0] == x && seen[k][1] == y);
+        if (dup) continue;
+        seen[ns][0] = x; seen[ns][1] = y; ns++;
+        put_point(q, x, y, w);
     }
 }
 static void make_quadrature(int n1d, quadrule_t *q) {
+    q->nq = 0;
     if (n1d == 2) {
-        q->nq = 3;
-        const double P[3][2] = {{1.0 / 6, 1.0 / 6}, {2.0 / 3, 1.0 / 6}, {1.0 / 6, 2.0 / 3}};
-        for (int i = 0; i < 3; ++i) { q->xi[i] = P[i][0]; q->eta[i] = P[i][1]; q->w[i] = 1.0 / 6; }
+        put_point(q, 0.17855872826361643, 0.1550510257216822, 0.5 * 0.31804138174397717);
+        put_point(q, 0.07503111022260812, 0.6449489742783178, 0.5 * 0.18195861825602283);
+        put_point(q, 0.6663902460147014, 0.1550510257216822, 0.5 * 0.31804138174397717);
+        put_point(q, 0.28001991549907407, 0.6449489742783178, 0.5 * 0.18195861825602283);
     } else if (n1d == 3) {
-        q->nq = 7;
         const double s15 = sqrt(15.0);
-        const double a = (6.0 - s15) / 21.0, b = (6.0 + s15) / 21.0;
-        const double wa = (155.0 - s15) / 2400.0, wb = (155.0 + s15) / 2400.0;
-        const double P[7][3] = {{1.0 / 3, 1.0 / 3, 9.0 / 80}, {a, a, wa}, {1 - 2 * a, a, wa},
-                                {a, 1 - 2 * a, wa},           {b, b, wb}, {1 - 2 * b, b, wb},
-                                {b, 1 - 2 * b, wb}};
-        for (int i = 0; i < 7; ++i) { q->xi[i] = P[i][0]; q->eta[i] = P[i][1]; q->w[i] = P[i][2]; }
+        const double p0 = 2.0 / 7.0 - s15 / 21.0, p1 = 2.0 / 7.0 + s15 / 21.0;
+        const double p2 = 3.0 / 7.0 - 2.0 * s15 / 21.0, p3 = 3.0 / 7.0 + 2.0 * s15 / 21.0;
+        const double w0 = 9.0 / 40.0, w1 = 31.0 / 240.0 - s15 / 1200.0, w2 = 31.0 / 240.0 + s15 / 1200.0;
+        put_point(q, 1.0 / 3.0, 1.0 / 3.0, 0.5 * w0);
+        put_point(q, p3, p0, 0.5 * w1);
+        put_point(q, p0, p3, 0.5 * w1);
+        put_point(q, p0, p0, 0.5 * w1);
+        put_point(q, p2, p1, 0.5 * w2);
+        put_point(q, p1, p2, 0.5 * w2);
+        put_point(q, p1, p1, 0.5 * w2);
     } else {
-        /* collapsed (Duffy) rule n x n: xi = (1+s)/2, eta = (1-s)(1+t)/4 */
-        int n = 4;
-        double gx[8], gw[8], jx[8], jw[8];
-        gauss_jacobi(n, 0.0, gx, gw);
-        gauss_jacobi(n, 1.0, jx, jw);
-        q->nq = n * n;
-        int k = 0;
-        for (int i = 0; i < n; ++i)
-            for (int j = 0; j < n; ++j) {
-                double s = jx[i], t = gx[j];
-                q->xi[k] = 0.5 * (1.0 + s);
-                q->eta[k] = 0.25 * (1.0 - s) * (1.0 + t);
-                q->w[k] = jw[i] * gw[j] / 8.0;
-                k++;
-            }
+        /* three orbits (a, a, 1-2a) and one orbit (b1, b2, 1-b1-b2); weights for unit total */
+        static const double a[3] = {0.03373064855458785, 0.24157738259540357, 0.47430969250471822};
+        static const double wa[3] = {0.016545050110792132, 0.12794417123015558, 0.07708664618598607};
+        static const double b1 = 0.047036644652595234, b2 = 0.19868331479735159, wb = 0.05587873290319978;
+        for (int o = 0; o < 3; ++o) put_orbit(q, a[o], a[o], 1.0 - 2.0 * a[o], 0.5 * wa[o]);
+        put_orbit(q, b1, b2, 1.0 - b1 - b2, 0.5 * wb);
     }
 }
 int oracle_get_quadrature(int n1d, double *xi, double *eta, double *w) {

@@ -2,6 +2,7 @@
 15 dissipation rows; about 40 s on a B200)."""
 import importlib.util
 import json
+import os
 from pathlib import Path
 
 import pytest
@@ -16,7 +17,10 @@ def test_all_golden_rows_on_the_gpu(capsys):
     spec.loader.exec_module(mod)
     mod.main()
     out = json.loads(capsys.readouterr().out)
+    if os.environ.get("WAVE_GOLDEN_OUT"):  # keep the measured deviations (profiles/)
+        Path(os.environ["WAVE_GOLDEN_OUT"]).write_text(json.dumps(out, indent=1))
     assert out["convergence_rows"] == 121 and out["dissdisp_rows"] == 15
-    assert out["worst_rel_dev_r1"]["rel_L2"] < 2e-6 and out["worst_rel_dev_r1"]["rel_H1"] < 2e-6
-    assert out["worst_rel_dev_r2"]["rel_L2"] < 6e-5 and out["worst_rel_dev_r2"]["rel_H1"] < 2e-5
+    # 7 printed digits in the reference's tables, for P1 and P2 alike
+    for key in ("worst_rel_dev_r1", "worst_rel_dev_r2"):
+        assert out[key]["rel_L2"] < 1e-6 and out[key]["rel_H1"] < 1e-6, out
     assert out["energy_ratio_bit_identical_rows"] >= 14 and out["worst_energy_ratio_dev"] < 5e-6

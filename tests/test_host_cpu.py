@@ -208,3 +208,38 @@ def test_storage_numbering_is_a_blockwise_permutation(nx, ny, r):
     starts = [partition_plan(nx, ny, r, k, ny).row_begin for k in range(ny)] + [n]  # one block per quad row
     for b0, b1 in zip(starts[:-1], starts[1:]):
         assert sorted(c2s[b0:b1].tolist()) == list(range(b0, b1))
+
+
+@pytest.mark.parametrize("n1d,nq,degree", [(2, 4, 3), (3, 7, 5), (4, 15, 7)])
+def test_library_quadrature_tables(n1d, nq, degree):
+    """The library integrates with the same QGaussSimplex<2>(n) tables as the oracle (deal.II >= 9.4:
+    Hillion 4-point, Hammer-Marlowe-Stroud 7-point, Witherden-Vincent 15-point), in the same point
+    order, each exact to its degree (src/WaveEquationBase.cpp:82,371)."""
+    from math import factorial as f
+
+    xi, eta, w = api.quadrature(n1d)
+    assert len(w) == nq and np.all(w > 0) and np.all(xi > 0) and np.all(eta > 0) and np.all(xi + eta < 1)
+    oxi, oeta, ow = np.zeros(16), np.zeros(16), np.zeros(16)
+    dp = C.POINTER(C.c_double)
+    assert O.lib().oracle_get_quadrature(n1d, oxi.ctypes.data_as(dp), oeta.ctypes.data_as(dp),
+                                         ow.ctypes.data_as(dp)) == nq
+    assert np.abs(xi - oxi[:nq]).max() < 1e-16 and np.abs(eta - oeta[:nq]).max() < 1e-16
+    assert np.abs(w - ow[:nq]).max() < 1e-17
+    for a in range(degree + 1):
+        for b in range(degree + 1 - a):
+            assert (w * xi ** a * eta ** b).sum() == pytest.approx(f(a) * f(b) / f(a + b + 2), abs=1e-15)
+    with pytest.raises(api.WaveError):
+        api.quadrature(5)
+
+
+def test_hillion_rule_is_the_collapsed_gauss_product():
+    """n = 2 (assembly and forcing at R = 1): eta = Gauss-Jacobi(1,0) nodes (4 -+ sqrt 6)/10 with weights
+    (9 +- sqrt 6)/36, xi = (1 - eta)(1 -+ 1/sqrt 3)/2, in deal.II's point order."""
+    xi, eta, w = api.quadrature(2)
+    s6, s3 = 6.0 ** 0.5, 3.0 ** 0.5
+    e = [(4 - s6) / 10, (4 + s6) / 10]
+    ww = [(9 + s6) / 72, (9 - s6) / 72]
+    expect = [((1 - e[0]) * (1 - 1 / s3) / 2, e[0], ww[0]), ((1 - e[1]) * (1 - 1 / s3) / 2, e[1], ww[1]),
+              ((1 - e[0]) * (1 + 1 / s3) / 2, e[0], ww[0]), ((1 - e[1]) * (1 + 1 / s3) / 2, e[1], ww[1])]
+    got = np.stack([xi, eta, w], axis=1)
+    assert np.abs(got - np.array(expect)).max() < 2e-16

@@ -73,7 +73,7 @@ def test_p2_mass_is_exact():
     assert M.min() < 0  # P2 mass matrices have negative vertex-vertex couplings
 
 
-@pytest.mark.parametrize("n1d,nq,deg", [(2, 3, 2), (3, 7, 5), (4, 16, 7)])
+@pytest.mark.parametrize("n1d,nq,deg", [(2, 4, 3), (3, 7, 5), (4, 15, 7)])
 def test_quadrature_degree(n1d, nq, deg):
     xi, eta, w = np.zeros(16), np.zeros(16), np.zeros(16)
     dp = C.POINTER(C.c_double)
