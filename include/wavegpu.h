@@ -94,6 +94,9 @@ int wave_create(const wave_config *cfg, wave_ctx **out);
 void wave_destroy(wave_ctx *ctx);
 /* Message of the last failure on this context (ctx may be NULL for wave_create failures). */
 const char *wave_last_error(const wave_ctx *ctx);
+/* CUDA devices visible to this process (0 without a driver or device); launchers size -np with it
+   and the host classes pick device local_rank % count. */
+int wave_device_count(void);
 /* 128-byte NCCL unique id to broadcast to all ranks before wave_create (rank 0 calls it). */
 int wave_comm_unique_id(void *out128);
 

@@ -2,7 +2,7 @@
 
     python nmpde-wave-equation_b200/build.py [--force]
 
-Outputs: nmpde-wave-equation_b200/lib/libwavegpu.so, bin/main-newmark, bin/main-theta.
+Outputs: nmpde-wave-equation_b200/lib/libwavegpu.so, bin/main-newmark, bin/main-theta, bin/wave-mpirun.
 nvcc cross-compiles without a GPU; the built files travel to the GPU box with the snapshot."""
 import os
 import subprocess
@@ -22,7 +22,8 @@ NVFLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", *ARCH]
 CXXFLAGS = ["-std=c++17", "-O2", "-fPIC", "-Wall"]
 
 LIB_SOURCES = ["kernels.cu", "ctx.cu", "expr.cpp", "quadrature.cpp"]
-HOST_SOURCES = ["ParameterReader.cpp", "WaveEquationBase.cpp", "WaveNewmark.cpp", "WaveTheta.cpp", "cli.cpp"]
+HOST_SOURCES = ["ParameterReader.cpp", "WaveEquationBase.cpp", "WaveNewmark.cpp", "WaveTheta.cpp", "cli.cpp",
+                "launch_env.cpp"]
 
 
 def _newer(target: Path, deps) -> bool:
@@ -61,12 +62,13 @@ def build(force=False, verbose=False):
     if HOST.exists() and all((HOST / s).exists() for s in HOST_SOURCES):  # + host_selftest (CPU-only checks)
         BIN.mkdir(exist_ok=True)
         hdeps = list(HOST.glob("*.hpp")) + list(HOST.glob("*.cpp")) + [HERE.parent / "include" / "wavegpu.h"]
-        for exe in ("main-newmark", "main-theta", "host_selftest"):
+        for exe in ("main-newmark", "main-theta", "host_selftest", "wave-mpirun"):
             target = BIN / exe
+            # the launcher is a single translation unit; the others share the host classes
+            common = [] if exe == "wave-mpirun" else [HOST / s for s in HOST_SOURCES]
             if force or _newer(target, hdeps + [LIB]):
                 _run(["g++", *CXXFLAGS, "-I", HERE.parent / "include", "-o", target, HOST / (exe + ".cpp"),
-                      *[HOST / s for s in HOST_SOURCES], "-L", LIB.parent, "-lwavegpu",
-                      "-Wl,-rpath,$ORIGIN/../lib"])
+                      *common, "-L", LIB.parent, "-lwavegpu", "-Wl,-rpath,$ORIGIN/../lib"])
     return LIB
 
 

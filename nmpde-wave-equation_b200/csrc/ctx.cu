@@ -869,6 +869,15 @@ void wave_default_config(wave_config *c) {
 
 const char *wave_last_error(const wave_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+int wave_device_count(void) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) {
+        cudaGetLastError();  // no driver / no device is an answer (0), not a sticky error
+        return 0;
+    }
+    return ndev;
+}
+
 int wave_comm_unique_id(void *out128) {
     std::string err;
     if (!g_nccl.load(err)) return fail(nullptr, WAVE_ERR_CUDA, err);

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <sstream>
 #include <stdexcept>
 
@@ -50,7 +51,8 @@ WaveEquationBase::WaveEquationBase(const std::string& problem_name_,
                                    Function<dim>* exact_solution_)
     : problem_name(problem_name_), N_el(N_el_), geometry(geometry_), r(r_), T(T_), delta_t(delta_t_), c(c_), f(f_),
       u0(u0_), v0(v0_), g(g_), dgdt(dgdt_), log_every(log_every_), print_every(print_every_),
-      exact_solution(exact_solution_), mpi_size(1), mpi_rank(0), pcout(std::cout, true)
+      exact_solution(exact_solution_), launch(detect_launch_environment()), mpi_size(launch.size),
+      mpi_rank(launch.rank), pcout(std::cout, launch.rank == 0)
 {
 }
 
@@ -96,7 +98,28 @@ void WaveEquationBase::create_context(int scheme, double theta, double beta, dou
         else if (v == "none" || v == "1")
             cfg.precond = WAVE_PRECOND_NONE;
     }
-    if (wave_create(&cfg, &ctx) != WAVE_OK)
+    // several ranks: one GPU each, strips of quad rows, the communicator id broadcast through the
+    // launcher's rendezvous file (the reference's MPI_COMM_WORLD needs no such step)
+    unsigned char comm_id[128] = {};
+    if (mpi_size > 1)
+    {
+        const int n_devices = wave_device_count();
+        if (n_devices > 0 && mpi_size > static_cast<unsigned int>(n_devices) && launch.local_rank >= static_cast<unsigned int>(n_devices))
+            throw std::runtime_error("rank " + std::to_string(mpi_rank) + " of " + std::to_string(mpi_size) +
+                                     " has no GPU of its own: " + std::to_string(n_devices) +
+                                     " device(s) visible; launch at most one rank per GPU");
+        if (mpi_rank == 0 && wave_comm_unique_id(comm_id) != WAVE_OK)
+            throw std::runtime_error(std::string("wave_comm_unique_id: ") + wave_last_error(nullptr));
+        share_communicator_id(launch, comm_id);
+        cfg.rank = static_cast<int32_t>(mpi_rank);
+        cfg.nranks = static_cast<int32_t>(mpi_size);
+        cfg.device = n_devices > 0 ? static_cast<int32_t>(launch.local_rank % n_devices) : -1;
+        cfg.nccl_unique_id = comm_id;
+    }
+    const int created = wave_create(&cfg, &ctx);
+    if (mpi_size > 1 && mpi_rank == 0)
+        std::remove(launch.rendezvous.c_str()); // every rank has joined (or the run is over)
+    if (created != WAVE_OK)
         throw std::runtime_error(std::string("wave_create: ") + wave_last_error(nullptr));
 
     struct Slot { int id; const Function<dim>* fn; const char* name; };
@@ -123,6 +146,9 @@ void WaveEquationBase::setup_mesh()
     pcout << "Initializing the mesh" << std::endl;
     // the structured simplex mesh is generated analytically on the device; no mesh file is written
     pcout << "  Number of elements = " << 2ull * N_el.first * N_el.second << std::endl;
+    if (mpi_size > 1)
+        pcout << "  Partition          = " << mpi_size << " strips of quad rows, one GPU each (" << launch.source
+              << ")" << std::endl;
 }
 
 void WaveEquationBase::setup_fe()
@@ -130,7 +156,8 @@ void WaveEquationBase::setup_fe()
     pcout << "Initializing the finite element space" << std::endl;
     pcout << "  Degree                     = " << r << std::endl;
     pcout << "  DoFs per cell              = " << (r == 1 ? 3 : 6) << std::endl;
-    pcout << "  Quadrature points per cell = " << (r == 1 ? 3 : 7) << std::endl;
+    double xi[16], eta[16], w[16];
+    pcout << "  Quadrature points per cell = " << wave_quadrature(static_cast<int32_t>(r) + 1, xi, eta, w) << std::endl;
 }
 
 void WaveEquationBase::setup_dof_handler()

@@ -14,6 +14,7 @@
 #include <string>
 #include <utility>
 
+#include "launch_env.hpp"
 #include "wave_types.hpp"
 
 /// A CSV time series that is created (with its header line) on the first row: runs with
@@ -121,8 +122,10 @@ class WaveEquationBase
     const unsigned int print_every;
     Function<dim>* exact_solution;
 
-    // one process drives one GPU; the strip partition over several GPUs is configured through
-    // WAVE_RANK / WAVE_NRANKS by a launcher
+    // One process drives one GPU.  Rank and size come from the launcher's environment (launch_env.hpp)
+    // where the reference asks MPI (include/WaveEquationBase.hpp:111-114); rank p owns the p-th strip
+    // of quad rows and rank 0 writes every file, as in the reference.
+    const LaunchEnvironment launch;
     const unsigned int mpi_size;
     const unsigned int mpi_rank;
 

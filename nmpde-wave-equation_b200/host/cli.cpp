@@ -6,6 +6,7 @@
 #include <memory>
 
 #include "ParameterReader.hpp"
+#include "launch_env.hpp"
 #include "WaveNewmark.hpp"
 #include "WaveTheta.hpp"
 
@@ -96,11 +97,23 @@ std::unique_ptr<WaveEquationBase> make_solver(Scheme scheme, const std::string& 
 int wave_cli_main(int argc, char* argv[], Scheme scheme)
 {
     const SchemeTraits tr = traits_of(scheme);
-    const ConditionalOStream pcout(std::cout, true);
+    // rank 0 speaks for the run, as with the reference's pcout (include/WaveEquationBase.hpp:119)
+    LaunchEnvironment launch;
+    try
+    {
+        launch = detect_launch_environment();
+    }
+    catch (const std::exception& e)
+    {
+        std::cout << "Error in the launcher environment: " << e.what() << std::endl;
+        return 1;
+    }
+    const ConditionalOStream pcout(std::cout, launch.rank == 0);
     const bool from_argument = argc > 1;
     const std::string parameters_file = from_argument ? argv[1] : kDefaultParameters;
 
-    pcout << "Backend: libwavegpu (CUDA sm_100a), 1 GPU" << std::endl << kRule << std::endl;
+    pcout << "Backend: libwavegpu (CUDA sm_100a), " << launch.size << (launch.size == 1 ? " GPU" : " GPUs") << std::endl
+          << kRule << std::endl;
     if (from_argument)
         pcout << "Using parameter file from argument: " << parameters_file << std::endl;
     else

@@ -9,6 +9,7 @@
 #include <iostream>
 
 #include "ParameterReader.hpp"
+#include "launch_env.hpp"
 #include "WaveEquationBase.hpp"
 
 namespace
@@ -39,8 +40,35 @@ bool throws(const std::function<void()>& f)
 }
 } // namespace
 
+// `host_selftest --rendezvous`: one rank of a launched group (wave-mpirun or rank variables set by
+// hand).  Rank 0 publishes a recognisable 128-byte record, every rank prints what it holds.
+int rendezvous_mode()
+{
+    try
+    {
+        const LaunchEnvironment env = detect_launch_environment();
+        unsigned char id[128];
+        for (int k = 0; k < 128; ++k)
+            id[k] = env.rank == 0 ? static_cast<unsigned char>(7 * k + 3) : 0;
+        share_communicator_id(env, id, 20.0);
+        unsigned long sum = 0;
+        for (int k = 0; k < 128; ++k)
+            sum += id[k] * static_cast<unsigned long>(k + 1);
+        std::printf("rank %u of %u local %u via %s id %lu\n", env.rank, env.size, env.local_rank,
+                    env.source.empty() ? "none" : env.source.c_str(), sum);
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        std::printf("error: %s\n", e.what());
+        return 1;
+    }
+}
+
 int main(int argc, char** argv)
 {
+    if (argc > 1 && std::string(argv[1]) == "--rendezvous")
+        return rendezvous_mode();
     const std::string dir = argc > 1 ? argv[1] : ".";
 
     // clean_double: src/WaveEquationBase.cpp:433-452 and scripts/dissipation_dispersion_sweep.py:333-357

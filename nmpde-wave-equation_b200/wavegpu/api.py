@@ -95,6 +95,7 @@ def lib():
         L.wave_cell_dofs.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, ip]
         L.wave_cell_dofs_storage.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, ip]
         L.wave_quadrature.argtypes = [C.c_int32, dp, dp, dp]
+        L.wave_device_count.argtypes = []
         L.wave_spmv.argtypes = [vp, C.c_int, dp, dp, C.c_size_t]
         L.wave_cg.argtypes = [vp, C.c_int, dp, dp, C.c_size_t, ip]
         L.wave_bench_spmv.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp]

@@ -84,3 +84,40 @@ def test_cli_divergence_is_reported_and_exit_code_zero(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0
     assert "Divergence detected at step" in r.stdout
+
+
+@pytest.mark.parametrize("exe,scheme,name,over", [
+    ("main-newmark", "newmark", "standing-mode-wsol", dict(Nel="24", R="2", Dt="0.02", T="0.5")),
+    ("main-theta", "theta", "sine-membrane", dict(Nel="30, 10", T="2.0")),
+])
+def test_cli_two_ranks_write_the_one_rank_artefacts(exe, scheme, name, over, tmp_path):
+    """`mpirun -np 2 main-...` of the reference -> `wave-mpirun -np 2 main-...`: two GPUs, strips of quad
+    rows, rank 0 writes the files; every series equals the one-GPU run's (needs >= 2 GPUs)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    p = problem(name, Save_Solution=False, Log_Every=2, Print_Every=5, **over)
+    series = {}
+    for ranks in (1, 2):
+        root = tmp_path / f"np{ranks}"
+        (root / "build").mkdir(parents=True)
+        (root / "parameters").mkdir()
+        write_json(root / "parameters" / "case.json", p)
+        r = subprocess.run([str(BIN / "wave-mpirun"), "-np", str(ranks), "--bind-to", "core", str(BIN / exe),
+                            "../parameters/case.json"], cwd=root / "build", capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert r.stdout.count("Simulation completed") == 1  # rank 0 speaks for the run
+        assert (f"{ranks} GPUs" in r.stdout) == (ranks > 1)
+        run_dirs = [d for d in (root / "results" / f"{scheme}-case").iterdir() if d.is_dir()]
+        assert len(run_dirs) == 1
+        series[ranks] = {f.name: list(csv.reader(f.open())) for f in sorted(run_dirs[0].glob("*.csv"))}
+    assert set(series[1]) == set(series[2]) and "energy.csv" in series[1] and "iterations.csv" in series[1]
+    assert series[1]["iterations.csv"] == series[2]["iterations.csv"]
+    # printed digits: energy 6, errors 7 (per-cell float sums, order differs between partitions), probe 11
+    rtol = {"energy.csv": 2e-6, "error.csv": 2e-6, "probe.csv": 1e-9}
+    for fname in series[1]:
+        a, b = series[1][fname], series[2][fname]
+        assert a[0] == b[0] and len(a) == len(b)
+        for ra, rb in zip(a[1:], b[1:]):
+            assert np.allclose([float(x) for x in ra], [float(x) for x in rb], rtol=rtol.get(fname, 0.0), atol=1e-14)

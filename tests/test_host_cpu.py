@@ -162,10 +162,75 @@ def test_host_selftest_binary(tmp_path):
 
 
 def test_mpirun_shim_drops_mpi_options():
+    """No GPU here, so -np 16 becomes one process: the program runs once with its own arguments."""
     shim = ROOT / "tools" / "mpirun-shim"
     r = subprocess.run([str(shim), "-np", "16", "--bind-to", "core", "--map-by", "socket", "--hostfile", "/tmp/x",
-                        "echo", "binary", "params.json"], capture_output=True, text=True, timeout=30)
+                        "--mca", "btl", "self,vader", "echo", "binary", "params.json"],
+                       capture_output=True, text=True, timeout=30)
     assert r.returncode == 0 and r.stdout.split() == ["binary", "params.json"]
+    assert "starting 1" in r.stderr
+    assert subprocess.run([str(shim), "-np", "2"], capture_output=True, timeout=30).returncode == 2  # no program
+
+
+def _launch(args, **env):
+    import os
+
+    return subprocess.run([str(BIN / "wave-mpirun"), *args], capture_output=True, text=True, timeout=60,
+                          env=dict(os.environ, **env))
+
+
+def test_launcher_starts_ranks_and_shares_the_communicator_id():
+    """`mpirun -np P` of the reference (README.md:113-114) -> bin/wave-mpirun: P processes with
+    WAVE_RANK / WAVE_NRANKS / WAVE_LOCAL_RANK, the 128-byte id published by rank 0 read by all."""
+    r = _launch(["-np", "3", "--bind-to", "core", "-x", "FOO=bar", str(BIN / "host_selftest"), "--rendezvous"],
+                WAVE_LAUNCH_MAX_RANKS="3")
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = sorted(r.stdout.strip().splitlines())
+    expect = sum((7 * k + 3) % 256 * (k + 1) for k in range(128))
+    assert lines == [f"rank {k} of 3 local {k} via WAVE_* id {expect}" for k in range(3)]
+    # more ranks than the cap: clamped, with a note
+    r = _launch(["-np", "8", str(BIN / "host_selftest"), "--rendezvous"], WAVE_LAUNCH_MAX_RANKS="2")
+    assert r.returncode == 0 and len(r.stdout.strip().splitlines()) == 2 and "starting 2" in r.stderr
+    # -x VAR=value reaches the ranks
+    r = _launch(["-np", "2", "-x", "FOO=bar", "sh", "-c", "echo $WAVE_RANK:$FOO"], WAVE_LAUNCH_MAX_RANKS="2")
+    assert sorted(r.stdout.split()) == ["0:bar", "1:bar"]
+
+
+def test_launcher_returns_the_first_failure_and_stops_the_other_ranks():
+    import time
+
+    t0 = time.time()
+    r = _launch(["-np", "2", "sh", "-c", "if [ $WAVE_RANK = 1 ]; then exit 3; else exec sleep 30; fi"],
+                WAVE_LAUNCH_MAX_RANKS="2")
+    assert r.returncode == 3 and time.time() - t0 < 20
+
+
+def test_rank_variables_of_other_launchers(tmp_path):
+    """Open MPI / MPICH / Slurm / torchrun rank variables are understood without an MPI library."""
+    import os
+
+    exe, rdv = str(BIN / "host_selftest"), str(tmp_path / "rdv")
+    for fam, (rk, sz, loc) in {"OMPI_COMM_WORLD_*": ("OMPI_COMM_WORLD_RANK", "OMPI_COMM_WORLD_SIZE",
+                                                     "OMPI_COMM_WORLD_LOCAL_RANK"),
+                               "PMI_*": ("PMI_RANK", "PMI_SIZE", "MPI_LOCALRANKID"),
+                               "SLURM_*": ("SLURM_PROCID", "SLURM_NTASKS", "SLURM_LOCALID"),
+                               "RANK/WORLD_SIZE": ("RANK", "WORLD_SIZE", "LOCAL_RANK")}.items():
+        env = {k: v for k, v in os.environ.items() if not k.startswith(("WAVE_", "OMPI_", "PMI_", "SLURM_"))}
+        env.pop("RANK", None), env.pop("WORLD_SIZE", None), env.pop("LOCAL_RANK", None)
+        env["WAVE_RENDEZVOUS"] = rdv
+        p1 = subprocess.Popen([exe, "--rendezvous"], env={**env, rk: "1", sz: "2", loc: "1"},
+                              stdout=subprocess.PIPE, text=True)
+        r0 = subprocess.run([exe, "--rendezvous"], env={**env, rk: "0", sz: "2", loc: "0"}, capture_output=True,
+                            text=True, timeout=30)
+        out1, _ = p1.communicate(timeout=30)
+        assert r0.returncode == 0 and p1.returncode == 0
+        assert r0.stdout.startswith(f"rank 0 of 2 local 0 via {fam} id ")
+        assert out1.startswith(f"rank 1 of 2 local 1 via {fam} id ") and out1.split()[-1] == r0.stdout.split()[-1]
+        os.remove(rdv)
+    env = {k: v for k, v in os.environ.items() if not k.startswith("WAVE_")}
+    r = subprocess.run([exe, "--rendezvous"], env={**env, "RANK": "5", "WORLD_SIZE": "2"}, capture_output=True,
+                       text=True, timeout=30)
+    assert r.returncode == 1 and "outside WORLD_SIZE=2" in r.stdout
 
 
 def test_bench_reference_arm_contract():
