@@ -23,7 +23,7 @@ CXXFLAGS = ["-std=c++17", "-O2", "-fPIC", "-Wall"]
 
 LIB_SOURCES = ["kernels.cu", "ctx.cu", "expr.cpp", "quadrature.cpp"]
 HOST_SOURCES = ["ParameterReader.cpp", "WaveEquationBase.cpp", "WaveNewmark.cpp", "WaveTheta.cpp", "cli.cpp",
-                "launch_env.cpp"]
+                "launch_env.cpp", "vtu_writer.cpp"]
 
 
 def _newer(target: Path, deps) -> bool:

@@ -3,6 +3,8 @@
 // CSV headers, stream formatting, step line); the numerics behind each call are libwavegpu's.
 #include "WaveEquationBase.hpp"
 
+#include "vtu_writer.hpp"
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -305,18 +307,113 @@ void WaveEquationBase::print_step_info()
     pcout << oss.str() << std::endl;
 }
 
+// Corner points of every cell in the reference's cell order (two triangles per quad, quads row by
+// row: T0 = {q0, q1, q2}, T1 = {q3, q2, q1}; src/WaveEquationBase.cpp:42-46) with the DoF that lives
+// on each corner (the first three entries of the cell's DoF list, for P1 and P2 alike).
+void WaveEquationBase::build_output_mesh() const
+{
+    OutputMesh& m = output_mesh;
+    const int32_t nx = static_cast<int32_t>(N_el.first), ny = static_cast<int32_t>(N_el.second);
+    const size_t n_cells = 2ull * nx * ny;
+    const double dx = (geometry.second[0] - geometry.first[0]) / nx, dy = (geometry.second[1] - geometry.first[1]) / ny;
+    std::vector<int32_t> owner_of_quad_row(static_cast<size_t>(ny), 0);
+    for (unsigned int p = 0; p < mpi_size; ++p)
+    {
+        wave_partition plan;
+        if (wave_partition_plan(nx, ny, static_cast<int32_t>(r), static_cast<int32_t>(p), static_cast<int32_t>(mpi_size),
+                                &plan) != WAVE_OK)
+            throw std::runtime_error("wave_partition_plan failed");
+        for (int64_t j = plan.quad_row_begin; j < plan.quad_row_end; ++j)
+            owner_of_quad_row[static_cast<size_t>(j)] = static_cast<int32_t>(p);
+    }
+    m.dof.resize(3 * n_cells);
+    m.vertex.resize(3 * n_cells);
+    m.xyz.resize(9 * n_cells);
+    m.partitioning.resize(3 * n_cells);
+    for (size_t cell = 0; cell < n_cells; ++cell)
+    {
+        int32_t dofs[6];
+        if (wave_cell_dofs(nx, ny, static_cast<int32_t>(r), static_cast<int64_t>(cell), dofs) != WAVE_OK)
+            throw std::runtime_error("wave_cell_dofs failed");
+        const int32_t quad = static_cast<int32_t>(cell / 2), i = quad % nx, j = quad / nx;
+        const bool upper = cell % 2 == 1;
+        const int32_t ci[3] = { upper ? i + 1 : i, upper ? i : i + 1, upper ? i + 1 : i };
+        const int32_t cj[3] = { upper ? j + 1 : j, upper ? j + 1 : j, upper ? j : j + 1 };
+        for (int k = 0; k < 3; ++k)
+        {
+            const size_t p = 3 * cell + k;
+            m.dof[p] = dofs[k];
+            m.vertex[p] = cj[k] * (nx + 1) + ci[k];
+            m.xyz[3 * p + 0] = static_cast<float>(geometry.first[0] + ci[k] * dx);
+            m.xyz[3 * p + 1] = static_cast<float>(geometry.first[1] + cj[k] * dy);
+            m.xyz[3 * p + 2] = 0.0f;
+            m.partitioning[p] = owner_of_quad_row[static_cast<size_t>(j)];
+        }
+    }
+    m.built = true;
+}
+
+// solution_NNNN.0.vtu + solution_NNNN.pvtu with the fields u, v, [u_exact], partitioning
+// (src/WaveEquationBase.cpp:330-365); written at step 0 and after every step unless
+// "Save Solution" is false.  The vectors come back from the device in canonical numbering
+// (collective over the ranks), rank 0 writes the single piece.
 void WaveEquationBase::output() const
 {
-    // VTU/PVTU visualisation output (src/WaveEquationBase.cpp:330-365) is outside the accelerated
-    // path; runs that ask for it are told once and continue.
-    static bool warned = false;
-    if (env_flag_enabled("NMPDE_SAVE_SOLUTION", true) && !warned)
+    if (!env_flag_enabled("NMPDE_SAVE_SOLUTION", true))
+        return;
+    const size_t n = static_cast<size_t>(wave_n_dofs(ctx));
+    host_u.resize(n);
+    host_v.resize(n);
+    check(wave_get_vector(ctx, WAVE_VEC_U, host_u.data(), n), "wave_get_vector(u)");
+    check(wave_get_vector(ctx, WAVE_VEC_V, host_v.data(), n), "wave_get_vector(v)");
+    if (mpi_rank != 0)
+        return;
+    if (!output_mesh.built)
+        build_output_mesh();
+    const OutputMesh& m = output_mesh;
+    const size_t n_points = m.dof.size();
+
+    std::vector<VtuField> fields;
+    fields.push_back({ "u", std::vector<double>(n_points) });
+    fields.push_back({ "v", std::vector<double>(n_points) });
+    for (size_t p = 0; p < n_points; ++p)
     {
-        warned = true;
-        std::cout << "  Note: 'Save Solution' (VTU output) is not provided by the GPU build; "
-                     "set \"Save Solution\": false to silence this note."
-                  << std::endl;
+        fields[0].values[p] = host_u[static_cast<size_t>(m.dof[p])];
+        fields[1].values[p] = host_v[static_cast<size_t>(m.dof[p])];
     }
+    if (exact_solution != nullptr)
+    {
+        // VectorTools::interpolate of the exact solution at the current time; the corner value is
+        // evaluated once per grid vertex at its double-precision coordinates
+        exact_solution->set_time(time);
+        const int32_t nx = static_cast<int32_t>(N_el.first);
+        const double dx = (geometry.second[0] - geometry.first[0]) / N_el.first,
+                     dy = (geometry.second[1] - geometry.first[1]) / N_el.second;
+        const size_t n_vertices = (static_cast<size_t>(N_el.first) + 1) * (N_el.second + 1);
+        std::vector<double> at_vertex(n_vertices);
+        std::vector<char> known(n_vertices, 0);
+        fields.push_back({ "u_exact", std::vector<double>(n_points) });
+        for (size_t p = 0; p < n_points; ++p)
+        {
+            const size_t vtx = static_cast<size_t>(m.vertex[p]);
+            if (!known[vtx])
+            {
+                const int32_t i = m.vertex[p] % (nx + 1), j = m.vertex[p] / (nx + 1);
+                at_vertex[vtx] =
+                    exact_solution->value(Point<dim>(geometry.first[0] + i * dx, geometry.first[1] + j * dy));
+                known[vtx] = 1;
+            }
+            fields.back().values[p] = at_vertex[vtx];
+        }
+    }
+    fields.push_back({ "partitioning", m.partitioning });
+
+    const std::string piece = vtu_piece_name("solution", timestep_number, 0);
+    write_vtu_piece(output_folder + piece, m.xyz, fields);
+    std::vector<std::string> names;
+    for (const VtuField& f : fields)
+        names.push_back(f.name);
+    write_pvtu_record(output_folder + pvtu_record_name("solution", timestep_number), { piece }, names);
 }
 
 bool WaveEquationBase::check_divergence(const double nu, const double nv, const double threshold) const

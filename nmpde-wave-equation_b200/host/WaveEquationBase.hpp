@@ -13,6 +13,7 @@
 #include <iostream>
 #include <string>
 #include <utility>
+#include <vector>
 
 #include "launch_env.hpp"
 #include "wave_types.hpp"
@@ -131,6 +132,20 @@ class WaveEquationBase
 
     wave_ctx* ctx = nullptr;
     ConditionalOStream pcout;
+
+  private:
+    // what output() needs of the mesh, built on its first call: per output point (three per cell)
+    // the DoF and the grid vertex it sits on, the coordinates and the owning rank of its cell
+    struct OutputMesh
+    {
+        bool built = false;
+        std::vector<int32_t> dof, vertex;
+        std::vector<float> xyz;
+        std::vector<double> partitioning;
+    };
+    mutable OutputMesh output_mesh;
+    mutable std::vector<double> host_u, host_v;
+    void build_output_mesh() const;
 };
 
 /// Format a double for folder names: fixed notation, trailing zeros stripped, '.' -> '_'

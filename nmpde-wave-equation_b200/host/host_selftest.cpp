@@ -10,6 +10,7 @@
 
 #include "ParameterReader.hpp"
 #include "launch_env.hpp"
+#include "vtu_writer.hpp"
 #include "WaveEquationBase.hpp"
 
 namespace
@@ -65,10 +66,43 @@ int rendezvous_mode()
     }
 }
 
+// `host_selftest --vtu <dir>`: two cells (one quad) with recognisable field values through the VTU
+// writer; tests/test_host_cpu.py parses the files back.
+int vtu_mode(const std::string& dir)
+{
+    try
+    {
+        const std::vector<float> xyz = { 0, 0, 0, 1, 0, 0, 0, 2, 0, /* T1 */ 1, 2, 0, 0, 2, 0, 1, 0, 0 };
+        std::vector<VtuField> fields = { { "u", { 0.5, 1.5, 2.5, 3.5, 2.5, 1.5 } },
+                                         { "partitioning", { 0, 0, 0, 1, 1, 1 } } };
+        const std::string piece = vtu_piece_name("solution", 7, 0);
+        write_vtu_piece(dir + "/" + piece, xyz, fields);
+        write_pvtu_record(dir + "/" + pvtu_record_name("solution", 7), { piece }, { "u", "partitioning" });
+        std::printf("%s %s\n", piece.c_str(), pvtu_record_name("solution", 12345).c_str());
+        fields[0].values.pop_back();
+        try
+        {
+            write_vtu_piece(dir + "/bad.vtu", xyz, fields);
+            return 1;
+        }
+        catch (const std::invalid_argument&)
+        {
+        }
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        std::printf("error: %s\n", e.what());
+        return 1;
+    }
+}
+
 int main(int argc, char** argv)
 {
     if (argc > 1 && std::string(argv[1]) == "--rendezvous")
         return rendezvous_mode();
+    if (argc > 2 && std::string(argv[1]) == "--vtu")
+        return vtu_mode(argv[2]);
     const std::string dir = argc > 1 ? argv[1] : ".";
 
     // clean_double: src/WaveEquationBase.cpp:433-452 and scripts/dissipation_dispersion_sweep.py:333-357

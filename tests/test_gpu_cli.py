@@ -121,3 +121,40 @@ def test_cli_two_ranks_write_the_one_rank_artefacts(exe, scheme, name, over, tmp
         assert a[0] == b[0] and len(a) == len(b)
         for ra, rb in zip(a[1:], b[1:]):
             assert np.allclose([float(x) for x in ra], [float(x) for x in rb], rtol=rtol.get(fname, 0.0), atol=1e-14)
+
+
+def test_cli_save_solution_writes_vtu(tmp_path):
+    """"Save Solution": true (the reference's default): solution_NNNN.0.vtu + .pvtu at step 0 and after
+    every step with u, v, u_exact and partitioning as point data (src/WaveEquationBase.cpp:330-365)."""
+    from wavegpu import cell_dofs
+    from wavegpu.vtu import read_vtu
+
+    (tmp_path / "build").mkdir()
+    (tmp_path / "parameters").mkdir()
+    p = problem("standing-mode-wsol", Nel="6, 4", R="2", Dt="0.05", T="0.15", Save_Solution=True, Log_Every=1)
+    write_json(tmp_path / "parameters" / "vtu.json", p)
+    r = subprocess.run([str(BIN / "main-newmark"), "../parameters/vtu.json"], cwd=tmp_path / "build",
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = O.run(p, "newmark", log_every=1)
+    steps = out["steps"]
+    run_dir = next(d for d in (tmp_path / "results" / "newmark-vtu").iterdir() if d.is_dir())
+    assert sorted(f.name for f in run_dir.glob("solution_*")) == sorted(
+        [f"solution_{k:04d}.0.vtu" for k in range(steps + 1)] + [f"solution_{k:04d}.pvtu" for k in range(steps + 1)])
+    pts, conn, offs, types, data = read_vtu(run_dir / f"solution_{steps:04d}.0.vtu")
+    ncells = 2 * 6 * 4
+    assert len(pts) == 3 * ncells and np.all(types == 5) and offs[-1] == 3 * ncells
+    assert set(data) == {"u", "v", "u_exact", "partitioning"} and not data["partitioning"].any()
+    corner = cell_dofs(6, 4, 2)[:, :3].ravel()
+    o = out["oracle"]
+    u, v = o.vector(O.Oracle.U), o.vector(O.Oracle.V)
+    assert np.abs(data["u"] - u[corner]).max() <= 1e-10 * np.abs(u).max()
+    assert np.abs(data["v"] - v[corner]).max() <= 1e-10 * np.abs(v).max()
+    sx, sy = o.support_points()
+    assert np.abs(pts[:, 0] - sx[corner]).max() < 1e-6 and np.abs(pts[:, 1] - sy[corner]).max() < 1e-6
+    t_end = out["time"]
+    exact = np.cos(np.sqrt(2.0) * np.pi * t_end) * np.sin(np.pi * sx[corner]) * np.sin(np.pi * sy[corner])
+    assert np.abs(data["u_exact"] - exact).max() < 1e-12
+    # step 0 holds the initial condition
+    _, _, _, _, d0 = read_vtu(run_dir / "solution_0000.0.vtu")
+    assert np.abs(d0["u"] - np.sin(np.pi * sx[corner]) * np.sin(np.pi * sy[corner])).max() < 1e-12

@@ -13,6 +13,7 @@ import pytest
 from oracle import oracle as O
 from wavegpu import api, cell_dofs, partition_plan, problem
 from wavegpu.problems import NAMES, write_json
+from wavegpu.vtu import read_vtu
 
 ROOT = Path(__file__).resolve().parent.parent
 BIN = ROOT / "nmpde-wave-equation_b200" / "bin"
@@ -308,3 +309,22 @@ def test_hillion_rule_is_the_collapsed_gauss_product():
               ((1 - e[0]) * (1 + 1 / s3) / 2, e[0], ww[0]), ((1 - e[1]) * (1 + 1 / s3) / 2, e[1], ww[1])]
     got = np.stack([xi, eta, w], axis=1)
     assert np.abs(got - np.array(expect)).max() < 2e-16
+
+
+def test_vtu_writer_round_trip(tmp_path):
+    """solution_NNNN.0.vtu / solution_NNNN.pvtu as DataOut::write_vtu_with_pvtu_record names them
+    (src/WaveEquationBase.cpp:363-364): unshared corner points, triangles, point data."""
+    import xml.etree.ElementTree as ET
+
+    r = subprocess.run([str(BIN / "host_selftest"), "--vtu", str(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout
+    assert r.stdout.split() == ["solution_0007.0.vtu", "solution_12345.pvtu"]
+    pts, conn, offs, types, data = read_vtu(tmp_path / "solution_0007.0.vtu")
+    assert pts.tolist() == [[0, 0, 0], [1, 0, 0], [0, 2, 0], [1, 2, 0], [0, 2, 0], [1, 0, 0]]
+    assert conn.tolist() == list(range(6)) and offs.tolist() == [3, 6] and types.tolist() == [5, 5]
+    assert data["u"].tolist() == [0.5, 1.5, 2.5, 3.5, 2.5, 1.5] and data["partitioning"].tolist() == [0, 0, 0, 1, 1, 1]
+    rec = ET.parse(tmp_path / "solution_0007.pvtu").getroot()
+    assert rec.attrib["type"] == "PUnstructuredGrid"
+    assert [p.attrib["Source"] for p in rec.findall("PUnstructuredGrid/Piece")] == ["solution_0007.0.vtu"]
+    assert [a.attrib["Name"] for a in rec.findall("PUnstructuredGrid/PPointData/PDataArray")] == ["u", "partitioning"]
+    assert not (tmp_path / "bad.vtu").exists() or (tmp_path / "bad.vtu").stat().st_size == 0
