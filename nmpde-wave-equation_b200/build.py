@@ -37,6 +37,28 @@ def _run(cmd):
     subprocess.check_call([str(c) for c in cmd])
 
 
+EXECUTABLES = ("main-newmark", "main-theta", "host_selftest", "wave-mpirun")
+
+
+def build_executables(force=False, only_missing=False):
+    """Host executables (same names as the reference's CMake targets, plus the CPU self-test and the
+    launcher).  only_missing: build what is absent and leave existing files alone, whatever their age
+    (a snapshot copied to another machine does not keep modification times)."""
+    BIN.mkdir(exist_ok=True)
+    hdeps = list(HOST.glob("*.hpp")) + list(HOST.glob("*.cpp")) + [HERE.parent / "include" / "wavegpu.h"]
+    for exe in EXECUTABLES:
+        target = BIN / exe
+        if only_missing:
+            if target.exists():
+                continue
+        elif not (force or _newer(target, hdeps + [LIB])):
+            continue
+        # the launcher is a single translation unit; the others share the host classes
+        common = [] if exe == "wave-mpirun" else [HOST / s for s in HOST_SOURCES]
+        _run(["g++", *CXXFLAGS, "-I", HERE.parent / "include", "-o", target, HOST / (exe + ".cpp"),
+              *common, "-L", LIB.parent, "-lwavegpu", "-Wl,-rpath,$ORIGIN/../lib"])
+
+
 def build(force=False, verbose=False):
     OBJ.mkdir(exist_ok=True)
     LIB.parent.mkdir(exist_ok=True)
@@ -58,17 +80,7 @@ def build(force=False, verbose=False):
         list(ex.map(_run, jobs))
     if force or jobs or not LIB.exists():
         _run([NVCC, "-shared", *ARCH, "-o", LIB, *objs, "-ldl"])
-    # host executables (same names as the reference's CMake targets)
-    if HOST.exists() and all((HOST / s).exists() for s in HOST_SOURCES):  # + host_selftest (CPU-only checks)
-        BIN.mkdir(exist_ok=True)
-        hdeps = list(HOST.glob("*.hpp")) + list(HOST.glob("*.cpp")) + [HERE.parent / "include" / "wavegpu.h"]
-        for exe in ("main-newmark", "main-theta", "host_selftest", "wave-mpirun"):
-            target = BIN / exe
-            # the launcher is a single translation unit; the others share the host classes
-            common = [] if exe == "wave-mpirun" else [HOST / s for s in HOST_SOURCES]
-            if force or _newer(target, hdeps + [LIB]):
-                _run(["g++", *CXXFLAGS, "-I", HERE.parent / "include", "-o", target, HOST / (exe + ".cpp"),
-                      *common, "-L", LIB.parent, "-lwavegpu", "-Wl,-rpath,$ORIGIN/../lib"])
+    build_executables(force=force, only_missing=False)
     return LIB
 
 

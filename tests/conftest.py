@@ -26,3 +26,20 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def host_executables():
+    """bin/main-newmark, main-theta, host_selftest, wave-mpirun are build products (git-ignored): make
+    sure they exist, building only what is missing (g++ against the in-tree library)."""
+    import importlib.util
+
+    pkg = ROOT / "nmpde-wave-equation_b200"
+    spec = importlib.util.spec_from_file_location("wave_build", pkg / "build.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    if any(not (mod.BIN / exe).exists() for exe in mod.EXECUTABLES):
+        from wavegpu import api
+
+        api.lib()  # builds the library first when it is missing
+        mod.build_executables(only_missing=True)

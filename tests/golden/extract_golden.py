@@ -1,14 +1,15 @@
 """Extract the known-answer rows this repo tests against from the reference's own shipped
 result tables (run once in the build container; /root/reference does not exist on the GPU box).
 
-    python tests/golden/extract_golden.py
+    python tests/golden/extract_golden.py [--all]
 
 Sources (reference artefacts, read-only):
   analysis/data/convergence-results.csv   final relative L2/H1 errors, standing mode, T=1
       recipe: scripts/convergence_sweep.py:165-179 (standing-mode-wsol.json + overrides)
   analysis/data/dissdisp-results.csv      energy_ratio etc., Nel=60, r=1, T=5, Log Every=1
       recipe: scripts/dissipation_dispersion_sweep.py:179-198
-Outputs: tests/golden/convergence_rows.json, tests/golden/dissdisp_rows.json
+Outputs: tests/golden/convergence_rows.json, tests/golden/dissdisp_rows.json (the rows the test suite
+runs) and, with --all, convergence_rows_all.json / dissdisp_rows_all.json (every row, for the offline sweeps)
 """
 import csv
 import json
@@ -54,5 +55,34 @@ def main():
     print(len(rows), "convergence rows,", len(drows), "dissdisp rows")
 
 
+def main_all():
+    """Every row of both tables, unfiltered (tools/golden_sweep_oracle.py, tools/golden_sweep_gpu.py --all)."""
+    rows = []
+    with open(REF / "convergence-results.csv") as fh:
+        for lineno, row in enumerate(csv.DictReader(fh), start=2):
+            method = "theta" if row["method"].startswith("theta") else "newmark"
+            rows.append({
+                "line": lineno, "scheme": method, "Nel": int(row["N_el_x"]), "R": int(row["r"]), "Dt": row["dt"],
+                "T": row["T"],
+                "Theta": None if row["theta"] == "N/A" else float(row["theta"]),
+                "Beta": None if row["beta"] == "N/A" else float(row["beta"]),
+                "Gamma": None if row["gamma"] == "N/A" else float(row["gamma"]),
+                "rel_L2": float(row["rel_L2_error_final"]), "rel_H1": float(row["rel_H1_error_final"])})
+    (OUT / "convergence_rows_all.json").write_text(json.dumps(rows, indent=0))
+    drows = []
+    with open(REF / "dissdisp-results.csv") as fh:
+        for lineno, row in enumerate(csv.DictReader(fh), start=2):
+            drows.append({"line": lineno, "scheme": row["scheme"], "Nel": int(row["Nel"]), "R": int(row["R"]),
+                          "Dt": row["dt"], "T": row["T"], "energy_ratio": float(row["energy_ratio"]),
+                          "max_rel_L2": float(row["max_rel_L2"]), "final_rel_L2": float(row["final_rel_L2"]),
+                          "final_rel_H1": float(row["final_rel_H1"])})
+    (OUT / "dissdisp_rows_all.json").write_text(json.dumps(drows, indent=0))
+    print(len(rows), "convergence rows,", len(drows), "dissdisp rows (all)")
+
+
 if __name__ == "__main__":
+    import sys
+
     main()
+    if "--all" in sys.argv:
+        main_all()
