@@ -203,6 +203,9 @@ int wave_timers(wave_ctx *ctx, double out_ms[6], int reset);
    read back the accumulated count and device milliseconds (roofline.achieved of bench.py is
    algorithmic bytes / (ms / launches) taken live inside the timed steps). */
 int wave_spmv_timing(wave_ctx *ctx, int on, double *launches, double *ms_total);
+/* 1 when this context runs its Jacobi-PCG solves as one cooperative kernel (experimental, selected
+   with WAVE_CG_FUSED=1 in the environment of wave_setup when the problem fits on chip), else 0. */
+int wave_cg_fused_active(const wave_ctx *ctx);
 /* Device-time and iteration statistics of the CG solves since the last reset:
    out = {solves, iterations, spmv_launches, ms_total}. */
 int wave_cg_stats(wave_ctx *ctx, double out[4], int reset);

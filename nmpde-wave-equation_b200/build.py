@@ -21,7 +21,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVFLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", *ARCH]
 CXXFLAGS = ["-std=c++17", "-O2", "-fPIC", "-Wall"]
 
-LIB_SOURCES = ["kernels.cu", "ctx.cu", "expr.cpp", "quadrature.cpp"]
+LIB_SOURCES = ["kernels.cu", "ctx.cu", "cg_fused.cu", "expr.cpp", "quadrature.cpp"]
 HOST_SOURCES = ["ParameterReader.cpp", "WaveEquationBase.cpp", "WaveNewmark.cpp", "WaveTheta.cpp", "cli.cpp",
                 "launch_env.cpp", "vtu_writer.cpp"]
 

@@ -1,0 +1,284 @@
+// cg_fused.cu -- see cg_fused.cuh.  Opt-in (WAVE_CG_FUSED=1); not yet run on a device.
+#include "cg_fused.cuh"
+
+#include <cooperative_groups.h>
+
+#include <climits>
+
+namespace cg = cooperative_groups;
+
+namespace wv {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+static_assert(kFusedThreads == kWindow, "thread t of a block holds slot t of each of its windows");
+
+// Totals of NV per-thread values, identical in every thread of every block: block tree, one partial
+// per block, grid barrier, then every block adds the partials in the same fixed order.
+// `buf` holds gridDim.x * NV doubles and must not be the buffer of the previous call.
+template <int NV>
+__device__ __forceinline__ void grid_allsum(cg::grid_group &grid, double (&v)[NV], double *buf, double *s_red,
+                                            double *s_bc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(kFull, v[k], off);
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) s_red[warp * NV + k] = v[k];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double x = s_red[lane * NV + k];  // kFusedThreads / 32 == 32 warps
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(kFull, x, off);
+            if (lane == 0) buf[(size_t)blockIdx.x * NV + k] = x;
+        }
+    }
+    grid.sync();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double s = 0.0;
+            for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(&buf[(size_t)b * NV + k]);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(kFull, s, off);
+            if (lane == 0) s_bc[k] = s;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = s_bc[k];
+}
+
+// one row of A times the staged part of d: ascending columns, separate multiply and add (the serial
+// CSR arithmetic of k_spmv).  Padding entries (value 0) may carry a column outside the staged range:
+// the index is clamped into it.
+template <int CH>
+__device__ __forceinline__ double row_times_staged(const Sell &A, const double *__restrict__ val, uint32_t base,
+                                                   int len, const double *sd, int c0, unsigned cn) {
+    double s = 0.0;
+    for (int k0 = 0; k0 < len; k0 += CH) {
+        int c[CH];
+        double v[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            const int kk = min(k0 + k, len - 1);
+            const uint32_t q = base + (uint32_t)kk * kSlice;
+            c[k] = A.col[q];
+            v[k] = val[q];
+        }
+#pragma unroll
+        for (int k = 0; k < CH; ++k)
+            if (k0 + k < len) {  // warp-uniform
+                const unsigned idx = min((unsigned)(c[k] - c0), cn - 1u);
+                s = __dadd_rn(s, __dmul_rn(v[k], sd[idx]));
+            }
+    }
+    return s;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(kFusedThreads, 1) k_cg_fused(CgFusedArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double smem[];
+    __shared__ double s_red[2 * 32];
+    __shared__ double s_bc[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *sx = smem;                                         // x of my rows   [wpb][1024]
+    double *sg = smem + (size_t)a.wpb * kFusedThreads;         // g of my rows   [wpb][1024]
+    double *sd = smem + 2 * (size_t)a.wpb * kFusedThreads;     // d of the block's column range
+    const int c0 = a.blk_c0[blockIdx.x];
+    const unsigned cn = (unsigned)a.blk_cn[blockIdx.x];
+    const int diag0 = a.own_off - c0;                          // staged index of row r's own column = diag0 + r
+
+    // scalars of the recurrences: carried redundantly, and identically, by every thread of the grid
+    double gh_old = a.S->gh_old, gh_new = a.S->gh_new, gg = a.S->gg, res = a.S->res, dAd = 0.0;
+    const double reduced_tol = a.S->reduced_tol, tol = a.S->tol;
+    const int maxit = a.S->maxit;
+    int it = a.S->it, status = a.S->status;
+    if (status != 0) return;  // the start residual already met the criterion (same answer in every block)
+
+    int rk[kFusedMaxWin];
+    double hk[kFusedMaxWin];
+#pragma unroll
+    for (int k = 0; k < kFusedMaxWin; ++k) {
+        rk[k] = -1;
+        hk[k] = 0.0;
+        const int win = blockIdx.x * a.wpb + k;
+        if (k < a.wpb && win < a.nwin) {
+            const int r = a.A.row_of[(size_t)win * kWindow + tid];
+            rk[k] = r;
+            if (r >= 0) {
+                sx[k * kFusedThreads + tid] = a.x_own[r];
+                sg[k * kFusedThreads + tid] = a.g[r];
+            }
+        }
+    }
+
+    const size_t pstride = (size_t)gridDim.x * 2;
+    for (;;) {
+        // the block's part of d (written by all blocks in phase 3 of the previous iteration, or by the
+        // start kernel): L2 loads, this SM's L1 may hold last iteration's lines
+        for (unsigned i = tid; i < cn; i += kFusedThreads) sd[i] = __ldcg(&a.d[c0 + i]);
+        __syncthreads();
+
+        // phase 1: h = A d, dAd = d . h
+        double acc1[1] = {0.0};
+#pragma unroll
+        for (int k = 0; k < kFusedMaxWin; ++k) {
+            const int win = blockIdx.x * a.wpb + k;
+            if (k < a.wpb && win < a.nwin) {
+                const int slice = win * (kWindow / kSlice) + warp;
+                const uint32_t b0 = a.A.slice_ptr[slice];
+                const int len = (int)((a.A.slice_ptr[slice + 1] - b0) >> 5);
+                const double s = row_times_staged<CH>(a.A, a.val, b0 + lane, len, sd, c0, cn);
+                hk[k] = s;
+                if (rk[k] >= 0) acc1[0] += s * sd[diag0 + rk[k]];
+            }
+        }
+        grid_allsum<1>(grid, acc1, a.partials, s_red, s_bc);
+        dAd = acc1[0];
+        const double alpha = gh_old / dAd;
+
+        // phase 2: g += alpha h ; gg = g . g ; h = D^-1 g ; gh' = g . h
+        double acc2[2] = {0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < kFusedMaxWin; ++k)
+            if (rk[k] >= 0) {
+                const double gi = sg[k * kFusedThreads + tid] + alpha * hk[k];
+                sg[k * kFusedThreads + tid] = gi;
+                acc2[0] += gi * gi;
+                const double hi = a.dinv[rk[k]] * gi;
+                hk[k] = hi;
+                acc2[1] += gi * hi;
+            }
+        grid_allsum<2>(grid, acc2, a.partials + pstride, s_red, s_bc);
+        gg = acc2[0];
+        gh_new = acc2[1];
+
+        // iteration_status(it, res) of ReductionControl(maxit, tol, reduce), then beta
+        res = sqrt(fabs(gg));
+        ++it;
+        if (res <= reduced_tol || res <= tol) status = 1;
+        else if (it >= maxit || isnan(res)) status = 2;
+        const double beta = gh_new / gh_old;
+
+        // phase 3: x += alpha d ; d = beta d - h (published for the next SpMV of every block)
+#pragma unroll
+        for (int k = 0; k < kFusedMaxWin; ++k)
+            if (rk[k] >= 0) {
+                const double dold = sd[diag0 + rk[k]];
+                sx[k * kFusedThreads + tid] += alpha * dold;
+                if (status == 0) a.d[a.own_off + rk[k]] = beta * dold - hk[k];
+            }
+        gh_old = gh_new;
+        if (status != 0) break;  // same decision in every thread of the grid
+        grid.sync();
+    }
+
+#pragma unroll
+    for (int k = 0; k < kFusedMaxWin; ++k)
+        if (rk[k] >= 0) a.x_own[rk[k]] = sx[k * kFusedThreads + tid];
+    if (blockIdx.x == 0 && tid == 0) {
+        a.S->it = it;
+        a.S->res = res;
+        a.S->status = status;
+        a.S->gg = gg;
+        a.S->gh_new = gh_new;
+        a.S->gh_old = gh_old;
+        a.S->dAd = dAd;
+    }
+}
+
+__global__ void __launch_bounds__(kWindow) k_window_col_range(Sell A, int nwin, int32_t *cmin, int32_t *cmax) {
+    __shared__ int s_lo[kWindow / 32], s_hi[kWindow / 32];
+    const int win = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int lo = INT_MAX, hi = -1;
+    if (win < nwin) {
+        const size_t slot = (size_t)win * kWindow + tid;
+        const int r = A.row_of[slot];
+        if (r >= 0) {
+            const uint32_t base = A.slice_ptr[slot >> 5] + (uint32_t)lane;
+            const uint32_t len = A.rowptr[r + 1] - A.rowptr[r];
+            for (uint32_t k = 0; k < len; ++k) {
+                const int c = A.col[base + kSlice * k];
+                lo = min(lo, c);
+                hi = max(hi, c);
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = min(lo, __shfl_xor_sync(kFull, lo, off));
+        hi = max(hi, __shfl_xor_sync(kFull, hi, off));
+    }
+    if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
+    __syncthreads();
+    if (warp == 0) {
+        lo = s_lo[lane];
+        hi = s_hi[lane];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            lo = min(lo, __shfl_xor_sync(kFull, lo, off));
+            hi = max(hi, __shfl_xor_sync(kFull, hi, off));
+        }
+        if (lane == 0 && win < nwin) { cmin[win] = lo; cmax[win] = hi; }
+    }
+}
+
+void note(const Launcher &l, cudaError_t e) {
+    if (l.count) ++*l.count;
+    if (l.error && *l.error == cudaSuccess) *l.error = e != cudaSuccess ? e : cudaPeekAtLastError();
+}
+
+using FusedKernel = void (*)(CgFusedArgs);
+FusedKernel kernel_for(const Sell &A) { return A.chunk <= 7 ? k_cg_fused<7> : k_cg_fused<10>; }
+
+}  // namespace
+
+void launch_window_col_range(const Launcher &l, const Sell &A, int nwin, int32_t *cmin, int32_t *cmax) {
+    k_window_col_range<<<nwin, kWindow, 0, l.stream>>>(A, nwin, cmin, cmax);
+    note(l, cudaSuccess);
+}
+
+size_t cg_fused_smem_bytes(int wpb, int stage_cap) {
+    return sizeof(double) * (2 * (size_t)wpb * kFusedThreads + (size_t)stage_cap);
+}
+
+bool cg_fused_supported(int grid, size_t smem_bytes) {
+    int dev = 0, coop = 0, sms = 0, optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (!coop || smem_bytes + 1024 > (size_t)optin) return false;  // 1 KiB left for the static arrays
+    for (FusedKernel k : {FusedKernel(k_cg_fused<7>), FusedKernel(k_cg_fused<10>)}) {
+        // always the device maximum: contexts with different plans share the kernel's attribute
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kFusedThreads, smem_bytes) != cudaSuccess ||
+            (int64_t)occ * sms < grid) {
+            cudaGetLastError();
+            return false;
+        }
+    }
+    return true;
+}
+
+cudaError_t launch_cg_fused(const Launcher &l, int grid, size_t smem_bytes, const CgFusedArgs &a) {
+    CgFusedArgs args = a;
+    void *params[] = {&args};
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)kernel_for(a.A), dim3((unsigned)grid),
+                                                      dim3(kFusedThreads), params, smem_bytes, l.stream);
+    note(l, e);
+    return e;
+}
+
+}  // namespace wv

@@ -17,6 +17,7 @@
 
 #include "../../include/wavegpu.h"
 #include "expr.hpp"
+#include "cg_fused.cuh"
 #include "kernels.cuh"
 
 namespace wv {
@@ -26,6 +27,8 @@ Quadrature make_quadrature(int n1d);
 using namespace wv;
 
 namespace {
+
+constexpr int kSMsFallback = 148;  // B200
 
 thread_local std::string g_create_error;
 
@@ -151,6 +154,15 @@ struct wave_ctx {
     // multigrid preconditioner
     Mg *mg = nullptr;
     double *mg_buf[3] = {nullptr, nullptr, nullptr};  // level-0 work vectors
+
+    // K6f, opt-in (WAVE_CG_FUSED=1): the whole Jacobi-PCG solve as one cooperative kernel (cg_fused.cuh)
+    struct FusedPlan {
+        bool ok = false;
+        int grid = 0, wpb = 0, stage_cap = 0;
+        size_t smem = 0;
+        int32_t *blk_c0 = nullptr, *blk_cn = nullptr;
+        double *partials = nullptr;
+    } fused;
 
     // NCCL + NVLink peer exchange
     Nccl::comm_t comm = nullptr;
@@ -407,11 +419,31 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
     }
     RET(allreduce(ctx, &ctx->S->gg, 2));
     launch_cg_start(l, ctx->S);
+    const bool fused = ctx->fused.ok && !use_mg;
+    if (fused) {  // K6f: every iteration inside one cooperative kernel; the loop below only reads the outcome
+        CgFusedArgs fa{};
+        fa.A = ctx->A;
+        fa.val = Sval;
+        fa.dinv = dinv;
+        fa.x_own = x + L.own_off;
+        fa.d = ctx->d;
+        fa.own_off = L.own_off;
+        fa.g = ctx->g;
+        fa.S = ctx->S;
+        fa.partials = ctx->fused.partials;
+        fa.nwin = ctx->nslices / (kWindow / kSlice);
+        fa.wpb = ctx->fused.wpb;
+        fa.blk_c0 = ctx->fused.blk_c0;
+        fa.blk_cn = ctx->fused.blk_cn;
+        fa.stage_cap = ctx->fused.stage_cap;
+        CK(launch_cg_fused(l, ctx->fused.grid, ctx->fused.smem, fa));
+    }
     int enq = 0;
     // iteration counts of consecutive time steps are nearly equal (warm start): enqueue as many
     // iterations as the previous solve needed, then poll in pairs
     int chunk = ctx->prev_its[slot] > 0 ? ctx->prev_its[slot] : 4;
     const int maxit = ctx->hS->maxit;
+    if (fused) chunk = 0;
     for (;;) {
         for (int k = 0; k < chunk; ++k) {
             const bool p2p = ctx->pc.enabled != 0;
@@ -458,7 +490,7 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
         CK(cudaMemcpyAsync(ctx->hS, ctx->S, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         RET(launch_check(ctx));
-        if (ctx->hS->status != 0) break;
+        if (ctx->hS->status != 0 || fused) break;
         if (enq > maxit + 8) break;
         chunk = use_mg ? 1 : 2;  // a skipped multigrid iteration still costs ~50 no-op launches
     }
@@ -719,6 +751,60 @@ int dev_alloc(wave_ctx *ctx, T **p, size_t count, bool zero = true) {
     return WAVE_OK;
 }
 
+// K6f plan: block b of the cooperative kernel owns the windows [b wpb, (b+1) wpb) and stages the column
+// range of their entries in shared memory.  Possible when every block's rows (x, g: 16 B per row) and
+// its staged range fit in one SM's shared memory; otherwise the three-kernel iteration stays.
+int fused_plan(wave_ctx *ctx) {
+    auto &f = ctx->fused;
+    f.ok = false;
+    const char *env = std::getenv("WAVE_CG_FUSED");
+    if (!env || std::atoi(env) == 0) return WAVE_OK;
+    if (ctx->cfg.nranks != 1 || ctx->cfg.precond != WAVE_PRECOND_JACOBI) return WAVE_OK;
+    const int nwin = ctx->nslices / (kWindow / kSlice);
+    int sms = kSMsFallback;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int wpb = (nwin + sms - 1) / sms;
+    if (wpb > kFusedMaxWin) return WAVE_OK;
+    const int grid = (nwin + wpb - 1) / wpb;
+    int32_t *cmin = nullptr, *cmax = nullptr;
+    RET(dev_alloc(ctx, &cmin, (size_t)nwin, false));
+    RET(dev_alloc(ctx, &cmax, (size_t)nwin, false));
+    launch_window_col_range(ctx->launcher, ctx->A, nwin, cmin, cmax);
+    std::vector<int32_t> lo(nwin), hi(nwin), c0(grid), cn(grid);
+    CK(cudaMemcpyAsync(lo.data(), cmin, sizeof(int32_t) * nwin, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hi.data(), cmax, sizeof(int32_t) * nwin, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(cmin));
+    CK(cudaFree(cmax));
+    int stage = 1;
+    for (int b = 0; b < grid; ++b) {
+        int32_t l = INT32_MAX, h = -1;
+        for (int w = b * wpb; w < std::min(nwin, (b + 1) * wpb); ++w) {
+            l = std::min(l, lo[w]);
+            h = std::max(h, hi[w]);
+        }
+        if (h < l) { l = ctx->L.own_off; h = ctx->L.own_off; }  // a block of padding only
+        c0[b] = l;
+        cn[b] = h - l + 1;
+        stage = std::max(stage, (int)cn[b]);
+    }
+    const size_t smem = cg_fused_smem_bytes(wpb, stage);
+    if (!cg_fused_supported(grid, smem)) return WAVE_OK;
+    RET(dev_alloc(ctx, &f.blk_c0, (size_t)grid, false));
+    RET(dev_alloc(ctx, &f.blk_cn, (size_t)grid, false));
+    RET(dev_alloc(ctx, &f.partials, (size_t)grid * 4));
+    CK(cudaMemcpyAsync(f.blk_c0, c0.data(), sizeof(int32_t) * grid, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(f.blk_cn, cn.data(), sizeof(int32_t) * grid, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    f.grid = grid;
+    f.wpb = wpb;
+    f.stage_cap = stage;
+    f.smem = smem;
+    f.ok = true;
+    return WAVE_OK;
+}
+
 // Build the multigrid hierarchy for the scheme matrix bc(M + s K): [P2 on the mesh ->] P1 on the mesh ->
 // P1 on Nel/2, Nel/4, ... while the stiffness part still matters (s c^2 / (dx dy) > 1/4) and the mesh
 // halves evenly.  Every coarse level is a child context (pattern, rediscretised M and K, Dirichlet rows,
@@ -966,6 +1052,8 @@ void wave_destroy(wave_ctx *ctx) {
         if (b) cudaFree(b);
     for (int k = 0; k < ctx->n_ipc_opened; ++k) cudaIpcCloseMemHandle(ctx->ipc_opened[k]);
     if (ctx->mailbox) cudaFree(ctx->mailbox);
+    for (void *q : {(void *)ctx->fused.blk_c0, (void *)ctx->fused.blk_cn, (void *)ctx->fused.partials})
+        if (q) cudaFree(q);
     void *ptrs[] = {ctx->dprog, ctx->rowptr, ctx->slice_ptr, ctx->row_of, ctx->slot_of, ctx->col, ctx->c2i, ctx->i2c, ctx->tmp, ctx->M, ctx->K, ctx->S1, ctx->S2, ctx->dinv1, ctx->dinv2,
                     ctx->d0, ctx->u, ctx->v, ctx->a, ctx->unew, ctx->d, ctx->rhs, ctx->fvec, ctx->g, ctx->h,
                     ctx->scratch, ctx->brow, ctx->bx, ctx->by, ctx->partials, ctx->counter, ctx->S, ctx->res,
@@ -1206,6 +1294,7 @@ int wave_setup(wave_ctx *ctx) {
     }
     RET(sync_check(ctx));
     RET(setup_peer_exchange(ctx));
+    RET(fused_plan(ctx));
     ctx->is_setup = true;
     return WAVE_OK;
 }
@@ -1622,6 +1711,8 @@ int wave_cg_stats(wave_ctx *ctx, double out[4], int reset) {
     }
     return WAVE_OK;
 }
+
+int wave_cg_fused_active(const wave_ctx *ctx) { return ctx && ctx->fused.ok ? 1 : 0; }
 
 int wave_cell_dofs(int32_t nx, int32_t ny, int32_t r, int64_t cell, int32_t *out) {
     if (nx < 1 || ny < 1 || (r != 1 && r != 2) || cell < 0 || cell >= 2LL * nx * ny || !out) return WAVE_ERR_ARG;

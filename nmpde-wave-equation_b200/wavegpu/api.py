@@ -96,6 +96,7 @@ def lib():
         L.wave_cell_dofs_storage.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, ip]
         L.wave_quadrature.argtypes = [C.c_int32, dp, dp, dp]
         L.wave_device_count.argtypes = []
+        L.wave_cg_fused_active.argtypes = [vp]
         L.wave_spmv.argtypes = [vp, C.c_int, dp, dp, C.c_size_t]
         L.wave_cg.argtypes = [vp, C.c_int, dp, dp, C.c_size_t, ip]
         L.wave_bench_spmv.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp]
@@ -235,6 +236,9 @@ class WaveSolver:
     def _ck(self, rc):
         if rc:
             raise WaveError(rc, self.L.wave_last_error(self.h).decode())
+
+    def cg_fused_active(self):
+        return bool(self.L.wave_cg_fused_active(self.h))
 
     def close(self):
         if getattr(self, "h", None):

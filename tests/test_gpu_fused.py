@@ -1,0 +1,67 @@
+"""Parity of the experimental fused CG kernel (csrc/cg_fused.cu, WAVE_CG_FUSED=1) against the oracle and
+against the three-kernel iteration.  The kernel was written after round 1's GPU budget was spent and has
+not run on a device yet, so these tests only run on request:
+
+    WAVE_TEST_FUSED=1 timeout 300 python -m pytest tests/test_gpu_fused.py -x -q
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from wavegpu import WaveSolver, api, problem
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.environ.get("WAVE_TEST_FUSED"), reason="experimental: set WAVE_TEST_FUSED=1")]
+
+
+@pytest.fixture
+def fused_env(monkeypatch):
+    monkeypatch.setenv("WAVE_CG_FUSED", "1")
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300)
+
+
+@pytest.mark.parametrize("name,scheme,over", [
+    ("standing-mode-wsol", "newmark", dict(Nel="24", R=1, Dt="0.05")),
+    ("standing-mode-wsol", "theta", dict(Nel="16", R=2, Dt="0.05", Theta="0.5")),
+    ("sine-membrane", "theta", dict(Nel="45, 15")),
+    ("standing-mode-wsol", "newmark", dict(Nel="300, 40", R=1, Dt="0.01")),
+    ("ricker-wavelet", "newmark", dict(Nel="150", R=2)),
+])
+def test_fused_matches_oracle(fused_env, name, scheme, over):
+    p = problem(name, **over)
+    o = O.Oracle.from_params(p)
+    g = WaveSolver(p, scheme)
+    assert g.cg_fused_active()
+    if scheme == "newmark":
+        o.newmark_init(float(p["Dt"]), float(p["Beta"]), float(p["Gamma"]))
+    else:
+        o.theta_init(float(p["Dt"]), float(p["Theta"]))
+    g.init()
+    for _ in range(6):
+        (o.newmark_step if scheme == "newmark" else o.theta_step)()
+        its, _ = g.step()
+        assert its == o.iterations()
+    assert rel(g.vector(api.VEC_U), o.vector(O.Oracle.U)) < 1e-10
+    assert rel(g.vector(api.VEC_V), o.vector(O.Oracle.V)) < 1e-10
+    g.close()
+
+
+def test_fused_matches_three_kernel_path_at_bench_size(monkeypatch):
+    p = problem("standing-mode-wsol", Nel="1024", R=1, Dt="0.01")
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("WAVE_CG_FUSED", mode)
+        g = WaveSolver(p, "newmark")
+        assert g.cg_fused_active() == (mode == "1")
+        g.init()
+        its = [g.step()[0] for _ in range(5)]
+        out[mode] = (its, g.vector(api.VEC_U), g.energy())
+        g.close()
+    assert out["0"][0] == out["1"][0]
+    assert rel(out["1"][1], out["0"][1]) < 1e-10
+    assert abs(out["1"][2] - out["0"][2]) < 1e-10 * abs(out["0"][2])

@@ -1,6 +1,7 @@
 """Run every known-answer row of tests/golden/ through libwavegpu (the reference's own result tables:
 analysis/data/convergence-results.csv and dissdisp-results.csv) and report the worst deviations.
-    python tools/golden_sweep_gpu.py            # on a B200
+    python tools/golden_sweep_gpu.py            # on a B200: the 136 rows of the test suite
+    python tools/golden_sweep_gpu.py --all OUT  # every row of both tables (490 + 47), per-row JSON to OUT
 """
 import json
 import sys
@@ -62,5 +63,44 @@ def main():
                       "worst_energy_ratio_dev": worst_ratio, "seconds": time.time() - t0}, indent=1))
 
 
+def main_all(out_path):
+    """Every row of both tables (the reference's scripts/*_sweep.py regression, from the fixtures):
+    per-row oracle-free comparison with the printed values; long rows take minutes on a B200."""
+    gold = ROOT / "tests" / "golden"
+    rows = []
+    for row in json.loads((gold / "convergence_rows_all.json").read_text()):
+        kw = dict(Nel=row["Nel"], R=row["R"], Dt=row["Dt"], T=row["T"])
+        for k in ("Theta", "Beta", "Gamma"):
+            if row.get(k) is not None:
+                kw[k] = row[k]
+        t0 = time.time()
+        try:
+            e, _, _ = run(problem("standing-mode-wsol", **kw), row["scheme"])
+            got, err = [e[2], e[3]], None
+        except Exception as ex:  # diverged explicit runs end in WAVE_ERR_DIVERGED
+            got, err = None, str(ex)
+        rows.append({"table": "convergence", "line": row["line"], "gold": [row["rel_L2"], row["rel_H1"]], "gpu": got,
+                     "error": err, "seconds": time.time() - t0})
+        Path(out_path).write_text(json.dumps(rows))
+    for row in json.loads((gold / "dissdisp_rows_all.json").read_text()):
+        kind, val = row["scheme"].split("-")
+        extra = {"Theta": val} if kind == "theta" else {"Beta": val, "Gamma": "0.5"}
+        p = problem("standing-mode-wsol", Nel=row["Nel"], R=row["R"], Dt=row["Dt"], T=row["T"], **extra)
+        t0 = time.time()
+        try:
+            e, E, rl2 = run(p, "theta" if kind == "theta" else "newmark", log_every=1)
+            got, err = [E[-1] / E[0], max(rl2), rl2[-1], e[3]], None
+        except Exception as ex:
+            got, err = None, str(ex)
+        rows.append({"table": "dissdisp", "line": row["line"],
+                     "gold": [row["energy_ratio"], row["max_rel_L2"], row["final_rel_L2"], row["final_rel_H1"]],
+                     "gpu": got, "error": err, "seconds": time.time() - t0})
+        Path(out_path).write_text(json.dumps(rows))
+    print(len(rows), "rows ->", out_path)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 2 and sys.argv[1] == "--all":
+        main_all(sys.argv[2])
+    else:
+        main()
