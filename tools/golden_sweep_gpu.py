@@ -18,19 +18,20 @@ TIGHT = dict(reduce=1e-13, tol=1e-30)
 
 def run(p, scheme, log_every=0):
     g = WaveSolver(p, scheme, cg=TIGHT)
-    g.init()
-    t, dt, T, step = 0.0, float(p["Dt"]), float(p["T"]), 0
-    energies, rel_l2 = [], []
-    while t < T:
-        t += dt
-        step += 1
-        g.step()
-        if log_every and step % log_every == 0:
-            energies.append(float("%.6g" % g.energy()))
-            rel_l2.append(g.errors()[2])
-    e = g.errors()
-    g.close()
-    return e, energies, rel_l2
+    try:
+        g.init()
+        t, dt, T, step = 0.0, float(p["Dt"]), float(p["T"]), 0
+        energies, rel_l2 = [], []
+        while t < T:
+            t += dt
+            step += 1
+            g.step()
+            if log_every and step % log_every == 0:
+                energies.append(float("%.6g" % g.energy()))
+                rel_l2.append(g.errors()[2])
+        return g.errors(), energies, rel_l2
+    finally:
+        g.close()
 
 
 def main():
