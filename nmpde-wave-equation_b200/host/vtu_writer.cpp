@@ -104,7 +104,7 @@ void write_vtu_piece(const std::string& path, const std::vector<float>& xyz, con
     data_array(os, "Int32", "connectivity", 1, connectivity);
     data_array(os, "Int32", "offsets", 1, offsets);
     data_array(os, "UInt8", "types", 1, types);
-    os << "      </Cells>\n      <PointData Scalars=\"scalars\">\n";
+    os << "      </Cells>\n      <PointData" << (fields.empty() ? "" : " Scalars=\"" + fields.front().name + "\"") << ">\n";
     for (const VtuField& f : fields)
         data_array(os, "Float64", f.name, 1, f.values);
     os << "      </PointData>\n    </Piece>\n  </UnstructuredGrid>\n</VTKFile>\n";
@@ -121,7 +121,7 @@ void write_pvtu_record(const std::string& path, const std::vector<std::string>& 
     os << "<?xml version=\"1.0\"?>\n"
        << "<VTKFile type=\"PUnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n"
        << "  <PUnstructuredGrid GhostLevel=\"0\">\n"
-       << "    <PPointData Scalars=\"scalars\">\n";
+       << "    <PPointData" << (field_names.empty() ? "" : " Scalars=\"" + field_names.front() + "\"") << ">\n";
     for (const std::string& name : field_names)
         os << "      <PDataArray type=\"Float64\" Name=\"" << name << "\" format=\"binary\"/>\n";
     os << "    </PPointData>\n"
