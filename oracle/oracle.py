@@ -40,6 +40,9 @@ def lib():
     global _lib
     if _lib is None:
         build()
+        # idle OpenMP threads sleep instead of spinning: thousands of tiny parallel regions (small test
+        # meshes) otherwise crawl when the cores are shared with other processes
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")
         L = C.CDLL(str(_LIB_PATH))
         dp = C.POINTER(C.c_double)
         ip = C.POINTER(C.c_int)

@@ -31,6 +31,9 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+/* loops shorter than this run on the calling thread: small test meshes would spend their time in
+   the fork/join of thousands of tiny parallel regions */
+#define OMP_MIN_WORK 50000
 
 /* ------------------------------------------------------------------------- */
 /* Expression evaluator: the muParser subset deal.II's FunctionParser accepts   */
@@ -884,7 +887,7 @@ int oracle_assemble(oracle_problem *p) {
 
 /* Trilinos vmult (Epetra_CrsMatrix::Multiply) */
 static void spmv(const oracle_problem *p, const double *val, const double *x, double *y) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if ((p->n) > OMP_MIN_WORK)
     for (int64_t i = 0; i < p->n; ++i) {
         double s = 0.0;
         for (int64_t k = p->rowptr[i]; k < p->rowptr[i + 1]; ++k) s += val[k] * x[p->col[k]];
@@ -893,16 +896,16 @@ static void spmv(const oracle_problem *p, const double *val, const double *x, do
 }
 static double dot(const oracle_problem *p, const double *x, const double *y) {
     double s = 0.0;
-#pragma omp parallel for reduction(+ : s) schedule(static)
+#pragma omp parallel for reduction(+ : s) schedule(static) if ((p->n) > OMP_MIN_WORK)
     for (int64_t i = 0; i < p->n; ++i) s += x[i] * y[i];
     return s;
 }
 static void axpy(const oracle_problem *p, double a, const double *x, double *y) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if ((p->n) > OMP_MIN_WORK)
     for (int64_t i = 0; i < p->n; ++i) y[i] += a * x[i];
 }
 static void vcopy(const oracle_problem *p, const double *x, double *y) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if ((p->n) > OMP_MIN_WORK)
     for (int64_t i = 0; i < p->n; ++i) y[i] = x[i];
 }
 
@@ -911,7 +914,7 @@ static void vcopy(const oracle_problem *p, const double *x, double *y) {
 static void add_forcing(oracle_problem *p, double *out, double scale, double t_np1, double t_n,
                         double w_np1, double w_n, int two_levels) {
     const int dpc = p->dpc, nq = p->q.nq;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if ((p->ncells) > OMP_MIN_WORK)
     for (int64_t c = 0; c < p->ncells; ++c) {
         double X0, Y0, J[4], det;
         cell_geom(p, c, &X0, &Y0, J, &det);
@@ -1143,7 +1146,7 @@ static int cg_solve_ex(oracle_problem *p, const double *Aval, double *x, const d
     double *g = p->cg_g, *d = p->cg_d, *h = p->cg_h;
     const int64_t n = p->n;
     use_mg = use_mg && p->precond == 2 && p->mg != NULL;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if ((n) > OMP_MIN_WORK)
     for (int64_t i = 0; i < n; ++i) {
         double dg = 1.0;
         for (int64_t k = p->rowptr[i]; k < p->rowptr[i + 1]; ++k)
@@ -1160,7 +1163,7 @@ static int cg_solve_ex(oracle_problem *p, const double *Aval, double *x, const d
         mg_apply(p, g, h);
         for (int64_t i = 0; i < n; ++i) d[i] = -h[i];
     } else {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if ((n) > OMP_MIN_WORK)
         for (int64_t i = 0; i < n; ++i) { h[i] = p->dinv[i] * g[i]; d[i] = -h[i]; }
     }
     double gh = dot(p, g, h);
@@ -1176,13 +1179,13 @@ static int cg_solve_ex(oracle_problem *p, const double *Aval, double *x, const d
         if (use_mg)
             mg_apply(p, g, h);
         else {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if ((n) > OMP_MIN_WORK)
             for (int64_t i = 0; i < n; ++i) h[i] = p->dinv[i] * g[i];
         }
         double beta = gh;
         gh = dot(p, g, h);
         beta = gh / beta;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if ((n) > OMP_MIN_WORK)
         for (int64_t i = 0; i < n; ++i) d[i] = beta * d[i] - h[i];
     }
 }
@@ -1373,7 +1376,7 @@ int oracle_errors(oracle_problem *p, double t, double *out) {
     const int dpc = p->dpc, nq = p->qerr.nq;
     const double hfd = 1e-8;
     double e_l2 = 0, e_h1 = 0, n_l2 = 0, n_h1 = 0;
-#pragma omp parallel for reduction(+ : e_l2, e_h1, n_l2, n_h1) schedule(static)
+#pragma omp parallel for reduction(+ : e_l2, e_h1, n_l2, n_h1) schedule(static) if ((p->ncells) > OMP_MIN_WORK)
     for (int64_t c = 0; c < p->ncells; ++c) {
         double X0, Y0, J[4], det;
         cell_geom(p, c, &X0, &Y0, J, &det);
