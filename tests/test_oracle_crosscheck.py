@@ -150,6 +150,18 @@ class Space:
         idx = range(self.n) if idx is None else idx
         return np.array([self.fn[name](self.pts[i, 0], self.pts[i, 1], t) for i in idx])
 
+    def value_at_centre(self, u):
+        """u_h at the centre of the box: first cell that contains the point."""
+        xs, ys = [q[0] for q in self.vxy], [q[1] for q in self.vxy]
+        px, py = 0.5 * (min(xs) + max(xs)), 0.5 * (min(ys) + max(ys))
+        for c, d in zip(self.cells, self.cell_dofs):
+            v0, J, _, Jinv = self._geometry(c)
+            xi, eta = Jinv @ (np.array([px, py]) - v0)
+            if xi >= -1e-12 and eta >= -1e-12 and xi + eta <= 1 + 1e-12:
+                phi, _ = shape(self.r, xi, eta)
+                return float(phi @ u[d])
+        raise AssertionError("centre not found")
+
     def solve_with_bc(self, A, rhs, values):
         """apply_boundary_values + exact solve: boundary rows become d0 e_i."""
         A = A.tolil(copy=True)
@@ -256,6 +268,11 @@ def test_independent_restatement_agrees_with_the_oracle(name, scheme, over):
     assert rel(v, ov) < 2e-9, rel(v, ov)
     if a is not None:
         assert rel(a, oa) < 2e-9, rel(a, oa)
+    # compute_and_log_energy and log_point_probe on the independent state (src/WaveEquationBase.cpp:148-206)
+    S = Space(p)
+    E = 0.5 * (v @ (S.M @ v) + u @ (S.K @ u))
+    assert abs(E - o.energy()) <= 1e-8 * max(abs(E), 1e-300)
+    assert abs(S.value_at_centre(u) - o.probe()) <= 2e-9 * max(np.abs(ou).max(), 1e-300)
 
 
 def test_independent_numbering_pattern_and_matrices():
