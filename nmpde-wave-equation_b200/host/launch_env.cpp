@@ -66,18 +66,25 @@ std::string default_rendezvous_path()
 
 LaunchEnvironment detect_launch_environment()
 {
-    struct Family { const char* label; const char* rank; const char* size; const char* local; };
+    // Variables only a process launcher sets are trusted as they are.  SLURM_* also exist in a plain
+    // batch shell (a directly started binary is then one rank, as it is for the reference without srun)
+    // and RANK / WORLD_SIZE are common pod-level settings, so those two families must be asked for:
+    // WAVE_LAUNCHER=slurm or WAVE_LAUNCHER=torchrun.
+    struct Family { const char* label; const char* rank; const char* size; const char* local; const char* opt_in; };
     static const Family families[] = {
-        { "WAVE_*", "WAVE_RANK", "WAVE_NRANKS", "WAVE_LOCAL_RANK" },
-        { "OMPI_COMM_WORLD_*", "OMPI_COMM_WORLD_RANK", "OMPI_COMM_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_RANK" },
-        { "PMI_*", "PMI_RANK", "PMI_SIZE", "MPI_LOCALRANKID" },
-        { "SLURM_*", "SLURM_PROCID", "SLURM_NTASKS", "SLURM_LOCALID" },
-        { "RANK/WORLD_SIZE", "RANK", "WORLD_SIZE", "LOCAL_RANK" },
+        { "WAVE_*", "WAVE_RANK", "WAVE_NRANKS", "WAVE_LOCAL_RANK", nullptr },
+        { "OMPI_COMM_WORLD_*", "OMPI_COMM_WORLD_RANK", "OMPI_COMM_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_RANK", nullptr },
+        { "PMI_*", "PMI_RANK", "PMI_SIZE", "MPI_LOCALRANKID", nullptr },
+        { "SLURM_*", "SLURM_PROCID", "SLURM_NTASKS", "SLURM_LOCALID", "slurm" },
+        { "RANK/WORLD_SIZE", "RANK", "WORLD_SIZE", "LOCAL_RANK", "torchrun" },
     };
+    const char* chosen = std::getenv("WAVE_LAUNCHER");
     LaunchEnvironment env;
     for (const Family& f : families)
     {
         unsigned int rank = 0, size = 1, local = 0;
+        if (f.opt_in && !(chosen && std::string(chosen) == f.opt_in))
+            continue;
         if (!read_unsigned(f.size, size) || !read_unsigned(f.rank, rank))
             continue;
         if (size == 0 || rank >= size)

@@ -20,8 +20,9 @@ struct LaunchEnvironment
     std::string source;     // which family of variables was found ("WAVE_*", "OMPI_*", ...)
 };
 
-/// Read WAVE_RANK/WAVE_NRANKS/WAVE_LOCAL_RANK, else OMPI_COMM_WORLD_*, PMI_*, SLURM_*, or torchrun's
-/// RANK/WORLD_SIZE/LOCAL_RANK; no variables = a single rank.  Throws std::invalid_argument on
+/// Read WAVE_RANK/WAVE_NRANKS/WAVE_LOCAL_RANK, else OMPI_COMM_WORLD_*, PMI_*; SLURM_PROCID/SLURM_NTASKS
+/// only with WAVE_LAUNCHER=slurm and RANK/WORLD_SIZE/LOCAL_RANK only with WAVE_LAUNCHER=torchrun (both
+/// are also set where nothing was launched in parallel); no variables = a single rank.  Throws std::invalid_argument on
 /// inconsistent values (rank >= size, non-numeric text).
 LaunchEnvironment detect_launch_environment();
 

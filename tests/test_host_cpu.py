@@ -219,6 +219,11 @@ def test_rank_variables_of_other_launchers(tmp_path):
         env = {k: v for k, v in os.environ.items() if not k.startswith(("WAVE_", "OMPI_", "PMI_", "SLURM_"))}
         env.pop("RANK", None), env.pop("WORLD_SIZE", None), env.pop("LOCAL_RANK", None)
         env["WAVE_RENDEZVOUS"] = rdv
+        if fam in ("SLURM_*", "RANK/WORLD_SIZE"):  # not launcher-specific: only on request
+            alone = subprocess.run([exe, "--rendezvous"], env={**env, rk: "1", sz: "2", loc: "1"},
+                                   capture_output=True, text=True, timeout=30)
+            assert alone.returncode == 0 and alone.stdout.startswith("rank 0 of 1 ")
+            env["WAVE_LAUNCHER"] = "slurm" if fam == "SLURM_*" else "torchrun"
         p1 = subprocess.Popen([exe, "--rendezvous"], env={**env, rk: "1", sz: "2", loc: "1"},
                               stdout=subprocess.PIPE, text=True)
         r0 = subprocess.run([exe, "--rendezvous"], env={**env, rk: "0", sz: "2", loc: "0"}, capture_output=True,
@@ -229,8 +234,8 @@ def test_rank_variables_of_other_launchers(tmp_path):
         assert out1.startswith(f"rank 1 of 2 local 1 via {fam} id ") and out1.split()[-1] == r0.stdout.split()[-1]
         os.remove(rdv)
     env = {k: v for k, v in os.environ.items() if not k.startswith("WAVE_")}
-    r = subprocess.run([exe, "--rendezvous"], env={**env, "RANK": "5", "WORLD_SIZE": "2"}, capture_output=True,
-                       text=True, timeout=30)
+    r = subprocess.run([exe, "--rendezvous"], env={**env, "RANK": "5", "WORLD_SIZE": "2", "WAVE_LAUNCHER": "torchrun"},
+                       capture_output=True, text=True, timeout=30)
     assert r.returncode == 1 and "outside WORLD_SIZE=2" in r.stdout
 
 
