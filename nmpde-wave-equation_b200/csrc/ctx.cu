@@ -1295,6 +1295,29 @@ int wave_setup(wave_ctx *ctx) {
     RET(sync_check(ctx));
     RET(setup_peer_exchange(ctx));
     RET(fused_plan(ctx));
+    // Experiment for problems whose matrix fits in L2 (opt-in, WAVE_L2_PERSIST=<MiB>): mark the values of
+    // the system matrix as persisting in L2 for the kernels of this stream, so the vector traffic of the
+    // CG iteration does not evict them between SpMVs.  Not measured yet.
+    if (const char *mb = std::getenv("WAVE_L2_PERSIST")) {
+        const size_t want = (size_t)std::max(0, std::atoi(mb)) << 20;
+        int dev = 0, max_persist = 0, max_window = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        const size_t carve = std::min(want, (size_t)max_persist);
+        if (carve > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+            cudaStreamAttrValue v{};
+            const size_t bytes = std::min((size_t)ctx->nnz_pad * sizeof(double), (size_t)max_window);
+            v.accessPolicyWindow.base_ptr = ctx->S1;
+            v.accessPolicyWindow.num_bytes = bytes;
+            v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)bytes);
+            v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess)
+                cudaGetLastError();
+        } else
+            cudaGetLastError();
+    }
     ctx->is_setup = true;
     return WAVE_OK;
 }
