@@ -54,6 +54,98 @@ __device__ __forceinline__ void grid_allsum(cg::grid_group &grid, double (&v)[NV
     for (int k = 0; k < NV; ++k) v[k] = s_bc[k];
 }
 
+// ---- several ranks: the two sums of an iteration also run over the NVLink mailboxes ----------------
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+constexpr long long kPeerWait = 6000000000LL;    // ~3 s: a lost peer must not hang the GPU
+constexpr long long kLocalWait = 30000000000LL;  // block 0 always answers within kPeerWait
+
+// Two 8-byte words per double, each carrying 32 payload bits and the low 32 bits of the sequence number
+// (the self-validating words of kernels.cu's p2p_allreduce).
+__device__ __forceinline__ void put_tagged(unsigned long long *dst, double v, unsigned long long tag) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    st_relaxed_sys(&dst[0], (bits & 0xffffffffull) | tag);
+    st_relaxed_sys(&dst[1], (bits >> 32) | tag);
+}
+__device__ __forceinline__ bool get_tagged(const unsigned long long *src, unsigned long long tag, long long limit,
+                                           double &out) {
+    const long long t0 = clock64();
+    unsigned long long lo, hi;
+    for (;;) {
+        lo = ld_relaxed_sys(&src[0]);
+        hi = ld_relaxed_sys(&src[1]);
+        if ((lo & 0xffffffff00000000ull) == tag && (hi & 0xffffffff00000000ull) == tag) break;
+        if (clock64() - t0 > limit) return false;
+    }
+    out = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+    return true;
+}
+
+// On entry v[] holds this rank's totals (identical in every thread of the grid); on return the totals
+// over all ranks, identical in every thread of every rank.  Block 0 is the only block that talks to the
+// peers: it stores its words into every rank's mailbox, collects the ranks' words from its own mailbox
+// (bounded wait), adds them in rank order and publishes the result -- or NaN after a timeout -- in the
+// local `pub` words, which every block reads.  One source of truth: all blocks take the same branch.
+template <int NV>
+__device__ __forceinline__ void peer_allsum(const PeerComm &pc, unsigned long long *pub, unsigned long long seq,
+                                            double (&v)[NV], double *s_bc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = (int)(seq & 1ull);
+    const unsigned long long tag = (seq & 0xffffffffull) << 32;
+    unsigned long long *mine = pub + slot * 4;
+    __syncthreads();  // every thread has taken its copy of the previous reduction out of s_bc
+    if (warp == 0) {
+        if (blockIdx.x == 0) {
+            double got[NV];
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) got[k] = 0.0;
+            if (lane < pc.nranks) {
+#pragma unroll
+                for (int k = 0; k < NV; ++k) put_tagged(&pc.box[lane]->ll[slot][pc.rank][2 * k], v[k], tag);
+#pragma unroll
+                for (int k = 0; k < NV; ++k)
+                    ok = get_tagged(&pc.box[pc.rank]->ll[slot][lane][2 * k], tag, kPeerWait, got[k]) && ok;
+            }
+            ok = __all_sync(kFull, ok);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                double t = 0.0;
+                for (int r = 0; r < pc.nranks; ++r) t += __shfl_sync(kFull, got[k], r);  // rank order everywhere
+                if (!ok) t = __longlong_as_double(0x7ff8000000000000LL);
+                if (lane == 0) put_tagged(&mine[2 * k], t, tag);
+            }
+            if (!ok && lane == 0) *pc.status = 3;
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                double t;
+                if (!get_tagged(&mine[2 * k], tag, kLocalWait, t)) t = __longlong_as_double(0x7ff8000000000000LL);
+                s_bc[k] = t;
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = s_bc[k];
+    __syncthreads();  // s_bc is written again by the next reduction of this block
+}
+
 // one row of A times the staged part of d: ascending columns, separate multiply and add (the serial
 // CSR arithmetic of k_spmv).  Padding entries (value 0) may carry a column outside the staged range:
 // the index is clamped into it.
@@ -81,7 +173,7 @@ __device__ __forceinline__ double row_times_staged(const Sell &A, const double *
     return s;
 }
 
-template <int CH>
+template <int CH, bool PEERS>
 __global__ void __launch_bounds__(kFusedThreads, 1) k_cg_fused(CgFusedArgs a) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double smem[];
@@ -120,7 +212,25 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_cg_fused(CgFusedArgs a) {
     }
 
     const size_t pstride = (size_t)gridDim.x * 2;
-    for (;;) {
+    // several ranks: does this block's staged range reach into the ghost blocks of d?
+    const bool reads_lo_ghost = PEERS && a.pc.rank > 0 && c0 < a.own_off;
+    const bool reads_hi_ghost = PEERS && a.pc.rank < a.pc.nranks - 1 && c0 + (int)cn > a.own_off + a.A.nrows;
+    const int hi0 = a.A.nrows - a.pc.hi_count;
+    for (int iter = 0;; ++iter) {
+        if (PEERS && iter > 0 && (reads_lo_ghost || reads_hi_ghost)) {
+            // the neighbours stored their boundary blocks of d into my ghost blocks in their phase 3 and
+            // raised the flag after their grid barrier (iteration 0: the host exchanged the halo)
+            if (tid == 0) {
+                const unsigned long long want = a.halo_seq0 + (unsigned long long)iter;
+                const PeerMailbox *box = a.pc.box[a.pc.rank];
+                const long long t0 = clock64();
+                bool ok = true;
+                while (ok && reads_lo_ghost && ld_acquire_sys(&box->halo_flag[0]) < want) ok = clock64() - t0 < kPeerWait;
+                while (ok && reads_hi_ghost && ld_acquire_sys(&box->halo_flag[1]) < want) ok = clock64() - t0 < kPeerWait;
+                if (!ok) *a.pc.status = 3;  // the sums stay global, so every block still takes the same branches
+            }
+            __syncthreads();
+        }
         // the block's part of d (written by all blocks in phase 3 of the previous iteration, or by the
         // start kernel): L2 loads, this SM's L1 may hold last iteration's lines
         for (unsigned i = tid; i < cn; i += kFusedThreads) sd[i] = __ldcg(&a.d[c0 + i]);
@@ -141,6 +251,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_cg_fused(CgFusedArgs a) {
             }
         }
         grid_allsum<1>(grid, acc1, a.partials, s_red, s_bc);
+        if (PEERS) peer_allsum<1>(a.pc, a.pub, a.ar_seq0 + 2ull * iter + 1ull, acc1, s_bc);
         dAd = acc1[0];
         const double alpha = gh_old / dAd;
 
@@ -157,6 +268,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_cg_fused(CgFusedArgs a) {
                 acc2[1] += gi * hi;
             }
         grid_allsum<2>(grid, acc2, a.partials + pstride, s_red, s_bc);
+        if (PEERS) peer_allsum<2>(a.pc, a.pub, a.ar_seq0 + 2ull * iter + 2ull, acc2, s_bc);
         gg = acc2[0];
         gh_new = acc2[1];
 
@@ -173,11 +285,25 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_cg_fused(CgFusedArgs a) {
             if (rk[k] >= 0) {
                 const double dold = sd[diag0 + rk[k]];
                 sx[k * kFusedThreads + tid] += alpha * dold;
-                if (status == 0) a.d[a.own_off + rk[k]] = beta * dold - hk[k];
+                if (status == 0) {
+                    const double dnew = beta * dold - hk[k];
+                    a.d[a.own_off + rk[k]] = dnew;
+                    if (PEERS) {  // my first / last block of rows is the neighbours' ghost block
+                        if (a.pc.d_lo && rk[k] < a.pc.lo_count) a.pc.d_lo[rk[k]] = dnew;
+                        if (a.pc.d_hi && rk[k] >= hi0) a.pc.d_hi[rk[k] - hi0] = dnew;
+                    }
+                }
             }
         gh_old = gh_new;
-        if (status != 0) break;  // same decision in every thread of the grid
+        if (status != 0) break;  // same decision in every thread of the grid (and of every rank)
+        if (PEERS) __threadfence_system();  // my halo stores are ordered before the barrier and the flag
         grid.sync();
+        if (PEERS && blockIdx.x == 0 && tid == 0) {
+            const unsigned long long seq = a.halo_seq0 + (unsigned long long)iter + 1ull;
+            __threadfence_system();
+            if (a.pc.rank > 0) st_release_sys(&a.pc.box[a.pc.rank - 1]->halo_flag[1], seq);
+            if (a.pc.rank < a.pc.nranks - 1) st_release_sys(&a.pc.box[a.pc.rank + 1]->halo_flag[0], seq);
+        }
     }
 
 #pragma unroll
@@ -186,7 +312,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_cg_fused(CgFusedArgs a) {
     if (blockIdx.x == 0 && tid == 0) {
         a.S->it = it;
         a.S->res = res;
-        a.S->status = status;
+        a.S->status = (PEERS && __ldcg(a.pc.status) == 3) ? 3 : status;  // a peer wait timed out somewhere
         a.S->gg = gg;
         a.S->gh_new = gh_new;
         a.S->gh_old = gh_old;
@@ -236,7 +362,10 @@ void note(const Launcher &l, cudaError_t e) {
 }
 
 using FusedKernel = void (*)(CgFusedArgs);
-FusedKernel kernel_for(const Sell &A) { return A.chunk <= 7 ? k_cg_fused<7> : k_cg_fused<10>; }
+FusedKernel kernel_for(const Sell &A, bool peers) {
+    if (peers) return A.chunk <= 7 ? k_cg_fused<7, true> : k_cg_fused<10, true>;
+    return A.chunk <= 7 ? k_cg_fused<7, false> : k_cg_fused<10, false>;
+}
 
 }  // namespace
 
@@ -256,7 +385,8 @@ bool cg_fused_supported(int grid, size_t smem_bytes) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (!coop || smem_bytes + 1024 > (size_t)optin) return false;  // 1 KiB left for the static arrays
-    for (FusedKernel k : {FusedKernel(k_cg_fused<7>), FusedKernel(k_cg_fused<10>)}) {
+    for (FusedKernel k : {FusedKernel(k_cg_fused<7, false>), FusedKernel(k_cg_fused<10, false>),
+                          FusedKernel(k_cg_fused<7, true>), FusedKernel(k_cg_fused<10, true>)}) {
         // always the device maximum: contexts with different plans share the kernel's attribute
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024) != cudaSuccess) {
             cudaGetLastError();
@@ -275,7 +405,7 @@ bool cg_fused_supported(int grid, size_t smem_bytes) {
 cudaError_t launch_cg_fused(const Launcher &l, int grid, size_t smem_bytes, const CgFusedArgs &a) {
     CgFusedArgs args = a;
     void *params[] = {&args};
-    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)kernel_for(a.A), dim3((unsigned)grid),
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)kernel_for(a.A, a.pc.enabled != 0), dim3((unsigned)grid),
                                                       dim3(kFusedThreads), params, smem_bytes, l.stream);
     note(l, e);
     return e;

@@ -33,6 +33,11 @@ struct CgFusedArgs {
     int nwin, wpb;       // windows in the matrix, windows per block
     const int32_t *blk_c0, *blk_cn;  // per block: first staged column and number of staged columns
     int stage_cap;       // doubles of shared memory reserved for the staged part of d
+    // several ranks (pc.enabled): the two sums of an iteration also run over the NVLink mailboxes, the
+    // boundary blocks of d are stored into the neighbours' ghost blocks in phase 3, flags as in kernels.cu
+    PeerComm pc;
+    unsigned long long *pub;                 // 8 local words: block 0 publishes the all-rank totals here
+    unsigned long long ar_seq0, halo_seq0;   // iteration i uses ar_seq0 + 2i + 1, + 2i + 2 and halo_seq0 + i + 1
 };
 
 // per-window column range of the real (unpadded) entries: cmin[w], cmax[w]

@@ -162,6 +162,7 @@ struct wave_ctx {
         size_t smem = 0;
         int32_t *blk_c0 = nullptr, *blk_cn = nullptr;
         double *partials = nullptr;
+        unsigned long long *pub = nullptr;  // several ranks: block 0 publishes the all-rank totals here
     } fused;
 
     // NCCL + NVLink peer exchange
@@ -436,6 +437,13 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
         fa.blk_c0 = ctx->fused.blk_c0;
         fa.blk_cn = ctx->fused.blk_cn;
         fa.stage_cap = ctx->fused.stage_cap;
+        if (ctx->pc.enabled) {  // the first iteration's halo of d comes over NCCL, later ones inside the kernel
+            RET(halo_exchange(ctx, ctx->d));
+            fa.pc = ctx->pc;
+            fa.pub = ctx->fused.pub;
+            fa.ar_seq0 = ctx->ar_seq;
+            fa.halo_seq0 = ctx->halo_seq;
+        }
         CK(launch_cg_fused(l, ctx->fused.grid, ctx->fused.smem, fa));
     }
     int enq = 0;
@@ -499,6 +507,10 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     *iters = ctx->hS->it;
+    if (fused && ctx->pc.enabled) {  // the sequence numbers the kernel consumed (identical on every rank)
+        ctx->ar_seq += 2ull * (unsigned long long)ctx->hS->it;
+        ctx->halo_seq += (unsigned long long)ctx->hS->it;
+    }
     if (ctx->spmv_timing) drain_spmv_events(ctx, (size_t)ctx->hS->it);
     ctx->prev_its[slot] = ctx->hS->it;
     ctx->cg_stats[0] += 1;
@@ -759,7 +771,8 @@ int fused_plan(wave_ctx *ctx) {
     f.ok = false;
     const char *env = std::getenv("WAVE_CG_FUSED");
     if (!env || std::atoi(env) == 0) return WAVE_OK;
-    if (ctx->cfg.nranks != 1 || ctx->cfg.precond != WAVE_PRECOND_JACOBI) return WAVE_OK;
+    if (ctx->cfg.precond != WAVE_PRECOND_JACOBI) return WAVE_OK;
+    if (ctx->cfg.nranks != 1 && !ctx->pc.enabled) return WAVE_OK;  // several ranks: only over the NVLink mailboxes
     const int nwin = ctx->nslices / (kWindow / kSlice);
     int sms = kSMsFallback;
     int dev = 0;
@@ -794,6 +807,7 @@ int fused_plan(wave_ctx *ctx) {
     RET(dev_alloc(ctx, &f.blk_c0, (size_t)grid, false));
     RET(dev_alloc(ctx, &f.blk_cn, (size_t)grid, false));
     RET(dev_alloc(ctx, &f.partials, (size_t)grid * 4));
+    RET(dev_alloc(ctx, &f.pub, 8));
     CK(cudaMemcpyAsync(f.blk_c0, c0.data(), sizeof(int32_t) * grid, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f.blk_cn, cn.data(), sizeof(int32_t) * grid, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1052,7 +1066,8 @@ void wave_destroy(wave_ctx *ctx) {
         if (b) cudaFree(b);
     for (int k = 0; k < ctx->n_ipc_opened; ++k) cudaIpcCloseMemHandle(ctx->ipc_opened[k]);
     if (ctx->mailbox) cudaFree(ctx->mailbox);
-    for (void *q : {(void *)ctx->fused.blk_c0, (void *)ctx->fused.blk_cn, (void *)ctx->fused.partials})
+    for (void *q : {(void *)ctx->fused.blk_c0, (void *)ctx->fused.blk_cn, (void *)ctx->fused.partials,
+                    (void *)ctx->fused.pub})
         if (q) cudaFree(q);
     void *ptrs[] = {ctx->dprog, ctx->rowptr, ctx->slice_ptr, ctx->row_of, ctx->slot_of, ctx->col, ctx->c2i, ctx->i2c, ctx->tmp, ctx->M, ctx->K, ctx->S1, ctx->S2, ctx->dinv1, ctx->dinv2,
                     ctx->d0, ctx->u, ctx->v, ctx->a, ctx->unew, ctx->d, ctx->rhs, ctx->fvec, ctx->g, ctx->h,

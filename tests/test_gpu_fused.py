@@ -65,3 +65,61 @@ def test_fused_matches_three_kernel_path_at_bench_size(monkeypatch):
     assert out["0"][0] == out["1"][0]
     assert rel(out["1"][1], out["0"][1]) < 1e-10
     assert abs(out["1"][2] - out["0"][2]) < 1e-10 * abs(out["0"][2])
+
+
+def _rank_worker(rank, world, nccl_id, name, scheme, over, nsteps, q):
+    import sys
+    from pathlib import Path
+
+    import torch
+
+    root = Path(__file__).resolve().parent.parent
+    sys.path.insert(0, str(root))
+    sys.path.insert(0, str(root / "nmpde-wave-equation_b200"))
+    os.environ["WAVE_CG_FUSED"] = "1"
+    from wavegpu import WaveSolver, api, problem
+
+    torch.cuda.set_device(rank)
+    g = WaveSolver(problem(name, **over), scheme, rank=rank, nranks=world, nccl_id=nccl_id, device=rank)
+    fused = g.cg_fused_active()
+    g.init()
+    its = [g.step()[0] for _ in range(nsteps)]
+    u, e = g.vector(api.VEC_U), g.energy()
+    if rank == 0:
+        q.put((fused, u, e, its))
+    g.close()
+
+
+@pytest.mark.parametrize("name,scheme,over", [
+    ("standing-mode-wsol", "newmark", dict(Nel="40, 64", R=1, Dt="0.01")),
+    ("sine-membrane", "theta", dict(Nel="30, 12", R=2)),
+])
+def test_fused_ranks_match_one_rank(monkeypatch, name, scheme, over):
+    """K6f over two (or four) GPUs: sums over the NVLink mailboxes and halo stores inside the cooperative
+    kernel; the one-GPU three-kernel path is the yardstick."""
+    import torch
+    import torch.multiprocessing as mp
+
+    world = 4 if torch.cuda.device_count() >= 4 else 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("WAVE_CG_FUSED", "0")
+    nsteps = 8
+    g = WaveSolver(problem(name, **over), scheme)
+    g.init()
+    its1 = [g.step()[0] for _ in range(nsteps)]
+    u1, e1 = g.vector(api.VEC_U), g.energy()
+    g.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    nccl_id = api.comm_unique_id()
+    procs = [ctx.Process(target=_rank_worker, args=(rk, world, nccl_id, name, scheme, over, nsteps, q))
+             for rk in range(world)]
+    for p in procs:
+        p.start()
+    fused, u2, e2, its2 = q.get(timeout=300)
+    for p in procs:
+        p.join(120)
+    assert all(p.exitcode == 0 for p in procs) and fused
+    assert its2 == its1
+    assert rel(u2, u1) < 1e-10 and abs(e2 - e1) <= 1e-10 * abs(e1)
