@@ -207,6 +207,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precond", default="jacobi", choices=["jacobi", "mg"],
                     help="CG preconditioner: jacobi (north-star default) or the multigrid V-cycle (single GPU)")
+    ap.add_argument("--cg", default="three-kernel", choices=["three-kernel", "fused"],
+                    help="CG iteration: the measured three-kernel path (default) or the experimental cooperative "
+                         "kernel K6f (csrc/cg_fused.cu, WAVE_CG_FUSED=1; falls back when the problem does not fit)")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-scale-probe", action="store_true",
                     help="skip the SpMV / CG-iteration roofline probe on matrices larger than L2")
@@ -214,6 +217,8 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
+    if args.cg == "fused":
+        os.environ["WAVE_CG_FUSED"] = "1"  # read by wave_setup of every context created below
 
     import numpy as np
     import torch
@@ -252,6 +257,7 @@ def main():
                    stream=stream.cuda_stream, cg=cg_opts)
     g.init()
     setup_s = time.time() - t_setup0
+    cg_fused = g.cg_fused_active()
     n = g.n
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -367,6 +373,18 @@ def main():
                 "back_to_back": {"ms": ms_hot, "GB/s": alg_bytes / (ms_hot * 1e-3) / 1e9},
                 "note": "working set vs 126 MB L2: matrix %.0f MB + vectors; inside a CG solve the matrix is "
                         "re-read every iteration, so small workloads run partly from L2" % (12.0 * nnz / 1e6)}
+    if cg_fused:
+        # K6f: no per-SpMV launches to bracket; the figure is the whole solve (start residual, every
+        # iteration, the host's read-back) over its iterations, against 12 nnz + 26 n bytes per iteration
+        fb = 12.0 * nnz + 26.0 * g.nown
+        ms_it = cgs["ms_total"] / cgs["iterations"] if cgs["iterations"] else float("nan")
+        roofline.update({"kernel": "k_cg_fused (one cooperative kernel per solve: SpMV from staged d, updates on chip)",
+                         "algorithmic_bytes_per_launch": fb, "avg_launch_ms_in_step": ms_it,
+                         "achieved": fb / (ms_it * 1e-3) / 1e9, "frac": fb / (ms_it * 1e-3) / 1e9 / peak,
+                         "launches_timed": cgs["iterations"],
+                         "share_of_step_time": cgs["ms_total"] / total_ms if total_ms else None,
+                         "timed_over": "all CG solves of the timed steps: device ms per solve / iterations",
+                         "traffic": None})
     if rank != 0:
         g.close()
         if world > 1:
@@ -432,6 +450,7 @@ def main():
         "config": {"workload": workload, "problem": WORKLOADS[workload][0], "scheme": scheme,
                    "Nel": params["Nel"], "R": params["R"], "Dt": params["Dt"], "n_dofs": n,
                    "nnz_per_gpu": nnz, "cg_its_per_step": its_total / K, "preconditioner": args.precond,
+                   "cg_path": "fused (K6f)" if cg_fused else "three-kernel",
                    "cg_stop": "ReductionControl(10000, 1e-12, 1e-6)", "parallelism": f"strips{n_gpus}",
                    "l2": "flushed between steps (256 MiB write)" if flush is not None else "not flushed",
                    "setup_s": setup_s, "wall_s_timed_region": wall_s},
