@@ -132,6 +132,7 @@ struct wave_ctx {
     // vectors: u, v, a, unew, d are local-layout (ghosts included); rhs, fvec, g, h are row-indexed
     double *u = nullptr, *v = nullptr, *a = nullptr, *unew = nullptr, *d = nullptr;
     double *rhs = nullptr, *fvec = nullptr, *g = nullptr, *h = nullptr;
+    double *cellvec = nullptr;  // per-cell load vectors of the forcing kernel (non-separable forcing only)
     double *scratch = nullptr;  // global-size staging for gathers (allocated on demand)
     int64_t scratch_n = 0;
 
@@ -555,9 +556,8 @@ int compute_forcing(wave_ctx *ctx, double t_np1, double t_n, double w_np1, doubl
         *scale = two_levels ? w_np1 * T1 + w_n * eval(&ctx->f_time, 0.0, 0.0, t_n) : T1;
         return WAVE_OK;
     }
-    launch_fill(ctx->launcher, ctx->L.nown, 0.0, ctx->fvec);
     launch_forcing(ctx->launcher, ctx->L, ctx->dprog + WAVE_EXPR_F, &ctx->q_asm, t_np1, t_n, w_np1, w_n,
-                   two_levels, ctx->fvec);
+                   two_levels, ctx->cellvec, ctx->fvec);
     return WAVE_OK;
 }
 
@@ -780,16 +780,14 @@ int fused_plan(wave_ctx *ctx) {
     const int wpb = (nwin + sms - 1) / sms;
     if (wpb > kFusedMaxWin) return WAVE_OK;
     const int grid = (nwin + wpb - 1) / wpb;
-    int32_t *cmin = nullptr, *cmax = nullptr;
-    RET(dev_alloc(ctx, &cmin, (size_t)nwin, false));
-    RET(dev_alloc(ctx, &cmax, (size_t)nwin, false));
-    launch_window_col_range(ctx->launcher, ctx->A, nwin, cmin, cmax);
+    DevTmp<int32_t> cmin, cmax;
+    RET(dev_alloc(ctx, &cmin.p, (size_t)nwin, false));
+    RET(dev_alloc(ctx, &cmax.p, (size_t)nwin, false));
+    launch_window_col_range(ctx->launcher, ctx->A, nwin, cmin.p, cmax.p);
     std::vector<int32_t> lo(nwin), hi(nwin), c0(grid), cn(grid);
-    CK(cudaMemcpyAsync(lo.data(), cmin, sizeof(int32_t) * nwin, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(hi.data(), cmax, sizeof(int32_t) * nwin, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(lo.data(), cmin.p, sizeof(int32_t) * nwin, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hi.data(), cmax.p, sizeof(int32_t) * nwin, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaFree(cmin));
-    CK(cudaFree(cmax));
     int stage = 1;
     for (int b = 0; b < grid; ++b) {
         int32_t l = INT32_MAX, h = -1;
@@ -1070,7 +1068,7 @@ void wave_destroy(wave_ctx *ctx) {
                     (void *)ctx->fused.pub})
         if (q) cudaFree(q);
     void *ptrs[] = {ctx->dprog, ctx->rowptr, ctx->slice_ptr, ctx->row_of, ctx->slot_of, ctx->col, ctx->c2i, ctx->i2c, ctx->tmp, ctx->M, ctx->K, ctx->S1, ctx->S2, ctx->dinv1, ctx->dinv2,
-                    ctx->d0, ctx->u, ctx->v, ctx->a, ctx->unew, ctx->d, ctx->rhs, ctx->fvec, ctx->g, ctx->h,
+                    ctx->d0, ctx->u, ctx->v, ctx->a, ctx->unew, ctx->d, ctx->rhs, ctx->fvec, ctx->cellvec, ctx->g, ctx->h,
                     ctx->scratch, ctx->brow, ctx->bx, ctx->by, ctx->partials, ctx->counter, ctx->S, ctx->res,
                     ctx->flush_buf};
     for (void *p : ptrs)
@@ -1282,15 +1280,17 @@ int wave_setup(wave_ctx *ctx) {
             ctx->forcing_separable = false;
         }
         if (ctx->forcing_separable) {
-            Program *dS = nullptr;
-            RET(dev_alloc(ctx, &dS, 1, false));
-            CK(cudaMemcpyAsync(dS, &ctx->f_space, sizeof(Program), cudaMemcpyHostToDevice, ctx->stream));
-            launch_fill(l, L.nown, 0.0, ctx->fvec);
-            launch_forcing(l, L, dS, &ctx->q_asm, 0.0, 0.0, 1.0, 0.0, 0, ctx->fvec);
+            DevTmp<Program> dS;
+            DevTmp<double> cells;
+            RET(dev_alloc(ctx, &dS.p, 1, false));
+            RET(dev_alloc(ctx, &cells.p, (size_t)forcing_cells(L) * dofs_per_cell(L.mesh.r), false));
+            CK(cudaMemcpyAsync(dS.p, &ctx->f_space, sizeof(Program), cudaMemcpyHostToDevice, ctx->stream));
+            launch_forcing(l, L, dS.p, &ctx->q_asm, 0.0, 0.0, 1.0, 0.0, 0, cells.p, ctx->fvec);
             CK(cudaStreamSynchronize(ctx->stream));
-            CK(cudaFree(dS));
         }
     }
+    if (ctx->forcing_active && !ctx->forcing_separable)
+        RET(dev_alloc(ctx, &ctx->cellvec, (size_t)forcing_cells(L) * dofs_per_cell(L.mesh.r), false));
 
     // ---- scheme matrices (src/WaveNewmark.cpp:110-112, :372-374; src/WaveTheta.cpp:110-115) -----
     RET(dev_alloc(ctx, &ctx->S1, (size_t)ctx->nnz_pad, false));

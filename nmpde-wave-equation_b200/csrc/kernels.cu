@@ -334,55 +334,81 @@ __global__ void __launch_bounds__(kThreads) k_gather(int n, const int32_t *__res
 }
 
 // ---- K1: assemble_matrices (src/WaveNewmark.cpp:56-108 == src/WaveTheta.cpp:56-108) ---------------
-// One thread per cell: quadrature loop in the reference's order (q outer, i, j inner), c evaluated
-// at the quadrature point at parser time 0, then scatter-add of the owned rows into the CSR values.
+// Row gather, no atomics: one thread per owned DoF row.  For each adjacent cell, in ascending cell
+// order (entity_cells) -- the order in which the reference's serial cell loop adds into the global
+// entry -- the thread integrates its own row of the element matrices with the reference's quadrature
+// loop (q outer, j inner; c evaluated at the quadrature point at parser time 0) and adds it to the
+// row's entries.  Every entry is therefore a fixed sequence of additions: matrices are bitwise
+// reproducible between contexts and identical for any number of ranks.
+template <int R>
+__device__ void assemble_row(const Mesh &m, int i, int j, int kind, const Program *cprog, const Quadrature &Q,
+                             int n, const int64_t *icols, double *Mrow, double *Krow) {
+    constexpr int DPC = R == 1 ? 3 : 6;
+    int64_t cells[6];
+    const int nc = entity_cells(m, i, j, kind, cells);
+    const int64_t self = entity_dof_internal(m, i, j, kind);
+    for (int k = 0; k < n; ++k) { Mrow[k] = 0.0; Krow[k] = 0.0; }
+    for (int c = 0; c < nc; ++c) {
+        int64_t d[6];
+        cell_dofs_internal(m, cells[c], d);
+        int a = 0;
+#pragma unroll
+        for (int k = 0; k < DPC; ++k)
+            if (d[k] == self) a = k;
+        double X0, Y0, sx, sy;
+        cell_geometry(m, cells[c], X0, Y0, sx, sy);
+        const double det = sx * sy, adet = fabs(det);
+        const double ix = sy / det, iy = sx / det;  // J^{-T} = diag(1/sx, 1/sy) written as the adjugate / det
+        double Me[DPC], Ke[DPC];
+#pragma unroll
+        for (int b = 0; b < DPC; ++b) { Me[b] = 0.0; Ke[b] = 0.0; }
+        for (int q = 0; q < Q.nq; ++q) {
+            double phi[DPC], dxi[DPC], deta[DPC], gx[DPC], gy[DPC];
+            shape_values(R, Q.xi[q], Q.eta[q], phi);
+            shape_grads(R, Q.xi[q], Q.eta[q], dxi, deta);
+#pragma unroll
+            for (int b = 0; b < DPC; ++b) { gx[b] = ix * dxi[b]; gy[b] = iy * deta[b]; }
+            double pa = phi[0], gxa = gx[0], gya = gy[0];
+#pragma unroll
+            for (int b = 1; b < DPC; ++b)
+                if (a == b) { pa = phi[b]; gxa = gx[b]; gya = gy[b]; }
+            const double JxW = Q.w[q] * adet;
+            const double xq = X0 + sx * Q.xi[q], yq = Y0 + sy * Q.eta[q];
+            const double cv = eval(cprog, xq, yq, 0.0);
+            const double c2 = cv * cv;
+#pragma unroll
+            for (int b = 0; b < DPC; ++b) {
+                Me[b] += pa * phi[b] * JxW;
+                Ke[b] += c2 * (gxa * gx[b] + gya * gy[b]) * JxW;
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < DPC; ++b) {
+            int p = 0;
+            while (p < n - 1 && icols[p] != d[b]) ++p;
+            Mrow[p] += Me[b];
+            Krow[p] += Ke[b];
+        }
+    }
+}
 template <int R>
 __global__ void __launch_bounds__(128) k_assemble(Layout L, const Program *cprog, Quadrature Q, Sell A,
                                                   double *M, double *K) {
-    constexpr int DPC = R == 1 ? 3 : 6;
-    const int jtop = L.jq1 < L.mesh.ny ? L.jq1 : L.mesh.ny - 1;  // one quad row above the owned ones
-    const int64_t c_begin = 2LL * L.jq0 * L.mesh.nx, c_end = 2LL * (jtop + 1) * L.mesh.nx;
-    const int64_t cell = c_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= c_end) return;
-    double X0, Y0, sx, sy;
-    cell_geometry(L.mesh, cell, X0, Y0, sx, sy);
-    const double det = sx * sy, adet = fabs(det);
-    const double ix = sy / det, iy = sx / det;  // J^{-T} = diag(1/sx, 1/sy) written as the adjugate / det
-    double Me[DPC][DPC], Ke[DPC][DPC];
-#pragma unroll
-    for (int a = 0; a < DPC; ++a)
-#pragma unroll
-        for (int b = 0; b < DPC; ++b) { Me[a][b] = 0.0; Ke[a][b] = 0.0; }
-    for (int q = 0; q < Q.nq; ++q) {
-        double phi[DPC], dxi[DPC], deta[DPC], gx[DPC], gy[DPC];
-        shape_values(R, Q.xi[q], Q.eta[q], phi);
-        shape_grads(R, Q.xi[q], Q.eta[q], dxi, deta);
-#pragma unroll
-        for (int a = 0; a < DPC; ++a) { gx[a] = ix * dxi[a]; gy[a] = iy * deta[a]; }
-        const double JxW = Q.w[q] * adet;
-        const double xq = X0 + sx * Q.xi[q], yq = Y0 + sy * Q.eta[q];
-        const double cv = eval(cprog, xq, yq, 0.0);
-        const double c2 = cv * cv;
-#pragma unroll
-        for (int a = 0; a < DPC; ++a)
-#pragma unroll
-            for (int b = 0; b < DPC; ++b) {
-                Me[a][b] += phi[a] * phi[b] * JxW;
-                Ke[a][b] += c2 * (gx[a] * gx[b] + gy[a] * gy[b]) * JxW;
-            }
-    }
-    int64_t d[6];
-    cell_dofs_internal(L.mesh, cell, d);
-#pragma unroll
-    for (int a = 0; a < DPC; ++a) {
-        const int64_t row = d[a] - L.row0;
-        if (row < 0 || row >= L.nown) continue;
-#pragma unroll
-        for (int b = 0; b < DPC; ++b) {
-            const uint32_t pos = find_col(A, (int)row, (int32_t)(d[b] - L.col0));
-            atomicAdd(&M[pos], Me[a][b]);
-            atomicAdd(&K[pos], Ke[a][b]);
-        }
+    const SlotRange s = owned_slots(L);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= slot_count(L, s)) return;
+    int i, j, kind;
+    decode_slot(L, s, t, i, j, kind);
+    const int64_t dof = entity_dof_internal(L.mesh, i, j, kind);
+    if (dof < L.row0 || dof >= L.row0 + L.nown) return;
+    int64_t cols[kMaxRow], icols[kMaxRow];
+    double Mrow[kMaxRow], Krow[kMaxRow];
+    const int n = build_row(L.mesh, i, j, kind, cols, icols);
+    assemble_row<R>(L.mesh, i, j, kind, cprog, Q, n, icols, Mrow, Krow);
+    const uint32_t base = sell_row_base(A, (int)(dof - L.row0));
+    for (int k = 0; k < n; ++k) {
+        M[base + kSlice * k] = Mrow[k];
+        K[base + kSlice * k] = Krow[k];
     }
 }
 
@@ -439,13 +465,17 @@ __global__ void k_interpolate(Layout L, const Program *p, double t, double *vec,
 }
 
 // ---- K4: forcing load vector (src/WaveNewmark.cpp:151-171, src/WaveTheta.cpp:151-180) ---------------
+// Two passes, no atomics: (1) one thread per cell integrates the cell's load vector into cellvec
+// (cell-major, DPC entries per cell); (2) one thread per owned row adds the entries of its adjacent
+// cells in ascending cell order, the order of the reference's serial cell loop.
 template <int R>
-__global__ void __launch_bounds__(128) k_forcing(Layout L, const Program *f, Quadrature Q, double t_np1,
-                                                 double t_n, double w_np1, double w_n, int two_levels,
-                                                 double *fvec) {
+__global__ void __launch_bounds__(128) k_forcing_cells(Layout L, const Program *f, Quadrature Q, double t_np1,
+                                                       double t_n, double w_np1, double w_n, int two_levels,
+                                                       double *cellvec) {
     constexpr int DPC = R == 1 ? 3 : 6;
     const int jtop = L.jq1 < L.mesh.ny ? L.jq1 : L.mesh.ny - 1;
-    const int64_t c_begin = 2LL * L.jq0 * L.mesh.nx, c_end = 2LL * (jtop + 1) * L.mesh.nx;
+    const int jbot = L.jq0;  // block j holds the DoFs first met in quad row j: owned rows touch quad rows jq0 .. jq1
+    const int64_t c_begin = 2LL * jbot * L.mesh.nx, c_end = 2LL * (jtop + 1) * L.mesh.nx;
     const int64_t cell = c_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= c_end) return;
     double X0, Y0, sx, sy;
@@ -469,13 +499,34 @@ __global__ void __launch_bounds__(128) k_forcing(Layout L, const Program *f, Qua
 #pragma unroll
         for (int a = 0; a < DPC; ++a) acc[a] += fv * phi[a] * JxW;
     }
-    int64_t d[6];
-    cell_dofs_internal(L.mesh, cell, d);
 #pragma unroll
-    for (int a = 0; a < DPC; ++a) {
-        const int64_t row = d[a] - L.row0;
-        if (row >= 0 && row < L.nown) atomicAdd(&fvec[row], acc[a]);
+    for (int a = 0; a < DPC; ++a) cellvec[(cell - c_begin) * DPC + a] = acc[a];
+}
+template <int R>
+__global__ void __launch_bounds__(128) k_forcing_gather(Layout L, const double *__restrict__ cellvec,
+                                                        double *__restrict__ fvec) {
+    constexpr int DPC = R == 1 ? 3 : 6;
+    const SlotRange s = owned_slots(L);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= slot_count(L, s)) return;
+    int i, j, kind;
+    decode_slot(L, s, t, i, j, kind);
+    const int64_t dof = entity_dof_internal(L.mesh, i, j, kind);
+    if (dof < L.row0 || dof >= L.row0 + L.nown) return;
+    const int64_t c_begin = 2LL * L.jq0 * L.mesh.nx;
+    int64_t cells[6];
+    const int nc = entity_cells(L.mesh, i, j, kind, cells);
+    double sum = 0.0;
+    for (int c = 0; c < nc; ++c) {
+        int64_t d[6];
+        cell_dofs_internal(L.mesh, cells[c], d);
+        int a = 0;
+#pragma unroll
+        for (int k = 0; k < DPC; ++k)
+            if (d[k] == dof) a = k;
+        sum += cellvec[(cells[c] - c_begin) * DPC + a];
     }
+    fvec[dof - L.row0] = sum;
 }
 
 // ---- K5: boundary values (src/WaveNewmark.cpp:186-241, :348-374; src/WaveTheta.cpp:259-272) ---------
@@ -1024,13 +1075,9 @@ void launch_gather(const Launcher &l, int n, const int32_t *map, const double *s
     if (n <= 0) return;
     WV_LAUNCH(l, k_gather, stream_blocks(n), kThreads, 0, n, map, src, dst);
 }
-static int64_t assembly_cells(const Layout &L) {
-    const int jtop = L.jq1 < L.mesh.ny ? L.jq1 : L.mesh.ny - 1;
-    return 2LL * (jtop + 1 - L.jq0) * L.mesh.nx;
-}
 void launch_assemble(const Launcher &l, const Layout &L, const Program *c, const Quadrature *q, const Sell &A,
                      double *M, double *K) {
-    const int64_t n = assembly_cells(L);
+    const int64_t n = slot_count(L, owned_slots(L));
     if (L.mesh.r == 1) WV_LAUNCH(l, k_assemble<1>, blocks_for(n, 128), 128, 0, L, c, *q, A, M, K);
     else WV_LAUNCH(l, k_assemble<2>, blocks_for(n, 128), 128, 0, L, c, *q, A, M, K);
 }
@@ -1053,13 +1100,24 @@ void launch_interpolate(const Launcher &l, const Layout &L, const Program *p, do
     const int64_t n = slot_count(L, local_slots(L));
     WV_LAUNCH(l, k_interpolate, blocks_for(n, 128), 128, 0, L, p, t, vec, sx, sy);
 }
+// cells whose load vectors the owned rows need: the owned quad rows and the quad row above them
+int64_t forcing_cells(const Layout &L) {
+    const int jtop = L.jq1 < L.mesh.ny ? L.jq1 : L.mesh.ny - 1;
+    return 2LL * (jtop + 1 - L.jq0) * L.mesh.nx;
+}
 void launch_forcing(const Launcher &l, const Layout &L, const Program *f, const Quadrature *q, double t_np1,
-                    double t_n, double w_np1, double w_n, int two_levels, double *fvec) {
-    const int64_t n = assembly_cells(L);
-    if (L.mesh.r == 1)
-        WV_LAUNCH(l, k_forcing<1>, blocks_for(n, 128), 128, 0, L, f, *q, t_np1, t_n, w_np1, w_n, two_levels, fvec);
-    else
-        WV_LAUNCH(l, k_forcing<2>, blocks_for(n, 128), 128, 0, L, f, *q, t_np1, t_n, w_np1, w_n, two_levels, fvec);
+                    double t_n, double w_np1, double w_n, int two_levels, double *cellvec, double *fvec) {
+    const int64_t nc = forcing_cells(L);
+    const int64_t nr = slot_count(L, owned_slots(L));
+    if (L.mesh.r == 1) {
+        WV_LAUNCH(l, k_forcing_cells<1>, blocks_for(nc, 128), 128, 0, L, f, *q, t_np1, t_n, w_np1, w_n, two_levels,
+                  cellvec);
+        WV_LAUNCH(l, k_forcing_gather<1>, blocks_for(nr, 128), 128, 0, L, cellvec, fvec);
+    } else {
+        WV_LAUNCH(l, k_forcing_cells<2>, blocks_for(nc, 128), 128, 0, L, f, *q, t_np1, t_n, w_np1, w_n, two_levels,
+                  cellvec);
+        WV_LAUNCH(l, k_forcing_gather<2>, blocks_for(nr, 128), 128, 0, L, cellvec, fvec);
+    }
 }
 void launch_bc_values(const Launcher &l, int mode, int nb, const int32_t *brow, const double *bx,
                       const double *by, const Program *g, double t, double dt, double beta_dt2,

@@ -152,8 +152,11 @@ void launch_build_perm(const Launcher &, const Layout &, int32_t *c2i, int32_t *
 void launch_gather(const Launcher &, int n, const int32_t *map, const double *src, double *dst);
 void launch_interpolate(const Launcher &, const Layout &, const Program *p, double t, double *vec,
                         double *sx, double *sy);
+// load vector in two deterministic passes: per-cell vectors into cellvec (forcing_cells(L) * dofs_per_cell
+// doubles), then a row gather in cell order into fvec (owned rows)
+int64_t forcing_cells(const Layout &);
 void launch_forcing(const Launcher &, const Layout &, const Program *f, const Quadrature *q, double t_np1,
-                    double t_n, double w_np1, double w_n, int two_levels, double *fvec);
+                    double t_n, double w_np1, double w_n, int two_levels, double *cellvec, double *fvec);
 // K5 modes
 enum { BC_DIRECT = 0, BC_NEWMARK_IMPLICIT = 1, BC_SECOND_DIFF = 2 };
 void launch_bc_values(const Launcher &, int mode, int nb, const int32_t *brow, const double *bx,

@@ -13,7 +13,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+# oracle / reference parity first, API semantics and GPU-vs-GPU consistency afterwards: with `-x` a
+# failure in a later file can no longer hide the parity files
+ORDER = ["test_oracle_golden", "test_oracle_structure", "test_oracle_crosscheck", "test_gpu_parity",
+         "test_gpu_golden_sweep", "test_gpu_stencil", "test_gpu_multigrid", "test_gpu_multi", "test_gpu_cli"]
+
+
 def pytest_collection_modifyitems(config, items):
+    def rank(item):
+        stem = Path(str(item.fspath)).stem
+        return ORDER.index(stem) if stem in ORDER else len(ORDER)
+
+    items.sort(key=rank)  # stable: the order inside a file is kept
     try:
         import torch
 

@@ -65,7 +65,7 @@ def test_run_equals_repeated_step(scheme):
         a.step()
     done, its, nrm, tot = b.run(9)
     assert done == 9 and a.time == b.time
-    assert rel(a.vector(api.VEC_U), b.vector(api.VEC_U)) < 1e-12
+    assert np.array_equal(a.vector(api.VEC_U), b.vector(api.VEC_U))  # deterministic assembly and reductions
     a.close()
     b.close()
 
@@ -80,7 +80,7 @@ def test_reinit_restarts_the_run():
     g.init()
     for _ in range(4):
         g.step()
-    assert rel(g.vector(api.VEC_U), u1) < 1e-13
+    assert np.array_equal(g.vector(api.VEC_U), u1)
     g.close()
 
 
@@ -119,14 +119,17 @@ def test_identity_preconditioner_matches_oracle():
 
 
 def test_forcing_every_step_flag_is_equivalent():
-    p = problem("standing-mode-wsol", Nel="20", Dt="0.02")
+    """F = 0.0 with the forcing kernels forced to run every step: the load vector is exactly zero, and
+    assembly is a deterministic row gather, so the two contexts agree bit for bit."""
+    p = problem("standing-mode-wsol", Nel="20", Dt="0.02", Theta="0.5")
     a = WaveSolver(p, "theta")
     b = WaveSolver(p, "theta", flags=api.FLAG_FORCING_EVERY_STEP)
     a.init()
     b.init()
     a.run(8)
     b.run(8)
-    assert rel(a.vector(api.VEC_V), b.vector(api.VEC_V)) < 1e-12
+    assert np.array_equal(a.vector(api.VEC_V), b.vector(api.VEC_V))
+    assert np.array_equal(a.vector(api.VEC_U), b.vector(api.VEC_U))
     assert b.launch_count() > a.launch_count()
     a.close()
     b.close()
