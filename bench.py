@@ -5,10 +5,11 @@ roofline and the CPU path timed beside it.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
 
 A "step" is one pass of the reference's time loop body (src/WaveNewmark.cpp:424-440): assemble_rhs,
-the Dirichlet values, the Jacobi-PCG solve, the Newmark update and the norms.  Default workload at
-N=1: BASELINE.json configs[1] (standing-mode-wsol.json, Newmark beta=1/4 gamma=1/2, Nel=1024, R=1).
-At N>1 the default is the weak-scaled version of the same workload (Nel = 1024 x 1024*N on
-[0,1]x[0,N], one strip of 1024 quad rows per GPU).  Other workloads: see WORKLOADS.
+the Dirichlet values, the Jacobi-PCG solve, the Newmark update and the norms.  Default workload at every
+N: the north star's 64 M-DoF P2 Newmark run (standing-mode-wsol.json, Newmark beta=1/4 gamma=1/2,
+Nel=4096, R=2, 67 125 249 DoFs) -- strong scaling, the same global problem on 1, 2, 4, 8 GPUs.  At N=1 the
+line also carries BASELINE.json's other single-GPU configs as `extras` (c2, c3, c4, and the default
+workload with the multigrid preconditioner).  Other workloads: see WORKLOADS.
 
 Output: one JSON line (rank 0).  Timing: CUDA events on the context's stream around every step,
 L2 flushed between steps, max over ranks.  The oracle (oracle/) is used only for the cpu_baseline
@@ -52,7 +53,8 @@ WORKLOADS = {
     "newmark-4096-p2": ("standing-mode-wsol", "newmark", dict(Nel="4096", R="2", Dt="0.001"), "strong", False),
     "newmark-2048-p2": ("standing-mode-wsol", "newmark", dict(Nel="2048", R="2", Dt="0.002"), "strong", False),
 }
-DEFAULT = "c2-standing-newmark-1024-p1"
+DEFAULT = "newmark-4096-p2"  # the north star's 64 M-DoF P2 Newmark run; strong scaling at every N
+EXTRAS = ["c2-standing-newmark-1024-p1", "c3-gaussian-explicit-4096-p2", "c4-ricker-be-4096-p2"]
 # BASELINE.md publishes a number only for this workload: 410 881 DoFs x 625 steps / 296.3 s whole-process
 # wall time on one Xeon Gold 6238R core (AMG-CG); 16 ranks: 9.31 M, 32 ranks: 12.8 M DoF-steps/s
 PUBLISHED = {"published-newmark-640-p1": 0.867e6}
@@ -135,9 +137,29 @@ def hbm_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def cpu_sample_params(params):
+    """Bounded sample of a workload for the CPU arm: the same mesh widths (dx, dy), time step, scheme and
+    functions on a strip of fewer quad rows, about 4 M DoFs (the full 67 M-DoF workloads need ~140 s of
+    set-up and ~20 s per step on the host).  Small workloads are taken whole."""
+    from wavegpu.api import parse_geometry, parse_nel
+
+    nx, ny = parse_nel(params["Nel"])
+    r = int(params["R"])
+    per_row = r * (r * nx + 1)  # DoFs added per quad row
+    ny_s = max(8, int(round(4.2e6 / per_row)))
+    if ny_s >= ny:
+        return dict(params), "the whole workload"
+    x0, x1, y0, y1 = parse_geometry(params["Geometry"])
+    p = dict(params)
+    p["Nel"] = f"{nx}, {ny_s}"
+    p["Geometry"] = f"[{x0}, {x1}] x [{y0}, {y0 + (y1 - y0) * ny_s / ny!r}]"
+    return p, (f"strip of {ny_s} of the workload's {ny} quad rows (same dx, dy, Dt, functions; "
+               f"Nel = {nx} x {ny_s})")
+
+
 def time_oracle(params, scheme, budget_s, max_steps, warmup=1, precond=0):
     """The CPU path: oracle/wave_oracle.c (C restatement of the reference, OpenMP over all host
-    threads) stepping the same workload for a bounded number of steps."""
+    threads) stepping the sample for a bounded number of steps."""
     # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU path is meant to use every host core
     try:
         ncores = len(os.sched_getaffinity(0))
@@ -172,29 +194,97 @@ def time_oracle(params, scheme, budget_s, max_steps, warmup=1, precond=0):
             "cg_its_per_step": its / max(len(times), 1), "threads": O.lib().oracle_num_threads()}
 
 
+def workload_config(workload, params, scheme, n_dofs, precond="jacobi"):
+    """The part of `config` that names the workload: identical for the GPU arm and the reference arm."""
+    return {"workload": workload, "problem": WORKLOADS[workload][0], "scheme": scheme, "Nel": params["Nel"],
+            "R": str(params["R"]), "Dt": params["Dt"], "n_dofs": int(n_dofs), "preconditioner": precond,
+            "cg_stop": "ReductionControl(10000, 1e-12, 1e-6)"}
+
+
+def full_n_dofs(params):
+    from wavegpu.api import parse_nel
+
+    nx, ny = parse_nel(params["Nel"])
+    r = int(params["R"])
+    return (r * nx + 1) * (r * ny + 1)
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The deal.II/Trilinos
-    binaries cannot be built in this image, so this is the oracle port."""
+    binaries cannot be built in this image, so this is the oracle port, on all
+    host threads, on a bounded sample of the GPU arm's workload (same config, metric and unit)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     workload = args.workload or DEFAULT
-    params, scheme, scaling = make_params(workload, 1)
-    r = time_oracle(params, scheme, budget_s=150.0, max_steps=args.steps, warmup=min(args.warmup, 2))
+    params, scheme, scaling = make_params(workload, args.gpus)
+    sample, what = cpu_sample_params(params)
+    W = max(args.warmup, 3)
+    r = time_oracle(sample, scheme, budget_s=150.0, max_steps=args.steps, warmup=W)
     value = r["n"] * r["steps"] / r["seconds"]
+    sample_txt = (f"{what}: {r['n']} DoFs, {r['steps']} time steps after {W} warm-up steps "
+                  f"(oracle/wave_oracle.c, OpenMP, {r['threads']} threads); DoF-steps/s is a rate, "
+                  "so the sample's figure stands for the workload")
     line = {
         "impl": "reference", "metric": "dof_steps_per_sec", "value": value, "unit": "DoF-steps/s",
-        "n_gpus": args.gpus, "steps": r["steps"], "warmup": min(args.warmup, 2),
-        "ms_per_step": 1e3 * r["seconds"] / r["steps"], "higher_is_better": True, "scaling": scaling,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": W,
+        "ms_per_step": 1e3 * r["seconds"] / r["steps"] * (full_n_dofs(params) / r["n"]),
+        "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "n_dofs": r["n"], "cg_its_per_step": r["cg_its_per_step"],
-                   "preconditioner": "jacobi"},
+        "config": workload_config(workload, params, scheme, full_n_dofs(params)),
+        "run": {"steps_timed": r["steps"], "sample_n_dofs": r["n"], "sample_ms_per_step": 1e3 * r["seconds"] / r["steps"],
+                "cg_its_per_step": r["cg_its_per_step"], "setup_s": r["setup_s"],
+                "ms_per_step_note": "ms_per_step is the sample's step time scaled to the workload's DoF count"},
         "cpu_baseline": {"value": value, "unit": "DoF-steps/s", "cores": r["threads"], "kind": "port",
-                         "sample": f"{r['steps']} time steps of the same workload (oracle/wave_oracle.c, OpenMP)"},
+                         "sample": sample_txt},
         "e2e": {"value": value, "unit": "DoF-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def timed_steps(g, stream, K, flush, torch):
+    """K steps of solver g, each bracketed by CUDA events on the context's stream; L2 flushed between."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    its_total = 0
+    for k in range(K):
+        if flush is not None:
+            flush.fill_(k & 0xFF)
+        ev[k][0].record(stream)
+        its, _ = g.step()
+        ev[k][1].record(stream)
+        its_total += its[0] + its[1]
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in ev], its_total
+
+
+def extra_workload(name, stream, flush, torch, K, peak, precond=None):
+    """One more BASELINE workload on one GPU: DoF-steps/s, iterations, CG iteration time, flushed SpMV."""
+    from wavegpu import WaveSolver, api
+
+    params, scheme, _ = make_params(name, 1)
+    t0 = time.time()
+    g = WaveSolver(params, scheme, stream=stream.cuda_stream, cg=dict(precond=2) if precond == "mg" else None)
+    g.init()
+    setup_s = time.time() - t0
+    for _ in range(3):
+        g.step()
+    g.cg_stats(reset=True)
+    ms, its = timed_steps(g, stream, K, flush, torch)
+    cgs = g.cg_stats()
+    info = g.operator_info()
+    ms_sp, by_sp = g.bench_spmv(api.MAT_SYS1, reps=10, flush_l2=True)
+    out = {"workload": name, "n_dofs": g.n, "value": g.n * K / (sum(ms) * 1e-3), "unit": "DoF-steps/s",
+           "ms_per_step": sum(ms) / K, "steps": K, "cg_its_per_step": its / K,
+           "cg_ms_per_iteration": cgs["ms_total"] / max(cgs["iterations"], 1),
+           "cg_path": "fused (K6f)" if g.cg_fused_active() else "three-kernel",
+           "operator": info, "setup_s": setup_s,
+           "spmv_l2_flushed": {"ms": ms_sp, "GB/s": by_sp / ms_sp / 1e6, "frac": by_sp / ms_sp / 1e6 / peak,
+                               "algorithmic_bytes": by_sp}}
+    if precond == "mg":
+        out["preconditioner"] = "geometric multigrid V(2,2), damped Jacobi smoothing (WAVE_PRECOND_MG)"
+    g.close()
+    return out
 
 
 def main():
@@ -206,21 +296,24 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precond", default="jacobi", choices=["jacobi", "mg"],
-                    help="CG preconditioner: jacobi (north-star default) or the multigrid V-cycle (single GPU)")
-    ap.add_argument("--cg", default="three-kernel", choices=["three-kernel", "fused"],
-                    help="CG iteration: the measured three-kernel path (default) or the experimental cooperative "
-                         "kernel K6f (csrc/cg_fused.cu, WAVE_CG_FUSED=1; falls back when the problem does not fit)")
+                    help="CG preconditioner: jacobi (north-star default) or the multigrid V-cycle")
+    ap.add_argument("--cg", default="auto", choices=["auto", "three-kernel", "fused"],
+                    help="CG iteration: auto (the cooperative kernel K6f where the rows fit on chip, else three "
+                         "kernels), or force one of them")
+    ap.add_argument("--no-stencil", action="store_true", help="keep every matrix row in SELL form")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
-    ap.add_argument("--no-scale-probe", action="store_true",
-                    help="skip the SpMV / CG-iteration roofline probe on matrices larger than L2")
+    ap.add_argument("--no-extras", "--no-scale-probe", dest="no_extras", action="store_true",
+                    help="skip the extra BASELINE workloads (c2, c3, c4, multigrid) reported at N=1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
         return
-    if args.cg == "fused":
-        os.environ["WAVE_CG_FUSED"] = "1"  # read by wave_setup of every context created below
+    if args.cg != "auto":
+        os.environ["WAVE_CG_FUSED"] = "1" if args.cg == "fused" else "0"  # read by wave_setup
+    if args.no_stencil:
+        os.environ["WAVE_NO_STENCIL"] = "1"
 
-    import numpy as np
+    import numpy as np  # noqa: F401
     import torch
 
     from wavegpu import WaveSolver, api
@@ -258,6 +351,7 @@ def main():
     g.init()
     setup_s = time.time() - t_setup0
     cg_fused = g.cg_fused_active()
+    info = g.operator_info()
     n = g.n
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -268,7 +362,6 @@ def main():
             torch.cuda.synchronize()
 
     # clocks / throttle reasons are sampled from the warm-up through the timed and the bracketed pass
-    # (the timed region alone lasts only tens of milliseconds at 100 ms sampling)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -278,36 +371,22 @@ def main():
     g.cg_stats(reset=True)
     launches0 = g.launch_count()
     barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    its_total = 0
     wall0 = time.time()
-    for k in range(K):
-        if flush is not None:
-            flush.fill_(k & 0xFF)
-        ev[k][0].record(stream)
-        its, _ = g.step()
-        ev[k][1].record(stream)
-        its_total += its[0] + its[1]
+    step_ms, its_total = timed_steps(g, stream, K, flush, torch)
     barrier()
     wall_s = time.time() - wall0
-    step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
     launches = g.launch_count() - launches0
     cgs = g.cg_stats()
-    # second pass over further steps of the same run with every CG SpMV launch bracketed by events on
-    # the context stream (kept out of the pass above: the brackets cost ~1 us per launch)
-    g.spmv_timing(True)
+    # second pass over further steps of the same run with every kernel of the CG iterations bracketed by
+    # events on the context stream (kept out of the pass above: the brackets cost ~1 us per launch and
+    # switch off the programmatic overlap of consecutive kernels)
+    g.kernel_timing(True)
     Kr = max(3, min(K, 10))
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kr)]
-    for k in range(Kr):
-        if flush is not None:
-            flush.fill_(k & 0xFF)
-        ev2[k][0].record(stream)
-        g.step()
-        ev2[k][1].record(stream)
+    ms2, _ = timed_steps(g, stream, Kr, flush, torch)
     barrier()
-    spmv_launches, spmv_ms = g.spmv_timing(False)
-    bracketed_ms = float(sum(a.elapsed_time(b) for a, b in ev2))
+    kt_n, kt_ms = g.kernel_timing(False)
+    bracketed_ms = float(sum(ms2))
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
@@ -324,7 +403,6 @@ def main():
             return t.numpy()
 
         # every rank keeps (global-length) host arrays and moves its own rows each step
-        lo, hi = g.row0, g.row0 + g.nown
         if world == 1:
             u0_, v0_, a0_ = g.vector(api.VEC_U), g.vector(api.VEC_V), g.vector(api.VEC_A) if scheme == "newmark" else None
         else:
@@ -349,97 +427,80 @@ def main():
         e2e = {"value": n * Ke / e2e_s, "unit": "DoF-steps/s", "h2d_bytes_per_step": nvec * 8 * n,
                "d2h_bytes_per_step": nvec * 8 * n + 16 * world, "steps": Ke,
                "api": "wave_step_host (pinned host u, v, a in; u, v, a, norms out; every rank moves its own rows)"}
+        del u, v, a
 
-    # ---- roofline of the dominant kernel: the CG SpMV, timed live inside the steps above ------------
+    # ---- roofline of the dominant kernel, timed live inside the steps above --------------------------
     peak, peak_src = hbm_peak()
     nnz = g.nnz_local
-    alg_bytes = 12.0 * nnz + 20.0 * g.nown
-    avg_ms = spmv_ms / spmv_launches if spmv_launches else float("nan")
-    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if spmv_launches else float("nan")
-    ms_fl, _ = g.bench_spmv(api.MAT_SYS1, reps=20, flush_l2=True)
-    ms_hot, _ = g.bench_spmv(api.MAT_SYS1, reps=50, flush_l2=False)
+    kernels = []
+    names = ("k_spmv (CG A*d with fused d.Ad)", "k_cg_update (g += alpha Ad, h = D^-1 g, g.g, g.h)",
+             "k_cg_direction (x += alpha d, d = beta d - h)")
+    alg = (float(info["spmv_bytes"]), 40.0 * g.nown, 40.0 * g.nown)
+    for k in range(3):
+        if kt_n[k] > 0:
+            avg = kt_ms[k] / kt_n[k]
+            kernels.append({"kernel": names[k], "launches_timed": kt_n[k], "avg_launch_ms_in_step": avg,
+                            "algorithmic_bytes_per_launch": alg[k], "achieved": alg[k] / (avg * 1e-3) / 1e9,
+                            "frac": alg[k] / (avg * 1e-3) / 1e9 / peak,
+                            "share_of_step_time": kt_ms[k] / bracketed_ms if bracketed_ms else None})
+    ms_fl, by_fl = g.bench_spmv(api.MAT_SYS1, reps=20, flush_l2=True)
+    ms_it, by_it = (float("nan"), float("nan")) if cg_fused else g.bench_cg_iter(api.MAT_SYS1, reps=2)
     traffic = None
     tf = ROOT / "profiles" / "spmv_traffic.json"
-    if tf.exists():  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
-        traffic = json.loads(tf.read_text()).get(workload, {}).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "k_spmv<1,false> (CG A*d with fused d.Ad)", "achieved": achieved,
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
-                "avg_launch_ms_in_step": avg_ms, "launches_timed": spmv_launches,
-                "share_of_step_time": spmv_ms / bracketed_ms if bracketed_ms else None,
-                "timed_over": f"{Kr} further steps of the same run, every CG SpMV launch bracketed by CUDA events",
-                "l2_flushed_single_launch": {"ms": ms_fl, "GB/s": alg_bytes / (ms_fl * 1e-3) / 1e9,
-                                             "frac": alg_bytes / (ms_fl * 1e-3) / 1e9 / peak},
-                "back_to_back": {"ms": ms_hot, "GB/s": alg_bytes / (ms_hot * 1e-3) / 1e9},
-                "note": "working set vs 126 MB L2: matrix %.0f MB + vectors; inside a CG solve the matrix is "
-                        "re-read every iteration, so small workloads run partly from L2" % (12.0 * nnz / 1e6)}
-    if cg_fused:
-        # K6f: no per-SpMV launches to bracket; the figure is the whole solve (start residual, every
-        # iteration, the host's read-back) over its iterations, against 12 nnz + 26 n bytes per iteration
-        fb = 12.0 * nnz + 26.0 * g.nown
-        ms_it = cgs["ms_total"] / cgs["iterations"] if cgs["iterations"] else float("nan")
-        roofline.update({"kernel": "k_cg_fused (one cooperative kernel per solve: SpMV from staged d, updates on chip)",
-                         "algorithmic_bytes_per_launch": fb, "avg_launch_ms_in_step": ms_it,
-                         "achieved": fb / (ms_it * 1e-3) / 1e9, "frac": fb / (ms_it * 1e-3) / 1e9 / peak,
-                         "launches_timed": cgs["iterations"],
-                         "share_of_step_time": cgs["ms_total"] / total_ms if total_ms else None,
-                         "timed_over": "all CG solves of the timed steps: device ms per solve / iterations",
-                         "traffic": None})
+    roofline = None
+    if kernels:
+        dom = max(kernels, key=lambda kk: kk["share_of_step_time"] or 0.0)
+        if tf.exists() and world == 1:  # dram bytes per launch from the committed ncu capture of this workload
+            traffic = json.loads(tf.read_text()).get(workload, {}).get(dom["kernel"].split(" ")[0])
+        roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak,
+                    "peak_source": peak_src, "unit": "GB/s", "frac": dom["frac"], "traffic": traffic,
+                    "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+                    "avg_launch_ms_in_step": dom["avg_launch_ms_in_step"], "launches_timed": dom["launches_timed"],
+                    "share_of_step_time": dom["share_of_step_time"],
+                    "timed_over": f"{Kr} further steps of the same run, every CG kernel launch bracketed by CUDA events",
+                    "kernels": kernels}
+    elif cg_fused:
+        # K6f: no per-kernel launches to bracket; the figure is the whole solve (start residual, every
+        # iteration, the host's read-back) over its iterations, against its bytes per iteration
+        fb = float(info["spmv_bytes"]) - 16.0 * g.nown + 26.0 * g.nown
+        ms_i = cgs["ms_total"] / cgs["iterations"] if cgs["iterations"] else float("nan")
+        roofline = {"bound": "hbm", "kernel": "k_cg_fused (one cooperative kernel per solve: SpMV from staged d, "
+                                              "updates on chip)",
+                    "achieved": fb / (ms_i * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                    "frac": fb / (ms_i * 1e-3) / 1e9 / peak, "traffic": None,
+                    "algorithmic_bytes_per_launch": fb, "avg_launch_ms_in_step": ms_i,
+                    "launches_timed": cgs["iterations"],
+                    "share_of_step_time": cgs["ms_total"] / total_ms if total_ms else None,
+                    "timed_over": "all CG solves of the timed steps: device ms per solve / iterations"}
+    if roofline is not None:
+        roofline["spmv_l2_flushed_single_launch"] = {"ms": ms_fl, "GB/s": by_fl / ms_fl / 1e6,
+                                                     "frac": by_fl / ms_fl / 1e6 / peak, "algorithmic_bytes": by_fl}
+        roofline["cg_iteration"] = {"ms": ms_it, "algorithmic_bytes": by_it, "GB/s": by_it / ms_it / 1e6,
+                                    "frac": by_it / ms_it / 1e6 / peak}
+        roofline["operator"] = info
+    g.close()
     if rank != 0:
-        g.close()
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- the same kernels on matrices far larger than the 126 MB L2 (the bench workload's 88 MB matrix
-    # makes a 25 us kernel: launch ramp and tail weigh on its fraction) -------------------------------
-    at_scale = None
-    if world == 1 and not args.no_scale_probe:
-        from wavegpu.problems import problem as _problem
-
-        at_scale = []
-        for nel, r in (("4096", 1), ("2048", 2)):
-            gs = WaveSolver(_problem("standing-mode-wsol", Nel=nel, R=r, Dt="0.002"), "newmark",
-                            stream=stream.cuda_stream)
-            gs.init()
-            ms_s, by_s = gs.bench_spmv(api.MAT_SYS1, reps=10, flush_l2=True)
-            ms_c, by_c = gs.bench_cg_iter(api.MAT_SYS1, reps=2)
-            at_scale.append({"Nel": nel, "R": r, "n_dofs": gs.n, "nnz": gs.nnz_local,
-                             "spmv": {"ms": ms_s, "GB/s": by_s / ms_s / 1e6, "frac": by_s / ms_s / 1e6 / peak,
-                                      "algorithmic_bytes": by_s, "l2": "flushed before every launch"},
-                             "cg_iteration": {"ms": ms_c, "GB/s": by_c / ms_c / 1e6, "frac": by_c / ms_c / 1e6 / peak,
-                                              "algorithmic_bytes": by_c}})
-            gs.close()
-    # ---- the same workload with the multigrid V-cycle preconditioner (single GPU; the default `value`
-    # keeps the north star's Jacobi so that every N runs the same algorithm) ---------------------------
-    multigrid = None
-    if world == 1 and args.precond == "jacobi" and not args.no_scale_probe:
-        gm = WaveSolver(params, scheme, stream=stream.cuda_stream, cg=dict(precond=2))
-        gm.init()
-        for _ in range(W):
-            gm.step()
-        torch.cuda.synchronize()
-        evm = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        its_m = 0
-        for k in range(K):
-            if flush is not None:
-                flush.fill_(k & 0xFF)
-            evm[k][0].record(stream)
-            it_m, _ = gm.step()
-            evm[k][1].record(stream)
-            its_m += it_m[0] + it_m[1]
-        torch.cuda.synchronize()
-        ms_m = float(sum(a.elapsed_time(b) for a, b in evm))
-        multigrid = {"value": n * K / (ms_m * 1e-3), "unit": "DoF-steps/s", "ms_per_step": ms_m / K,
-                     "cg_its_per_step": its_m / K,
-                     "preconditioner": "geometric multigrid V(2,2), damped Jacobi smoothing (WAVE_PRECOND_MG)"}
-        gm.close()
+    # ---- the other BASELINE workloads on one GPU, and the multigrid preconditioner ---------------------
+    extras = None
+    if world == 1 and not args.no_extras:
+        Kx = max(3, min(K, 10))
+        extras = []
+        for name in EXTRAS:
+            if name != workload:
+                extras.append(extra_workload(name, stream, flush, torch, Kx, peak))
+        if args.precond == "jacobi":
+            extras.append(extra_workload(workload, stream, flush, torch, Kx, peak, precond="mg"))
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = time_oracle(params, scheme, budget_s=20.0, max_steps=10, precond=2 if args.precond == "mg" else 0)
+        sample, what = cpu_sample_params(params)
+        r = time_oracle(sample, scheme, budget_s=25.0, max_steps=10, precond=2 if args.precond == "mg" else 0)
         cpu = {"value": r["n"] * r["steps"] / r["seconds"], "unit": "DoF-steps/s", "cores": r["threads"],
                "kind": "port", "cg_its_per_step": r["cg_its_per_step"],
-               "sample": f"{r['steps']} time steps of the same workload on the host "
+               "sample": f"{what}: {r['n']} DoFs, {r['steps']} time steps on the host "
                          f"(oracle/wave_oracle.c, OpenMP, {r['threads']} threads)"}
 
     line = {
@@ -447,21 +508,19 @@ def main():
         "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": (value / PUBLISHED[workload]) if workload in PUBLISHED else None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "problem": WORKLOADS[workload][0], "scheme": scheme,
-                   "Nel": params["Nel"], "R": params["R"], "Dt": params["Dt"], "n_dofs": n,
-                   "nnz_per_gpu": nnz, "cg_its_per_step": its_total / K, "preconditioner": args.precond,
-                   "cg_path": "fused (K6f)" if cg_fused else "three-kernel",
-                   "cg_stop": "ReductionControl(10000, 1e-12, 1e-6)", "parallelism": f"strips{n_gpus}",
-                   "l2": "flushed between steps (256 MiB write)" if flush is not None else "not flushed",
-                   "setup_s": setup_s, "wall_s_timed_region": wall_s},
+        "config": workload_config(workload, params, scheme, n, args.precond),
+        "run": {"nnz_per_gpu": nnz, "cg_its_per_step": its_total / K,
+                "cg_path": "fused (K6f)" if cg_fused else "three-kernel", "parallelism": f"strips{n_gpus}",
+                "operator": "stencil tables + SELL-32" if info["stencil_rows"] else "SELL-32",
+                "l2": "flushed between steps (256 MiB write)" if flush is not None else "not flushed",
+                "setup_s": setup_s, "wall_s_timed_region": wall_s},
         "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
-        "roofline_at_scale": at_scale, "multigrid": multigrid, "cpu_baseline": cpu,
+        "extras": extras, "cpu_baseline": cpu,
         "cg": {"solves": cgs["solves"], "iterations": cgs["iterations"], "ms_total": cgs["ms_total"],
                "ms_per_iteration": cgs["ms_total"] / max(cgs["iterations"], 1)},
         "step_ms": {"min": min(step_ms), "max": max(step_ms)},
     }
     print(json.dumps(line), flush=True)
-    g.close()
     if world > 1:
         dist.destroy_process_group()
 

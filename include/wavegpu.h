@@ -85,6 +85,7 @@ typedef struct {
 } wave_config;
 
 #define WAVE_FLAG_FORCING_EVERY_STEP 1u /* assemble F even when it folds to 0 (as the reference) */
+#define WAVE_FLAG_NO_STENCIL 2u         /* keep every row in SELL form: no table-driven (matrix-free) rows */
 
 /* ---- life cycle ---------------------------------------------------------------------- */
 /* Fills a config with the reference's declared defaults (src/ParameterReader.cpp:39-105). */
@@ -203,6 +204,13 @@ int wave_timers(wave_ctx *ctx, double out_ms[6], int reset);
    read back the accumulated count and device milliseconds (roofline.achieved of bench.py is
    algorithmic bytes / (ms / launches) taken live inside the timed steps). */
 int wave_spmv_timing(wave_ctx *ctx, int on, double *launches, double *ms_total);
+/* The same for the three kernels of a CG iteration: slot 0 = SpMV A d (+ d.Ad), 1 = k_cg_update
+   (g += alpha Ad, h = D^-1 g, g.g, g.h), 2 = k_cg_direction (x += alpha d, d = beta d - h). */
+int wave_kernel_timing(wave_ctx *ctx, int on, double launches[3], double ms_total[3]);
+/* The operator behind SpMV (replaces TrilinosWrappers::SparseMatrix::vmult, src/WaveNewmark.cpp:139):
+   out = {rows served by the translation-invariant stencil tables (constant wave speed, structured mesh),
+   rows kept in SELL form, pattern entries of those rows, algorithmic bytes of one SpMV launch}. */
+int wave_operator_info(const wave_ctx *ctx, int64_t out[4]);
 /* 1 when this context runs its Jacobi-PCG solves as one cooperative kernel (experimental, selected
    with WAVE_CG_FUSED=1 in the environment of wave_setup when the problem fits on chip), else 0. */
 int wave_cg_fused_active(const wave_ctx *ctx);

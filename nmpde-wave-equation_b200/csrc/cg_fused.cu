@@ -1,4 +1,4 @@
-// cg_fused.cu -- see cg_fused.cuh.  Opt-in (WAVE_CG_FUSED=1); not yet run on a device.
+// cg_fused.cu -- see cg_fused.cuh.
 #include "cg_fused.cuh"
 
 #include <cooperative_groups.h>

@@ -75,6 +75,8 @@ struct Nccl {
 };
 Nccl g_nccl;
 
+constexpr uint32_t kFlagChild = 1u << 31;  // internal: a multigrid level created by mg_setup
+
 enum Phase { PH_RHS = 0, PH_BC, PH_CG, PH_UPDATE, PH_ENERGY, PH_OTHER, PH_COUNT };
 
 }  // namespace
@@ -126,6 +128,12 @@ struct wave_ctx {
     int64_t nnz_pad = 0;  // stored entries including padding
     Sell A{};
     double *M = nullptr, *K = nullptr, *S1 = nullptr, *S2 = nullptr;
+    // stencil operator (kernels.cuh): tables of M, K, SYS1, SYS2 (4 x kStencilKinds x kStencilMax), metadata,
+    // per-slice marks; stencil_rows = owned rows served by the tables, sell_nnz = entries of the other rows
+    double *st_tab = nullptr;
+    int32_t *st_meta = nullptr;
+    int2 *slice_info = nullptr;
+    int64_t stencil_rows = 0, sell_nnz = 0;
     double *dinv1 = nullptr, *dinv2 = nullptr;
     double *d0 = nullptr;  // [2]
 
@@ -179,10 +187,12 @@ struct wave_ctx {
     double phase_ms[PH_COUNT]{};
     cudaEvent_t ev[2 * PH_COUNT + 4]{};
     double cg_stats[4]{};
+    // live kernel timing inside the CG solves: slot 0 = SpMV (A d), 1 = k_cg_update, 2 = k_cg_direction
     bool spmv_timing = false;
     std::vector<cudaEvent_t> spmv_ev;  // pairs
+    std::vector<int> spmv_ev_tag;      // per pair: slot | iteration << 2
     size_t spmv_ev_used = 0;
-    double spmv_ms = 0.0, spmv_count = 0.0;
+    double kt_ms[3] = {0, 0, 0}, kt_count[3] = {0, 0, 0};
     double *flush_buf = nullptr;
     int64_t flush_n = 0;
 };
@@ -299,16 +309,19 @@ struct PhaseTimer {
     }
 };
 
-// resolve the recorded SpMV event pairs into (count, ms).  Only the first `valid_launches` pairs are
-// counted: launches enqueued after the solve converged return at once and must not dilute the average.
-void drain_spmv_events(wave_ctx *ctx, size_t valid_launches = (size_t)-1) {
+// resolve the recorded event pairs into per-slot (count, ms).  Only launches of iterations below
+// `valid_iterations` are counted: launches enqueued after the solve converged return at once and must not
+// dilute the averages.
+void drain_spmv_events(wave_ctx *ctx, int valid_iterations = 1 << 29) {
     if (!ctx->spmv_ev_used) return;
     cudaEventSynchronize(ctx->spmv_ev[ctx->spmv_ev_used - 1]);
-    for (size_t k = 0; k + 1 < ctx->spmv_ev_used && k / 2 < valid_launches; k += 2) {
+    for (size_t k = 0; k + 1 < ctx->spmv_ev_used; k += 2) {
+        const int tag = ctx->spmv_ev_tag[k / 2];
+        if ((tag >> 2) >= valid_iterations) continue;
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ctx->spmv_ev[k], ctx->spmv_ev[k + 1]) == cudaSuccess) {
-            ctx->spmv_ms += ms;
-            ctx->spmv_count += 1;
+            ctx->kt_ms[tag & 3] += ms;
+            ctx->kt_count[tag & 3] += 1;
         }
     }
     ctx->spmv_ev_used = 0;
@@ -316,9 +329,10 @@ void drain_spmv_events(wave_ctx *ctx, size_t valid_launches = (size_t)-1) {
 struct SpmvBracket {
     wave_ctx *ctx;
     bool on;
-    explicit SpmvBracket(wave_ctx *c) : ctx(c), on(c->spmv_timing) {
+    SpmvBracket(wave_ctx *c, int slot, int iteration) : ctx(c), on(c->spmv_timing) {
         if (!on) return;
-        if (ctx->spmv_ev_used + 2 > ctx->spmv_ev.size()) drain_spmv_events(ctx);
+        if (ctx->spmv_ev_used + 2 > ctx->spmv_ev.size()) { on = false; return; }  // full: skip, never drain mid-solve
+        ctx->spmv_ev_tag[ctx->spmv_ev_used / 2] = slot | (iteration << 2);
         cudaEventRecord(ctx->spmv_ev[ctx->spmv_ev_used], ctx->stream);
     }
     ~SpmvBracket() {
@@ -335,6 +349,22 @@ SpmvArgs spmv_base(wave_ctx *ctx) {
     a.counter = ctx->counter;
     a.pc = PeerComm{};  // peer exchange only inside the CG loop (cg_solve sets it)
     return a;
+}
+
+constexpr int kTabSize = kStencilKinds * kStencilMax;
+// the stencil table that belongs to a value array of `ctx` (null: none)
+const double *tab_of(const wave_ctx *ctx, const double *val) {
+    if (!ctx->st_tab || !val) return nullptr;
+    if (val == ctx->M) return ctx->st_tab;
+    if (val == ctx->K) return ctx->st_tab + kTabSize;
+    if (val == ctx->S1) return ctx->st_tab + 2 * kTabSize;
+    if (val == ctx->S2) return ctx->st_tab + 3 * kTabSize;
+    return nullptr;
+}
+// every SpMV of the library goes through here: `owner` is the context whose pattern and values are used
+void spmv(const wave_ctx *owner, const Launcher &l, SpmvArgs &a) {
+    for (auto &t : a.t) t.tab = tab_of(owner, t.val);
+    launch_spmv(l, a);
 }
 
 // SolverCG::solve (src/WaveNewmark.cpp:256-261): Jacobi-PCG on the BC-modified matrix `Sval`,
@@ -356,7 +386,7 @@ void mg_smooth(wave_ctx *ctx, MgLevel &lv, int sweeps, bool x_is_zero) {
         a.dinv = lv.dinv; a.jac_x = lv.x; a.jac_omega = lv.omega;
         a.y = lv.x2;
         a.skip_flag = skip;
-        launch_spmv(ctx->launcher, a);
+        spmv(c, ctx->launcher, a);
         std::swap(lv.x, lv.x2);
     }
 }
@@ -374,7 +404,7 @@ void mg_vcycle(wave_ctx *ctx, int l) {
         a.add0 = lv.b; a.addc0 = 1.0;
         a.y = lv.r;
         a.skip_flag = skip;
-        launch_spmv(ctx->launcher, a);
+        spmv(lv.c, ctx->launcher, a);
     }
     MgLevel &cv = m.lev[l + 1];
     const bool p_coarsening = lv.c->L.mesh.r == 2;
@@ -413,7 +443,7 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
         if (!use_mg) { a.dinv = dinv; a.h_out = ctx->h; a.d_out = ctx->d + L.own_off; }
         a.dot_mode = 2;
         a.result = &ctx->S->gg;
-        launch_spmv(l, a);
+        spmv(ctx, l, a);
     }
     if (use_mg) {  // h = V-cycle(g) ; d = -h ; gh = g.h
         const double *z = mg_apply(ctx, Sval, dinv, ctx->g);
@@ -477,13 +507,16 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
                                         : ctx->nslices;
             }
             {
-                SpmvBracket br(ctx);
-                launch_spmv(l, a);
+                SpmvBracket br(ctx, 0, enq + k);
+                spmv(ctx, l, a);
             }
             if (!p2p) RET(allreduce(ctx, &ctx->S->dAd, 1));
             const unsigned long long seq_b = p2p ? ++ctx->ar_seq : 0ull;
-            launch_cg_update(l, L.nown, ctx->S, ctx->g, ctx->h, use_mg ? nullptr : dinv, ctx->partials, ctx->counter,
-                             p2p ? ctx->pc : PeerComm{}, seq_b);
+            {
+                SpmvBracket br(ctx, 1, enq + k);
+                launch_cg_update(l, L.nown, ctx->S, ctx->g, ctx->h, use_mg ? nullptr : dinv, ctx->partials,
+                                 ctx->counter, p2p ? ctx->pc : PeerComm{}, seq_b);
+            }
             const double *z = ctx->h;
             if (use_mg) {  // h' = V-cycle(g) ; gh' = g.h'
                 z = mg_apply(ctx, Sval, dinv, ctx->g);
@@ -492,8 +525,11 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
             }
             if (!p2p) RET(allreduce(ctx, &ctx->S->gg, 2));
             const unsigned long long seq_h = p2p ? ++ctx->halo_seq : 0ull;
-            launch_cg_direction(l, L.nown, ctx->S, x + L.own_off, ctx->d + L.own_off, z, ctx->counter,
-                                p2p ? ctx->pc : PeerComm{}, seq_h);
+            {
+                SpmvBracket br(ctx, 2, enq + k);
+                launch_cg_direction(l, L.nown, ctx->S, x + L.own_off, ctx->d + L.own_off, z, ctx->counter,
+                                    p2p ? ctx->pc : PeerComm{}, seq_h);
+            }
         }
         enq += chunk;
         CK(cudaMemcpyAsync(ctx->hS, ctx->S, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
@@ -512,7 +548,7 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
         ctx->ar_seq += 2ull * (unsigned long long)ctx->hS->it;
         ctx->halo_seq += (unsigned long long)ctx->hS->it;
     }
-    if (ctx->spmv_timing) drain_spmv_events(ctx, (size_t)ctx->hS->it);
+    if (ctx->spmv_timing) drain_spmv_events(ctx, ctx->hS->it);
     ctx->prev_its[slot] = ctx->hS->it;
     ctx->cg_stats[0] += 1;
     ctx->cg_stats[1] += ctx->hS->it;
@@ -529,6 +565,9 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
 int build_system_matrix(wave_ctx *ctx, double s, double *out, double *dinv, double *d0) {
     const Launcher &l = ctx->launcher;
     launch_axpy_vals(l, ctx->nnz_pad, ctx->M, ctx->K, s, out);
+    if (ctx->st_tab)  // the same expression on the representative rows (Dirichlet rows are never stencil rows)
+        launch_axpy_vals(l, kTabSize, ctx->st_tab, ctx->st_tab + kTabSize, s,
+                         const_cast<double *>(tab_of(ctx, out)));
     launch_find_d0(l, ctx->L, ctx->A, out, d0);
     launch_bc_rows(l, ctx->L, ctx->nb, ctx->brow, ctx->A, out, d0);
     launch_dinv(l, ctx->L, ctx->A, out, ctx->cfg.precond == WAVE_PRECOND_NONE, dinv);
@@ -587,7 +626,7 @@ int newmark_step(wave_ctx *ctx, double t, int32_t iters[2], double norms[2]) {
         a.t[0] = {ctx->K, ctx->u, nullptr, 1.0, 0.0, -1.0};
         if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = fscale; }
         a.y = ctx->rhs;
-        launch_spmv(l, a);
+        spmv(ctx, l, a);
     }
     {
         PhaseTimer pt(ctx, PH_BC);
@@ -627,7 +666,7 @@ int theta_step(wave_ctx *ctx, double t, int32_t iters[2], double norms[2]) {
         a.t[1] = {ctx->K, ctx->u, nullptr, 1.0, 0.0, -dt * dt * th * (1 - th)};
         if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = th * dt * dt * fscale; }
         a.y = ctx->rhs;
-        launch_spmv(l, a);
+        spmv(ctx, l, a);
         launch_copy(l, L.nloc, ctx->u, ctx->unew);
     }
     {
@@ -648,7 +687,7 @@ int theta_step(wave_ctx *ctx, double t, int32_t iters[2], double norms[2]) {
         a.t[1] = {ctx->K, ctx->u, ctx->unew, 1.0 - th, th, -dt};
         if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = dt * fscale; }
         a.y = ctx->rhs;
-        launch_spmv(l, a);
+        spmv(ctx, l, a);
     }
     {
         PhaseTimer pt(ctx, PH_BC);
@@ -685,6 +724,13 @@ const double *mat_ptr(wave_ctx *ctx, int which) {
     case WAVE_MAT_SYS2: return ctx->S2;
     default: return nullptr;
     }
+}
+
+// algorithmic bytes of one SpMV launch: 12 B per entry + row map, x and y (20 B per row) for the rows kept in
+// SELL form; x and y only (16 B per row) for the rows served by the stencil tables
+double spmv_bytes(const wave_ctx *ctx) {
+    const double sell_rows = (double)(ctx->L.nown - ctx->stencil_rows);
+    return 12.0 * (double)ctx->sell_nnz + 20.0 * sell_rows + 16.0 * (double)ctx->stencil_rows;
 }
 
 int ensure_scratch(wave_ctx *ctx, int64_t n) {
@@ -769,8 +815,13 @@ int dev_alloc(wave_ctx *ctx, T **p, size_t count, bool zero = true) {
 int fused_plan(wave_ctx *ctx) {
     auto &f = ctx->fused;
     f.ok = false;
+    // default: on for a single rank whenever the rows fit on chip (measured on B200, c2: 32 us per iteration
+    // against 48 us of the three-kernel path); WAVE_CG_FUSED=0 switches it off, =1 also selects it for
+    // several ranks (over the NVLink mailboxes).  Multigrid levels (internal child contexts) never use it.
     const char *env = std::getenv("WAVE_CG_FUSED");
-    if (!env || std::atoi(env) == 0) return WAVE_OK;
+    const int want = env ? std::atoi(env) : -1;
+    if (want == 0 || (ctx->cfg.flags & kFlagChild)) return WAVE_OK;
+    if (ctx->cfg.nranks != 1 && want != 1) return WAVE_OK;
     if (ctx->cfg.precond != WAVE_PRECOND_JACOBI) return WAVE_OK;
     if (ctx->cfg.nranks != 1 && !ctx->pc.enabled) return WAVE_OK;  // several ranks: only over the NVLink mailboxes
     const int nwin = ctx->nslices / (kWindow / kSlice);
@@ -817,6 +868,41 @@ int fused_plan(wave_ctx *ctx) {
     return WAVE_OK;
 }
 
+// Detect the translation-invariant rows of M and K (kernels.cuh) and switch the SpMV of those slices to
+// the table-driven path.  Off with WAVE_FLAG_NO_STENCIL / WAVE_NO_STENCIL=1, on meshes too small to have a
+// generic middle quad, and when fewer than half of the rows match (variable wave speed).
+int stencil_setup(wave_ctx *ctx) {
+    const Layout &L = ctx->L;
+    const char *env = std::getenv("WAVE_NO_STENCIL");
+    if ((ctx->cfg.flags & WAVE_FLAG_NO_STENCIL) || (env && std::atoi(env) != 0)) return WAVE_OK;
+    if (L.mesh.nx < 8 || L.mesh.ny < 8) return WAVE_OK;
+    RET(dev_alloc(ctx, &ctx->st_tab, (size_t)4 * kTabSize));
+    RET(dev_alloc(ctx, &ctx->st_meta, (size_t)kTabSize + kStencilKinds));
+    RET(dev_alloc(ctx, &ctx->slice_info, (size_t)ctx->nslices, false));
+    DevTmp<int8_t> row_kind;
+    DevTmp<unsigned long long> counts;
+    RET(dev_alloc(ctx, &row_kind.p, (size_t)L.nown, false));
+    RET(dev_alloc(ctx, &counts.p, 2));
+    launch_stencil_tables(ctx->launcher, L, ctx->dprog + WAVE_EXPR_C, &ctx->q_asm, ctx->st_meta, ctx->st_tab,
+                          ctx->st_tab + kTabSize);
+    launch_stencil_classify(ctx->launcher, L, ctx->A, ctx->M, ctx->K, ctx->st_meta, ctx->st_tab,
+                            ctx->st_tab + kTabSize, row_kind.p, ctx->slice_info, counts.p);
+    unsigned long long h[2] = {0, 0};
+    CK(cudaMemcpyAsync(h, counts.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if ((int64_t)h[0] * kSlice * 2 < (int64_t)L.nown) {  // counts[0] counts slices
+        cudaFree(ctx->st_tab); ctx->st_tab = nullptr;
+        cudaFree(ctx->st_meta); ctx->st_meta = nullptr;
+        cudaFree(ctx->slice_info); ctx->slice_info = nullptr;
+        return WAVE_OK;
+    }
+    ctx->stencil_rows = (int64_t)h[0] * kSlice;
+    ctx->sell_nnz = (int64_t)h[1];
+    ctx->A.slice_info = ctx->slice_info;
+    ctx->A.st_meta = ctx->st_meta;
+    return WAVE_OK;
+}
+
 // Build the multigrid hierarchy for the scheme matrix bc(M + s K): [P2 on the mesh ->] P1 on the mesh ->
 // P1 on Nel/2, Nel/4, ... while the stiffness part still matters (s c^2 / (dx dy) > 1/4) and the mesh
 // halves evenly.  Every coarse level is a child context (pattern, rediscretised M and K, Dirichlet rows,
@@ -857,10 +943,14 @@ int mg_setup(wave_ctx *ctx, double s) {
         cfg.scheme = WAVE_SCHEME_NEWMARK;
         cfg.rank = 0; cfg.nranks = 1; cfg.nccl_unique_id = nullptr; cfg.device = -1;
         cfg.precond = WAVE_PRECOND_JACOBI;
-        cfg.flags = 0;
+        cfg.flags = kFlagChild | (ctx->cfg.flags & WAVE_FLAG_NO_STENCIL);
         cfg.stream = ctx->stream;
         wave_ctx *c = nullptr;
-        if (wave_create(&cfg, &c) != WAVE_OK) { delete m; return fail(ctx, WAVE_ERR_CUDA, wave_last_error(nullptr)); }
+        auto drop_levels = [&]() {
+            for (int l = 1; l < m->nlev; ++l) wave_destroy(m->lev[l].c);
+            delete m;
+        };
+        if (wave_create(&cfg, &c) != WAVE_OK) { drop_levels(); return fail(ctx, WAVE_ERR_CUDA, wave_last_error(nullptr)); }
         const Program zero = compile_expression("0.0", "x, y, t", "");
         for (int k = 0; k < WAVE_EXPR_SOLUTION; ++k) {
             c->hprog[k] = k == WAVE_EXPR_C ? ctx->hprog[k] : zero;
@@ -872,7 +962,7 @@ int mg_setup(wave_ctx *ctx, double s) {
         if (rc != WAVE_OK) {
             const std::string msg = std::string("multigrid level setup: ") + wave_last_error(c);
             wave_destroy(c);
-            delete m;
+            drop_levels();
             return fail(ctx, rc, msg);
         }
         MgLevel &lv = m->lev[m->nlev++];
@@ -1067,7 +1157,7 @@ void wave_destroy(wave_ctx *ctx) {
     for (void *q : {(void *)ctx->fused.blk_c0, (void *)ctx->fused.blk_cn, (void *)ctx->fused.partials,
                     (void *)ctx->fused.pub})
         if (q) cudaFree(q);
-    void *ptrs[] = {ctx->dprog, ctx->rowptr, ctx->slice_ptr, ctx->row_of, ctx->slot_of, ctx->col, ctx->c2i, ctx->i2c, ctx->tmp, ctx->M, ctx->K, ctx->S1, ctx->S2, ctx->dinv1, ctx->dinv2,
+    void *ptrs[] = {ctx->st_tab, ctx->st_meta, ctx->slice_info, ctx->dprog, ctx->rowptr, ctx->slice_ptr, ctx->row_of, ctx->slot_of, ctx->col, ctx->c2i, ctx->i2c, ctx->tmp, ctx->M, ctx->K, ctx->S1, ctx->S2, ctx->dinv1, ctx->dinv2,
                     ctx->d0, ctx->u, ctx->v, ctx->a, ctx->unew, ctx->d, ctx->rhs, ctx->fvec, ctx->cellvec, ctx->g, ctx->h,
                     ctx->scratch, ctx->brow, ctx->bx, ctx->by, ctx->partials, ctx->counter, ctx->S, ctx->res,
                     ctx->flush_buf};
@@ -1192,7 +1282,7 @@ int wave_setup(wave_ctx *ctx) {
     CK(cudaFree(slice_cnt));
     RET(dev_alloc(ctx, &ctx->col, (size_t)ctx->nnz_pad, false));
     ctx->A = Sell{ctx->slice_ptr, ctx->col, ctx->row_of, ctx->slot_of, ctx->rowptr, ctx->nslices, L.nown,
-                  L.mesh.r == 1 ? 7 : 10};
+                  L.mesh.r == 1 ? 7 : 10, L.own_off, nullptr, nullptr};
     launch_fill_int(l, ctx->nnz_pad, L.own_off, ctx->col);  // padding entries: a valid column, value 0
     launch_fill_cols(l, L, ctx->A, ctx->col);
 
@@ -1200,6 +1290,8 @@ int wave_setup(wave_ctx *ctx) {
     RET(dev_alloc(ctx, &ctx->M, (size_t)ctx->nnz_pad));
     RET(dev_alloc(ctx, &ctx->K, (size_t)ctx->nnz_pad));
     launch_assemble(l, L, ctx->dprog + WAVE_EXPR_C, &ctx->q_asm, ctx->A, ctx->M, ctx->K);
+    ctx->sell_nnz = ctx->nnz;
+    RET(stencil_setup(ctx));
 
     // ---- boundary list (closed form, host) --------------------------------------------------------
     {
@@ -1310,29 +1402,6 @@ int wave_setup(wave_ctx *ctx) {
     RET(sync_check(ctx));
     RET(setup_peer_exchange(ctx));
     RET(fused_plan(ctx));
-    // Experiment for problems whose matrix fits in L2 (opt-in, WAVE_L2_PERSIST=<MiB>): mark the values of
-    // the system matrix as persisting in L2 for the kernels of this stream, so the vector traffic of the
-    // CG iteration does not evict them between SpMVs.  Not measured yet.
-    if (const char *mb = std::getenv("WAVE_L2_PERSIST")) {
-        const size_t want = (size_t)std::max(0, std::atoi(mb)) << 20;
-        int dev = 0, max_persist = 0, max_window = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-        const size_t carve = std::min(want, (size_t)max_persist);
-        if (carve > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
-            cudaStreamAttrValue v{};
-            const size_t bytes = std::min((size_t)ctx->nnz_pad * sizeof(double), (size_t)max_window);
-            v.accessPolicyWindow.base_ptr = ctx->S1;
-            v.accessPolicyWindow.num_bytes = bytes;
-            v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)bytes);
-            v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            if (cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess)
-                cudaGetLastError();
-        } else
-            cudaGetLastError();
-    }
     ctx->is_setup = true;
     return WAVE_OK;
 }
@@ -1355,7 +1424,7 @@ int wave_init(wave_ctx *ctx) {
         a.t[0] = {ctx->K, ctx->u, nullptr, 1.0, 0.0, -1.0};
         if (ctx->forcing_active) { a.add0 = ctx->fvec; a.addc0 = fscale; }
         a.y = ctx->rhs;
-        launch_spmv(l, a);
+        spmv(ctx, l, a);
         launch_fill(l, L.nloc, 0.0, ctx->a);
         launch_bc_values(l, BC_SECOND_DIFF, ctx->nb, ctx->brow, ctx->bx, ctx->by, ctx->dprog + WAVE_EXPR_G, dt, dt, 0.0,
                          nullptr, ctx->a + L.own_off, ctx->rhs, ctx->d0);
@@ -1482,11 +1551,11 @@ int wave_energy(wave_ctx *ctx, double *out) {
     SpmvArgs a = spmv_base(ctx);
     a.t[0] = {ctx->K, ctx->u, nullptr, 1.0, 0.0, 1.0};
     a.dot_mode = 1; a.dotv = ctx->u + L.own_off; a.result = ctx->res + 2;
-    launch_spmv(ctx->launcher, a);
+    spmv(ctx, ctx->launcher, a);
     SpmvArgs b = spmv_base(ctx);
     b.t[0] = {ctx->M, ctx->v, nullptr, 1.0, 0.0, 1.0};
     b.dot_mode = 1; b.dotv = ctx->v + L.own_off; b.result = ctx->res + 3;
-    launch_spmv(ctx->launcher, b);
+    spmv(ctx, ctx->launcher, b);
     RET(allreduce(ctx, ctx->res + 2, 2));
     CK(cudaMemcpyAsync(ctx->hres + 2, ctx->res + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1610,7 +1679,7 @@ int wave_spmv(wave_ctx *ctx, int which, const double *x, double *y, size_t n) {
     SpmvArgs a = spmv_base(ctx);
     a.t[0] = {val, ctx->d, nullptr, 1.0, 0.0, 1.0};
     a.y = ctx->h;
-    launch_spmv(ctx->launcher, a);
+    spmv(ctx, ctx->launcher, a);
     RET(own_to_canonical(ctx, ctx->h, ctx->tmp));
     CK(cudaMemcpyAsync(y, ctx->tmp, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     return sync_check(ctx);
@@ -1654,14 +1723,14 @@ int wave_bench_spmv(wave_ctx *ctx, int which, int reps, int flush_l2, double *ms
     a.t[0] = {val, ctx->u, nullptr, 1.0, 0.0, 1.0};
     a.y = ctx->h;
     cudaEvent_t e0 = ctx->ev[2 * PH_COUNT + 2], e1 = ctx->ev[2 * PH_COUNT + 3];
-    for (int w = 0; w < 3; ++w) launch_spmv(ctx->launcher, a);
+    for (int w = 0; w < 3; ++w) spmv(ctx, ctx->launcher, a);
     CK(cudaStreamSynchronize(ctx->stream));
     double total = 0.0;
     if (flush_l2) {
         for (int r = 0; r < reps; ++r) {
             launch_flush_l2(ctx->launcher, ctx->flush_buf, ctx->flush_n);
             CK(cudaEventRecord(e0, ctx->stream));
-            launch_spmv(ctx->launcher, a);
+            spmv(ctx, ctx->launcher, a);
             CK(cudaEventRecord(e1, ctx->stream));
             CK(cudaEventSynchronize(e1));
             float ms = 0;
@@ -1670,7 +1739,7 @@ int wave_bench_spmv(wave_ctx *ctx, int which, int reps, int flush_l2, double *ms
         }
     } else {
         CK(cudaEventRecord(e0, ctx->stream));
-        for (int r = 0; r < reps; ++r) launch_spmv(ctx->launcher, a);
+        for (int r = 0; r < reps; ++r) spmv(ctx, ctx->launcher, a);
         CK(cudaEventRecord(e1, ctx->stream));
         CK(cudaEventSynchronize(e1));
         float ms = 0;
@@ -1678,7 +1747,7 @@ int wave_bench_spmv(wave_ctx *ctx, int which, int reps, int flush_l2, double *ms
         total = ms;
     }
     if (ms_avg) *ms_avg = total / reps;
-    if (bytes) *bytes = 12.0 * (double)ctx->nnz + 20.0 * (double)ctx->L.nown;
+    if (bytes) *bytes = spmv_bytes(ctx);
     return WAVE_OK;
 }
 
@@ -1694,7 +1763,7 @@ int wave_bench_cg_iter(wave_ctx *ctx, int which, int reps, double *ms_avg, doubl
     SpmvArgs a = spmv_base(ctx);
     a.t[0] = {val, ctx->d, nullptr, 1.0, 0.0, 1.0};
     a.y = ctx->rhs;
-    launch_spmv(ctx->launcher, a);
+    spmv(ctx, ctx->launcher, a);
     launch_zero_rows(ctx->launcher, ctx->nb, ctx->brow, ctx->rhs);  // x_B = 0 must satisfy the Dirichlet rows
     double ms_total = 0.0, its_total = 0.0;
     for (int r = 0; r < reps; ++r) {
@@ -1708,7 +1777,7 @@ int wave_bench_cg_iter(wave_ctx *ctx, int which, int reps, double *ms_avg, doubl
     }
     ctx->prev_its[0] = 0;
     if (ms_avg) *ms_avg = its_total > 0 ? ms_total / its_total : 0.0;
-    if (bytes) *bytes = 12.0 * (double)ctx->nnz + 100.0 * (double)L.nown;
+    if (bytes) *bytes = spmv_bytes(ctx) + 80.0 * (double)L.nown;
     return WAVE_OK;
 }
 
@@ -1727,19 +1796,29 @@ int wave_timers(wave_ctx *ctx, double out_ms[6], int reset) {
     }
     return WAVE_OK;
 }
-int wave_spmv_timing(wave_ctx *ctx, int on, double *launches, double *ms_total) {
+int wave_kernel_timing(wave_ctx *ctx, int on, double launches[3], double ms_total[3]) {
     if (!ctx) return WAVE_ERR_ARG;
     drain_spmv_events(ctx);
-    if (launches) *launches = ctx->spmv_count;
-    if (ms_total) *ms_total = ctx->spmv_ms;
+    for (int k = 0; k < 3; ++k) {
+        if (launches) launches[k] = ctx->kt_count[k];
+        if (ms_total) ms_total[k] = ctx->kt_ms[k];
+        ctx->kt_count[k] = 0.0;
+        ctx->kt_ms[k] = 0.0;
+    }
     if (on && ctx->spmv_ev.empty()) {
-        ctx->spmv_ev.resize(2048, nullptr);
+        ctx->spmv_ev.resize(16384, nullptr);
+        ctx->spmv_ev_tag.resize(ctx->spmv_ev.size() / 2, 0);
         for (auto &e : ctx->spmv_ev) CK(cudaEventCreate(&e));
     }
     ctx->spmv_timing = on != 0;
-    ctx->spmv_ms = 0.0;
-    ctx->spmv_count = 0.0;
     return WAVE_OK;
+}
+int wave_spmv_timing(wave_ctx *ctx, int on, double *launches, double *ms_total) {
+    double n[3] = {0, 0, 0}, ms[3] = {0, 0, 0};
+    const int rc = wave_kernel_timing(ctx, on, n, ms);
+    if (launches) *launches = n[0];
+    if (ms_total) *ms_total = ms[0];
+    return rc;
 }
 int wave_cg_stats(wave_ctx *ctx, double out[4], int reset) {
     if (!ctx) return WAVE_ERR_ARG;
@@ -1747,6 +1826,15 @@ int wave_cg_stats(wave_ctx *ctx, double out[4], int reset) {
         out[k] = ctx->cg_stats[k];
         if (reset) ctx->cg_stats[k] = 0.0;
     }
+    return WAVE_OK;
+}
+
+int wave_operator_info(const wave_ctx *ctx, int64_t out[4]) {
+    if (!ctx || !out) return WAVE_ERR_ARG;
+    out[0] = ctx->stencil_rows;
+    out[1] = ctx->L.nown - ctx->stencil_rows;
+    out[2] = ctx->sell_nnz;
+    out[3] = (int64_t)spmv_bytes(ctx);
     return WAVE_OK;
 }
 

@@ -412,6 +412,84 @@ __global__ void __launch_bounds__(128) k_assemble(Layout L, const Program *cprog
     }
 }
 
+// ---- stencil detection (see kernels.cuh) -------------------------------------------------------------
+// Representative rows: the entities of the mesh's middle quad, assembled by the row-gather code above.
+// The choice does not depend on the rank, so every rank holds bitwise identical tables.
+template <int R>
+__global__ void k_stencil_tables(Layout L, const Program *cprog, Quadrature Q, int32_t *st_meta, double *tabM,
+                                 double *tabK) {
+    const int kind = threadIdx.x;
+    const int nk = R == 1 ? 1 : kStencilKinds;
+    if (blockIdx.x != 0 || kind >= kStencilKinds) return;
+    if (kind >= nk) { st_meta[kStencilKinds * kStencilMax + kind] = 0; return; }
+    const int i = L.mesh.nx / 2, j = L.mesh.ny / 2;
+    int64_t cols[kMaxRow], icols[kMaxRow];
+    double Mrow[kMaxRow], Krow[kMaxRow];
+    const int n = build_row(L.mesh, i, j, kind, cols, icols);
+    assemble_row<R>(L.mesh, i, j, kind, cprog, Q, n, icols, Mrow, Krow);
+    const int64_t self = entity_dof_internal(L.mesh, i, j, kind);
+    st_meta[kStencilKinds * kStencilMax + kind] = n <= kStencilMax ? n : 0;
+    for (int k = 0; k < kStencilMax; ++k) {
+        const bool in = k < n && n <= kStencilMax;
+        st_meta[kind * kStencilMax + k] = in ? (int32_t)(icols[k] - self) : 0;
+        tabM[kind * kStencilMax + k] = in ? Mrow[k] : 0.0;
+        tabK[kind * kStencilMax + k] = in ? Krow[k] : 0.0;
+    }
+}
+// one thread per owned row: does it equal its kind's representative (offsets exactly, values to 1e-12)?
+__global__ void k_classify_rows(Layout L, Sell A, const double *__restrict__ M, const double *__restrict__ K,
+                                const int32_t *__restrict__ st_meta, const double *__restrict__ tabM,
+                                const double *__restrict__ tabK, int8_t *row_kind) {
+    const SlotRange s = owned_slots(L);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= slot_count(L, s)) return;
+    int i, j, kind;
+    decode_slot(L, s, t, i, j, kind);
+    const int64_t dof = entity_dof_internal(L.mesh, i, j, kind);
+    if (dof < L.row0 || dof >= L.row0 + L.nown) return;
+    const int row = (int)(dof - L.row0);
+    const int len = st_meta[kStencilKinds * kStencilMax + kind];
+    bool ok = len > 0 && !entity_on_boundary(L.mesh, i, j, kind) && (int)sell_row_len(A, row) == len;
+    if (ok) {
+        const uint32_t base = sell_row_base(A, row);
+        double mM = 0.0, mK = 0.0;
+        for (int k = 0; k < len; ++k) {
+            mM = fmax(mM, fabs(tabM[kind * kStencilMax + k]));
+            mK = fmax(mK, fabs(tabK[kind * kStencilMax + k]));
+        }
+        for (int k = 0; k < len && ok; ++k) {
+            const uint32_t q = base + kSlice * k;
+            ok = A.col[q] - (row + L.own_off) == st_meta[kind * kStencilMax + k] &&
+                 fabs(M[q] - tabM[kind * kStencilMax + k]) <= 1e-12 * mM &&
+                 fabs(K[q] - tabK[kind * kStencilMax + k]) <= 1e-12 * mK;
+        }
+    }
+    row_kind[row] = ok ? (int8_t)kind : (int8_t)-1;
+}
+// one warp per slice: all 32 rows present and of one matching kind -> stencil slice
+__global__ void k_classify_slices(Sell A, const int8_t *__restrict__ row_kind, int2 *slice_info,
+                                  unsigned long long *counts) {
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (s >= A.nslices) return;
+    const int r = A.row_of[s * kSlice + lane];
+    const int k = r >= 0 ? (int)row_kind[r] : -1;
+    const int k0 = __shfl_sync(kFull, k, 0), r0 = __shfl_sync(kFull, r, 0);
+    const bool same = __all_sync(kFull, k == k0 && k >= 0);
+    const bool consecutive = __all_sync(kFull, r == r0 + lane);
+    unsigned nnz = (!same && r >= 0) ? sell_row_len(A, r) : 0u;
+    unsigned rows = same ? 1u : 0u;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        nnz += __shfl_down_sync(kFull, nnz, off);
+        rows += __shfl_down_sync(kFull, rows, off);
+    }
+    if (lane == 0) {
+        slice_info[s] = make_int2(same ? k0 : -1, consecutive ? r0 : -1);
+        if (rows) atomicAdd(&counts[0], (unsigned long long)rows);
+        if (nnz) atomicAdd(&counts[1], (unsigned long long)nnz);
+    }
+}
+
 // ---- K2: matrix_a = M + s K on the shared pattern (src/WaveNewmark.cpp:111-112) --------------------
 __global__ void __launch_bounds__(kThreads) k_axpy_vals(int64_t nnz, const double *__restrict__ M,
                                                         const double *__restrict__ K, double s,
@@ -562,11 +640,28 @@ __device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
 
 template <int NT, bool TWOX, int CH, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) k_spmv(SpmvArgs a) {
+    __shared__ double s_tab[NT][kStencilKinds * kStencilMax];
+    __shared__ int s_meta[kStencilKinds * kStencilMax + kStencilKinds];
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
     if (a.skip_flag && *a.skip_flag != 0) return;
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (kThreads / 32);
+    // stencil slices take their column offsets and values from the tables (kernels.cuh); all terms of the
+    // launch must have one
+    bool stencil = a.A.slice_info != nullptr;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) stencil = stencil && a.t[t].tab != nullptr;
+    if (stencil) {
+        for (int k = threadIdx.x; k < kStencilKinds * kStencilMax + kStencilKinds; k += kThreads) {
+            s_meta[k] = a.A.st_meta[k];
+            if (k < kStencilKinds * kStencilMax) {
+#pragma unroll
+                for (int t = 0; t < NT; ++t) s_tab[t][k] = a.t[t].tab[k];
+            }
+        }
+        __syncthreads();
+    }
     double dots[2] = {0.0, 0.0};
     // Persistent warps, grid-stride over slices.  Per chunk a lane issues CH col loads and CH*NT val
     // loads back to back (unconditional: a short tail re-reads the row's last entry and is masked out
@@ -582,10 +677,12 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmv(SpmvArgs a) {
     int slice = it + rot < a.A.nslices ? it + rot : it + rot - a.A.nslices;
     uint32_t b = 0, e = 0;
     int r = -1;
+    int2 si = make_int2(-1, -1);
     if (it < a.A.nslices) {
+        if (stencil) si = a.A.slice_info[slice];
         b = a.A.slice_ptr[slice];
         e = a.A.slice_ptr[slice + 1];
-        r = a.A.row_of[slice * kSlice + lane];
+        r = si.y >= 0 ? si.y + lane : a.A.row_of[slice * kSlice + lane];
     }
     while (it < a.A.nslices) {
         // metadata of this warp's next slice, requested before the long-latency work below
@@ -593,10 +690,12 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmv(SpmvArgs a) {
         const int nslice = nit + rot < a.A.nslices ? nit + rot : nit + rot - a.A.nslices;
         uint32_t nb = 0, ne = 0;
         int nr = -1;
+        int2 nsi = make_int2(-1, -1);
         if (nit < a.A.nslices) {
+            if (stencil) nsi = a.A.slice_info[nslice];
             nb = a.A.slice_ptr[nslice];
             ne = a.A.slice_ptr[nslice + 1];
-            nr = a.A.row_of[nslice * kSlice + lane];
+            nr = nsi.y >= 0 ? nsi.y + lane : a.A.row_of[nslice * kSlice + lane];
         }
         const bool ghosty = a.pc.enabled && (slice < a.ghost_lo_slices || slice >= a.ghost_hi_slice0);
         if (ghosty && !halo_ready) {  // warp-uniform
@@ -610,19 +709,32 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmv(SpmvArgs a) {
             __syncwarp();
             halo_ready = true;
         }
-        const int len = (int)((e - b) >> 5);
+        const int kind = si.x;  // warp-uniform; >= 0: every lane holds a row of that kind
+        const int len = kind >= 0 ? s_meta[kStencilKinds * kStencilMax + kind] : (int)((e - b) >> 5);
         const uint32_t base = b + lane;
+        const int cself = r + a.A.own_off;
+        const int tb = kind * kStencilMax;
         double s = 0.0;
         for (int k0 = 0; k0 < len; k0 += CH) {
             int c[CH];
             double v[NT][CH], x[NT][CH];
+            if (kind >= 0) {
 #pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                const int kk = min(k0 + k, len - 1);
-                const uint32_t q = base + (uint32_t)kk * kSlice;
-                c[k] = ld_stream(&a.A.col[q]);
+                for (int k = 0; k < CH; ++k) {
+                    const int kk = min(k0 + k, len - 1);
+                    c[k] = cself + s_meta[tb + kk];
 #pragma unroll
-                for (int t = 0; t < NT; ++t) v[t][k] = ld_stream(&a.t[t].val[q]);
+                    for (int t = 0; t < NT; ++t) v[t][k] = s_tab[t][tb + kk];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < CH; ++k) {
+                    const int kk = min(k0 + k, len - 1);
+                    const uint32_t q = base + (uint32_t)kk * kSlice;
+                    c[k] = ld_stream(&a.A.col[q]);
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) v[t][k] = ld_stream(&a.t[t].val[q]);
+                }
             }
 #pragma unroll
             for (int k = 0; k < CH; ++k)
@@ -659,7 +771,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmv(SpmvArgs a) {
             if (a.dot_mode == 1) dots[0] += s * a.dotv[r];
             else if (a.dot_mode == 2) { dots[0] += s * s; dots[1] += s * hv; }
         }
-        it = nit; slice = nslice; b = nb; e = ne; r = nr;
+        it = nit; slice = nslice; b = nb; e = ne; r = nr; si = nsi;
     }
     if (a.dot_mode) {
         if (grid_sum_peers<2>(dots, a.partials, a.counter, a.pc, a.ar_seq) && threadIdx.x == 0) {
@@ -1080,6 +1192,19 @@ void launch_assemble(const Launcher &l, const Layout &L, const Program *c, const
     const int64_t n = slot_count(L, owned_slots(L));
     if (L.mesh.r == 1) WV_LAUNCH(l, k_assemble<1>, blocks_for(n, 128), 128, 0, L, c, *q, A, M, K);
     else WV_LAUNCH(l, k_assemble<2>, blocks_for(n, 128), 128, 0, L, c, *q, A, M, K);
+}
+void launch_stencil_tables(const Launcher &l, const Layout &L, const Program *c, const Quadrature *q, int32_t *st_meta,
+                           double *tabM, double *tabK) {
+    if (L.mesh.r == 1) WV_LAUNCH(l, k_stencil_tables<1>, 1, 32, 0, L, c, *q, st_meta, tabM, tabK);
+    else WV_LAUNCH(l, k_stencil_tables<2>, 1, 32, 0, L, c, *q, st_meta, tabM, tabK);
+}
+void launch_stencil_classify(const Launcher &l, const Layout &L, const Sell &A, const double *M, const double *K,
+                             const int32_t *st_meta, const double *tabM, const double *tabK, int8_t *row_kind,
+                             int2 *slice_info, unsigned long long *counts) {
+    const int64_t n = slot_count(L, owned_slots(L));
+    WV_LAUNCH(l, k_classify_rows, blocks_for(n, 128), 128, 0, L, A, M, K, st_meta, tabM, tabK, row_kind);
+    WV_LAUNCH(l, k_classify_slices, blocks_for((int64_t)A.nslices * 32, kThreads), kThreads, 0, A, row_kind, slice_info,
+              counts);
 }
 void launch_axpy_vals(const Launcher &l, int64_t nnz, const double *M, const double *K, double s, double *out) {
     WV_LAUNCH(l, k_axpy_vals, stream_blocks(nnz), kThreads, 0, nnz, M, K, s, out);

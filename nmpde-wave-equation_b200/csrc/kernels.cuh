@@ -47,6 +47,19 @@ constexpr int kMaxRow = 40;
 // All four value arrays (M, K, SYS1, SYS2) share this one pattern.
 constexpr int kSlice = 32;
 constexpr int kWindow = 1024;
+// ---- translation-invariant rows: the matrix-free ("stencil") operator -------------------------------
+// On the structured mesh with a constant wave speed almost every row of M, K and M + sK is a translate
+// of one of at most four rows (P1: the vertex row; P2: vertex, horizontal-, vertical-, diagonal-edge
+// rows): the same column offsets in storage numbering, in the same (ascending canonical column) order,
+// with the same values.  wave_setup detects this numerically (stencil_setup in ctx.cu): a representative
+// row per kind is assembled by the same row-gather code, every assembled row is compared with it
+// (offsets exactly, values to 1e-12 of the row's largest entry), and a slice whose 32 rows all match one
+// kind is marked.  k_spmv then takes the column offsets and values of such a slice from a 4 x 20 table in
+// shared memory instead of streaming 12 B per entry from HBM; the other slices (boundary rows, the first
+// two DoF lines, rows next to the first quad of a line) and every matrix with variable c keep the SELL
+// arrays.  The sum of a row runs over the same entries in the same order with the same arithmetic.
+constexpr int kStencilMax = 20;  // entries of the longest translation-invariant row (P2 vertex row: 19)
+constexpr int kStencilKinds = 4;
 struct Sell {
     const uint32_t *slice_ptr;  // nslices + 1, element offsets (multiples of 32)
     const int32_t *col;         // padded local column indices (padding: a valid column, value 0)
@@ -55,6 +68,12 @@ struct Sell {
     const uint32_t *rowptr;     // CSR row pointer (nown + 1) of the unpadded pattern
     int nslices, nrows;
     int chunk;                  // entries a lane keeps in flight: 7 (P1) or 10 (P2)
+    int own_off;                // local column of owned row 0
+    // stencil operator (null: none).  slice_info[s] = (kind or -1, first row or -1 when the slice's rows
+    // are not consecutive); st_meta = kStencilKinds x kStencilMax column offsets, then the kStencilKinds
+    // row lengths
+    const int2 *slice_info;
+    const int32_t *st_meta;
 };
 
 // device-resident CG state (deal.II SolverCG + ReductionControl, src/WaveNewmark.cpp:256-261)
@@ -93,6 +112,7 @@ struct SpmvTerm {
     const double *val;
     const double *xa, *xb;  // local-layout vectors; x = ca*xa + cb*xb
     double ca, cb, coef;
+    const double *tab;      // kStencilKinds x kStencilMax values of the translation-invariant rows (or null)
 };
 struct SpmvArgs {
     Sell A;
@@ -138,6 +158,13 @@ void launch_fill_int(const Launcher &, int64_t n, int32_t value, int32_t *dst);
 void launch_fill_cols(const Launcher &, const Layout &, const Sell &A, int32_t *col);
 void launch_assemble(const Launcher &, const Layout &, const Program *c, const Quadrature *q, const Sell &A,
                      double *M, double *K);
+// stencil detection: representative rows (one per kind) -> tables; per-row and per-slice classification.
+// counts[0] = rows served by the tables, counts[1] = pattern entries of the other rows
+void launch_stencil_tables(const Launcher &, const Layout &, const Program *c, const Quadrature *q, int32_t *st_meta,
+                           double *tabM, double *tabK);
+void launch_stencil_classify(const Launcher &, const Layout &, const Sell &A, const double *M, const double *K,
+                             const int32_t *st_meta, const double *tabM, const double *tabK, int8_t *row_kind,
+                             int2 *slice_info, unsigned long long *counts);
 void launch_axpy_vals(const Launcher &, int64_t nnz, const double *M, const double *K, double s, double *out);
 void launch_find_d0(const Launcher &, const Layout &, const Sell &A, const double *val, double *d0);
 void launch_bc_rows(const Launcher &, const Layout &, int nb, const int32_t *brow, const Sell &A, double *val,

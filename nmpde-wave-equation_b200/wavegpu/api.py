@@ -14,6 +14,7 @@ VEC_U, VEC_V, VEC_A, VEC_RHS = 0, 1, 2, 3
 MAT_M, MAT_K, MAT_SYS1, MAT_SYS2 = 0, 1, 2, 3
 SCHEME_NEWMARK, SCHEME_THETA = 0, 1
 FLAG_FORCING_EVERY_STEP = 1
+FLAG_NO_STENCIL = 2
 PRECOND_JACOBI, PRECOND_NONE, PRECOND_MG = 0, 1, 2
 
 STATUS = {0: "WAVE_OK", -1: "WAVE_ERR_ARG", -2: "WAVE_ERR_EXPR", -3: "WAVE_ERR_CUDA", -4: "WAVE_ERR_STATE",
@@ -97,6 +98,7 @@ def lib():
         L.wave_quadrature.argtypes = [C.c_int32, dp, dp, dp]
         L.wave_device_count.argtypes = []
         L.wave_cg_fused_active.argtypes = [vp]
+        L.wave_operator_info.argtypes = [vp, lp]
         L.wave_spmv.argtypes = [vp, C.c_int, dp, dp, C.c_size_t]
         L.wave_cg.argtypes = [vp, C.c_int, dp, dp, C.c_size_t, ip]
         L.wave_bench_spmv.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp]
@@ -105,6 +107,7 @@ def lib():
         L.wave_timers.argtypes = [vp, dp, C.c_int]
         L.wave_cg_stats.argtypes = [vp, dp, C.c_int]
         L.wave_spmv_timing.argtypes = [vp, C.c_int, dp, dp]
+        L.wave_kernel_timing.argtypes = [vp, C.c_int, dp, dp]
         L.wave_partition_plan.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.POINTER(WavePartition)]
         _lib = L
@@ -239,6 +242,12 @@ class WaveSolver:
 
     def cg_fused_active(self):
         return bool(self.L.wave_cg_fused_active(self.h))
+
+    def operator_info(self):
+        """{'stencil_rows', 'sell_rows', 'sell_nnz', 'spmv_bytes'} of this rank's operator."""
+        out = (C.c_int64 * 4)()
+        self._ck(self.L.wave_operator_info(self.h, out))
+        return dict(stencil_rows=out[0], sell_rows=out[1], sell_nnz=out[2], spmv_bytes=out[3])
 
     def close(self):
         if getattr(self, "h", None):
@@ -386,6 +395,12 @@ class WaveSolver:
         cnt, ms = C.c_double(), C.c_double()
         self._ck(self.L.wave_spmv_timing(self.h, int(on), C.byref(cnt), C.byref(ms)))
         return cnt.value, ms.value
+
+    def kernel_timing(self, on):
+        """Live bracketing of the CG kernels; returns ([launches] * 3, [ms] * 3) for SpMV, update, direction."""
+        cnt, ms = (C.c_double * 3)(), (C.c_double * 3)()
+        self._ck(self.L.wave_kernel_timing(self.h, int(on), cnt, ms))
+        return list(cnt), list(ms)
 
     def cg_stats(self, reset=False):
         out = (C.c_double * 4)()

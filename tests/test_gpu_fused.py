@@ -1,9 +1,6 @@
-"""Parity of the experimental fused CG kernel (csrc/cg_fused.cu, WAVE_CG_FUSED=1) against the oracle and
-against the three-kernel iteration.  The kernel was written after round 1's GPU budget was spent and has
-not run on a device yet, so these tests only run on request:
-
-    WAVE_TEST_FUSED=1 timeout 300 python -m pytest tests/test_gpu_fused.py -x -q
-"""
+"""Parity of the fused CG kernel K6f (csrc/cg_fused.cu: a whole Jacobi-PCG solve as one cooperative
+kernel) against the oracle and against the three-kernel iteration.  K6f is the default on one GPU whenever
+the rows fit on chip (WAVE_CG_FUSED=0 switches it off, =1 also selects it for several ranks)."""
 import os
 
 import numpy as np
@@ -12,8 +9,7 @@ import pytest
 from oracle import oracle as O
 from wavegpu import WaveSolver, api, problem
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("WAVE_TEST_FUSED"), reason="experimental: set WAVE_TEST_FUSED=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture

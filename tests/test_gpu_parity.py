@@ -162,9 +162,13 @@ def _march(p, scheme, nsteps, cg=None, check_every=1):
     ("traveling-square-bump", "newmark", dict(Nel="30, 10")),
     ("square-bump", "theta", dict(Nel="20")),
 ])
-def test_time_stepping_parity(name, scheme, over):
+@pytest.mark.parametrize("cg_path", ["auto", "three-kernel"])
+def test_time_stepping_parity(name, scheme, over, cg_path, monkeypatch):
     """Reference stopping rule ReductionControl(10000, 1e-12, 1e-6): same iteration counts and
-    solution vectors within 1e-10 relative of the oracle's."""
+    solution vectors within 1e-10 relative of the oracle's -- with the default CG path (the cooperative
+    kernel K6f at these sizes) and with the three-kernel iteration."""
+    if cg_path == "three-kernel":
+        monkeypatch.setenv("WAVE_CG_FUSED", "0")
     p = problem(name, **over)
     o, g, worst, its_equal = _march(p, scheme, 25)
     assert worst < 1e-10, worst
