@@ -129,7 +129,7 @@ __device__ __forceinline__ void peer_allsum(const PeerComm &pc, unsigned long lo
                 if (!ok) t = __longlong_as_double(0x7ff8000000000000LL);
                 if (lane == 0) put_tagged(&mine[2 * k], t, tag);
             }
-            if (!ok && lane == 0) *pc.status = 3;
+            if (!ok && lane == 0) *pc.status = 1;
         }
         if (lane == 0) {
 #pragma unroll
@@ -188,10 +188,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_cg_fused(CgFusedArgs a) {
     const int diag0 = a.own_off - c0;                          // staged index of row r's own column = diag0 + r
 
     // scalars of the recurrences: carried redundantly, and identically, by every thread of the grid
-    double gh_old = a.S->gh_old, gh_new = a.S->gh_new, gg = a.S->gg, res = a.S->res, dAd = 0.0;
+    double gh_old = a.S->gh[0], gh_new = a.S->gh_new, gg = a.S->gg, res = a.S->res, dAd = 0.0;
     const double reduced_tol = a.S->reduced_tol, tol = a.S->tol;
     const int maxit = a.S->maxit;
-    int it = a.S->it, status = a.S->status;
+    int it = a.S->it, status = a.S->status[0];
     if (status != 0) return;  // the start residual already met the criterion (same answer in every block)
 
     int rk[kFusedMaxWin];
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_cg_fused(CgFusedArgs a) {
                 bool ok = true;
                 while (ok && reads_lo_ghost && ld_acquire_sys(&box->halo_flag[0]) < want) ok = clock64() - t0 < kPeerWait;
                 while (ok && reads_hi_ghost && ld_acquire_sys(&box->halo_flag[1]) < want) ok = clock64() - t0 < kPeerWait;
-                if (!ok) *a.pc.status = 3;  // the sums stay global, so every block still takes the same branches
+                if (!ok) *a.pc.status = 1;  // the sums stay global, so every block still takes the same branches
             }
             __syncthreads();
         }
@@ -312,10 +312,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_cg_fused(CgFusedArgs a) {
     if (blockIdx.x == 0 && tid == 0) {
         a.S->it = it;
         a.S->res = res;
-        a.S->status = (PEERS && __ldcg(a.pc.status) == 3) ? 3 : status;  // a peer wait timed out somewhere
+        a.S->status[0] = status;  // a peer wait that timed out is recorded in CgScalars::peer_timeout
         a.S->gg = gg;
         a.S->gh_new = gh_new;
-        a.S->gh_old = gh_old;
+        a.S->gh[0] = gh_old;
         a.S->dAd = dAd;
     }
 }

@@ -133,6 +133,9 @@ struct wave_ctx {
     double *st_tab = nullptr;
     int32_t *st_meta = nullptr;
     int2 *slice_info = nullptr;
+    int32_t *sell_list = nullptr, *st_order = nullptr;
+    std::vector<int32_t> h_st_meta;  // host copies: the launches pass them as kernel parameters
+    std::vector<double> h_tab;
     int64_t stencil_rows = 0, sell_nnz = 0;
     double *dinv1 = nullptr, *dinv2 = nullptr;
     double *d0 = nullptr;  // [2]
@@ -152,7 +155,7 @@ struct wave_ctx {
     std::vector<int32_t> h_bdof_global;  // all boundary DoFs (global ids, sorted)
 
     // reductions / CG state
-    double *partials = nullptr;
+    double *partials = nullptr, *partials2 = nullptr, *partials3 = nullptr;  // SpMV / update / other sums
     unsigned *counter = nullptr;
     CgScalars *S = nullptr;
     CgScalars *hS = nullptr;  // pinned
@@ -352,14 +355,18 @@ SpmvArgs spmv_base(wave_ctx *ctx) {
 }
 
 constexpr int kTabSize = kStencilKinds * kStencilMax;
-// the stencil table that belongs to a value array of `ctx` (null: none)
+// which stencil table belongs to a value array of `ctx` (-1: none), and its host copy
+int tab_index(const wave_ctx *ctx, const double *val) {
+    if (!ctx->st_tab || !val) return -1;
+    if (val == ctx->M) return 0;
+    if (val == ctx->K) return 1;
+    if (val == ctx->S1) return 2;
+    if (val == ctx->S2) return 3;
+    return -1;
+}
 const double *tab_of(const wave_ctx *ctx, const double *val) {
-    if (!ctx->st_tab || !val) return nullptr;
-    if (val == ctx->M) return ctx->st_tab;
-    if (val == ctx->K) return ctx->st_tab + kTabSize;
-    if (val == ctx->S1) return ctx->st_tab + 2 * kTabSize;
-    if (val == ctx->S2) return ctx->st_tab + 3 * kTabSize;
-    return nullptr;
+    const int k = tab_index(ctx, val);
+    return k < 0 || ctx->h_tab.empty() ? nullptr : ctx->h_tab.data() + (size_t)k * kTabSize;
 }
 // every SpMV of the library goes through here: `owner` is the context whose pattern and values are used
 void spmv(const wave_ctx *owner, const Launcher &l, SpmvArgs &a) {
@@ -370,9 +377,8 @@ void spmv(const wave_ctx *owner, const Launcher &l, SpmvArgs &a) {
 // SolverCG::solve (src/WaveNewmark.cpp:256-261): Jacobi-PCG on the BC-modified matrix `Sval`,
 // start vector x (local layout), right-hand side b (row-indexed).
 // V-cycle on level l: lev.x <- approximate solution of S x = lev.b from x = 0 (all launches asynchronous)
-void mg_smooth(wave_ctx *ctx, MgLevel &lv, int sweeps, bool x_is_zero) {
+void mg_smooth(wave_ctx *ctx, MgLevel &lv, int sweeps, bool x_is_zero, const int *skip) {
     wave_ctx *c = lv.c;
-    const int *skip = &ctx->S->status;
     for (int sw = 0; sw < sweeps; ++sw) {
         if (sw == 0 && x_is_zero) {
             launch_scale_rows(ctx->launcher, c->L.nown, lv.omega, lv.dinv, lv.b, lv.x, skip);
@@ -390,12 +396,11 @@ void mg_smooth(wave_ctx *ctx, MgLevel &lv, int sweeps, bool x_is_zero) {
         std::swap(lv.x, lv.x2);
     }
 }
-void mg_vcycle(wave_ctx *ctx, int l) {
+void mg_vcycle(wave_ctx *ctx, int l, const int *skip) {
     Mg &m = *ctx->mg;
     MgLevel &lv = m.lev[l];
-    const int *skip = &ctx->S->status;
-    if (l == m.nlev - 1) { mg_smooth(ctx, lv, m.nu_coarse, true); return; }
-    mg_smooth(ctx, lv, m.nu, true);
+    if (l == m.nlev - 1) { mg_smooth(ctx, lv, m.nu_coarse, true, skip); return; }
+    mg_smooth(ctx, lv, m.nu, true, skip);
     {   // r = b - S x
         SpmvArgs a = spmv_base(lv.c);
         a.partials = ctx->partials;
@@ -410,18 +415,18 @@ void mg_vcycle(wave_ctx *ctx, int l) {
     const bool p_coarsening = lv.c->L.mesh.r == 2;
     if (p_coarsening) launch_restrict_p2p1(ctx->launcher, lv.c->L, cv.c->L, lv.r, cv.b, skip);
     else launch_restrict_p1(ctx->launcher, lv.c->L, cv.c->L, lv.r, cv.b, skip);
-    mg_vcycle(ctx, l + 1);
+    mg_vcycle(ctx, l + 1, skip);
     if (p_coarsening) launch_prolong_add_p2p1(ctx->launcher, lv.c->L, cv.c->L, cv.x, lv.x, skip);
     else launch_prolong_add_p1(ctx->launcher, lv.c->L, cv.c->L, cv.x, lv.x, skip);
-    mg_smooth(ctx, lv, m.nu, false);
+    mg_smooth(ctx, lv, m.nu, false, skip);
 }
 // z = V-cycle(g) on the fine level; returns the vector holding z
-const double *mg_apply(wave_ctx *ctx, const double *Sval, const double *dinv, const double *g) {
+const double *mg_apply(wave_ctx *ctx, const double *Sval, const double *dinv, const double *g, const int *skip) {
     MgLevel &f = ctx->mg->lev[0];
     f.S = Sval;
     f.dinv = dinv;
     f.b = const_cast<double *>(g);
-    mg_vcycle(ctx, 0);
+    mg_vcycle(ctx, 0, skip);
     return f.x;
 }
 
@@ -433,7 +438,7 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
     cudaEvent_t e0 = ctx->ev[2 * PH_COUNT], e1 = ctx->ev[2 * PH_COUNT + 1];
     CK(cudaEventRecord(e0, ctx->stream));
     // the status of the previous solve must not gate the kernels of this one (V-cycle before k_cg_start)
-    CK(cudaMemsetAsync(&ctx->S->status, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->S->status, 0, 2 * sizeof(int), ctx->stream));
     RET(halo_exchange(ctx, x));
     {   // g = A x - b ; h = D^-1 g ; d = -h ; gg, gh
         SpmvArgs a = spmv_base(ctx);
@@ -446,7 +451,7 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
         spmv(ctx, l, a);
     }
     if (use_mg) {  // h = V-cycle(g) ; d = -h ; gh = g.h
-        const double *z = mg_apply(ctx, Sval, dinv, ctx->g);
+        const double *z = mg_apply(ctx, Sval, dinv, ctx->g, &ctx->S->status[0]);
         launch_dot_gz(l, L.nown, ctx->g, z, ctx->d + L.own_off, ctx->partials, ctx->counter, &ctx->S->gh_new, nullptr);
     }
     RET(allreduce(ctx, &ctx->S->gg, 2));
@@ -483,10 +488,16 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
     int chunk = ctx->prev_its[slot] > 0 ? ctx->prev_its[slot] : 4;
     const int maxit = ctx->hS->maxit;
     if (fused) chunk = 0;
+    // where the sums of an iteration travel: per-block partials summed by the consumer kernel on one rank,
+    // the NVLink mailboxes for 2..8 ranks, NCCL all-reduces of the scalars otherwise
+    const bool p2p = ctx->pc.enabled != 0;
+    const int sum_mode = p2p ? SUM_MAILBOX : (ctx->cfg.nranks > 1 ? SUM_SCALAR : SUM_PARTIALS);
+    const int nvec_blocks = cg_vector_blocks(L.nown);
+    double *p1 = ctx->partials, *p2 = ctx->partials2;
     for (;;) {
         for (int k = 0; k < chunk; ++k) {
-            const bool p2p = ctx->pc.enabled != 0;
-            const bool first_it = (enq + k) == 0;
+            const int it = enq + k, parity = it & 1;
+            const bool first_it = it == 0;
             // halo of d: NCCL for the first iteration (d comes from the residual kernel), afterwards the
             // neighbours' k_cg_direction wrote it into the ghost blocks and raised halo flag `halo_seq`
             if (!p2p || first_it) RET(halo_exchange(ctx, ctx->d));
@@ -495,8 +506,10 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
             a.y = ctx->h;
             a.dot_mode = 1;
             a.dotv = ctx->d + L.own_off;
-            a.result = &ctx->S->dAd;
-            a.skip_flag = &ctx->S->status;
+            a.skip_flag = &ctx->S->status[parity];
+            a.partials = p1;
+            if (sum_mode == SUM_SCALAR) a.result = &ctx->S->dAd;
+            else a.dot_publish = 1;
             if (p2p) {
                 a.pc = ctx->pc;
                 a.ar_seq = ++ctx->ar_seq;
@@ -506,36 +519,39 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
                                         ? ((L.nown - ctx->pc.hi_count) / kWindow) * (kWindow / kSlice)
                                         : ctx->nslices;
             }
+            for (auto &t : a.t) t.tab = tab_of(ctx, t.val);
+            const CgSumIo in1{sum_mode, p1, spmv_launch_blocks(a), 2, a.ar_seq};
             {
-                SpmvBracket br(ctx, 0, enq + k);
-                spmv(ctx, l, a);
+                SpmvBracket br(ctx, 0, it);
+                launch_spmv(l, a);
             }
-            if (!p2p) RET(allreduce(ctx, &ctx->S->dAd, 1));
+            if (sum_mode == SUM_SCALAR) RET(allreduce(ctx, &ctx->S->dAd, 1));
             const unsigned long long seq_b = p2p ? ++ctx->ar_seq : 0ull;
             {
-                SpmvBracket br(ctx, 1, enq + k);
-                launch_cg_update(l, L.nown, ctx->S, ctx->g, ctx->h, use_mg ? nullptr : dinv, ctx->partials,
-                                 ctx->counter, p2p ? ctx->pc : PeerComm{}, seq_b);
+                SpmvBracket br(ctx, 1, it);
+                launch_cg_update(l, L.nown, parity, ctx->S, ctx->g, ctx->h, use_mg ? nullptr : dinv, in1, p2,
+                                 ctx->counter, p2p ? ctx->pc : PeerComm{}, seq_b, sum_mode);
             }
             const double *z = ctx->h;
             if (use_mg) {  // h' = V-cycle(g) ; gh' = g.h'
-                z = mg_apply(ctx, Sval, dinv, ctx->g);
-                launch_dot_gz(l, L.nown, ctx->g, z, nullptr, ctx->partials, ctx->counter, &ctx->S->gh_new,
-                              &ctx->S->status);
+                z = mg_apply(ctx, Sval, dinv, ctx->g, &ctx->S->status[parity]);
+                launch_dot_gz(l, L.nown, ctx->g, z, nullptr, ctx->partials3, ctx->counter, &ctx->S->gh_new,
+                              &ctx->S->status[parity]);
             }
-            if (!p2p) RET(allreduce(ctx, &ctx->S->gg, 2));
+            if (sum_mode == SUM_SCALAR) RET(allreduce(ctx, &ctx->S->gg, 2));
             const unsigned long long seq_h = p2p ? ++ctx->halo_seq : 0ull;
+            const CgSumIo in2{sum_mode, p2, nvec_blocks, 2, seq_b};
             {
-                SpmvBracket br(ctx, 2, enq + k);
-                launch_cg_direction(l, L.nown, ctx->S, x + L.own_off, ctx->d + L.own_off, z, ctx->counter,
-                                    p2p ? ctx->pc : PeerComm{}, seq_h);
+                SpmvBracket br(ctx, 2, it);
+                launch_cg_direction(l, L.nown, it, ctx->S, x + L.own_off, ctx->d + L.own_off, z, in2, use_mg ? 1 : 0,
+                                    ctx->counter, p2p ? ctx->pc : PeerComm{}, seq_h);
             }
         }
         enq += chunk;
         CK(cudaMemcpyAsync(ctx->hS, ctx->S, sizeof(CgScalars), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         RET(launch_check(ctx));
-        if (ctx->hS->status != 0 || fused) break;
+        if (ctx->hS->status[enq & 1] != 0 || fused) break;
         if (enq > maxit + 8) break;
         chunk = use_mg ? 1 : 2;  // a skipped multigrid iteration still costs ~50 no-op launches
     }
@@ -543,6 +559,7 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
     CK(cudaEventSynchronize(e1));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
+    const int status = ctx->hS->status[enq & 1];
     *iters = ctx->hS->it;
     if (fused && ctx->pc.enabled) {  // the sequence numbers the kernel consumed (identical on every rank)
         ctx->ar_seq += 2ull * (unsigned long long)ctx->hS->it;
@@ -554,9 +571,11 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
     ctx->cg_stats[1] += ctx->hS->it;
     ctx->cg_stats[2] += ctx->hS->it + 1;
     ctx->cg_stats[3] += ms;
-    if (ctx->hS->status == 3)
+    if (ctx->hS->peer_timeout) {
+        CK(cudaMemsetAsync(&ctx->S->peer_timeout, 0, sizeof(int), ctx->stream));
         return fail(ctx, WAVE_ERR_CUDA, "peer exchange timed out: a neighbouring rank did not arrive (NVLink mailbox)");
-    if (ctx->hS->status != 1)
+    }
+    if (status != 1)
         return fail(ctx, WAVE_ERR_NOCONV, "CG did not converge within the iteration limit (SolverControl::NoConvergence)");
     return WAVE_OK;
 }
@@ -565,9 +584,15 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
 int build_system_matrix(wave_ctx *ctx, double s, double *out, double *dinv, double *d0) {
     const Launcher &l = ctx->launcher;
     launch_axpy_vals(l, ctx->nnz_pad, ctx->M, ctx->K, s, out);
-    if (ctx->st_tab)  // the same expression on the representative rows (Dirichlet rows are never stencil rows)
-        launch_axpy_vals(l, kTabSize, ctx->st_tab, ctx->st_tab + kTabSize, s,
-                         const_cast<double *>(tab_of(ctx, out)));
+    if (ctx->st_tab && tab_index(ctx, out) >= 0) {
+        // the same expression on the representative rows (Dirichlet rows are never stencil rows), then the
+        // host copy the launches pass as kernel parameters
+        const int k = tab_index(ctx, out);
+        launch_axpy_vals(l, kTabSize, ctx->st_tab, ctx->st_tab + kTabSize, s, ctx->st_tab + (size_t)k * kTabSize);
+        CK(cudaMemcpyAsync(ctx->h_tab.data() + (size_t)k * kTabSize, ctx->st_tab + (size_t)k * kTabSize,
+                           sizeof(double) * kTabSize, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     launch_find_d0(l, ctx->L, ctx->A, out, d0);
     launch_bc_rows(l, ctx->L, ctx->nb, ctx->brow, ctx->A, out, d0);
     launch_dinv(l, ctx->L, ctx->A, out, ctx->cfg.precond == WAVE_PRECOND_NONE, dinv);
@@ -890,16 +915,80 @@ int stencil_setup(wave_ctx *ctx) {
     unsigned long long h[2] = {0, 0};
     CK(cudaMemcpyAsync(h, counts.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if ((int64_t)h[0] * kSlice * 2 < (int64_t)L.nown) {  // counts[0] counts slices
+    // host copies of the tables; the kernel's unrolled rows assume the row lengths of the element
+    ctx->h_st_meta.assign((size_t)kTabSize + kStencilKinds, 0);
+    ctx->h_tab.assign((size_t)4 * kTabSize, 0.0);
+    CK(cudaMemcpyAsync(ctx->h_st_meta.data(), ctx->st_meta, sizeof(int32_t) * ctx->h_st_meta.size(),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_tab.data(), ctx->st_tab, sizeof(double) * 2 * kTabSize, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int32_t *len = ctx->h_st_meta.data() + kTabSize;
+    const bool lengths_ok = L.mesh.r == 1 ? len[0] == 7 : (len[0] == 19 && len[1] == 9 && len[2] == 9 && len[3] == 9);
+    if (!lengths_ok || (int64_t)h[0] * 2 < (int64_t)L.nown) {
+        ctx->h_st_meta.clear();
+        ctx->h_tab.clear();
         cudaFree(ctx->st_tab); ctx->st_tab = nullptr;
         cudaFree(ctx->st_meta); ctx->st_meta = nullptr;
         cudaFree(ctx->slice_info); ctx->slice_info = nullptr;
         return WAVE_OK;
     }
-    ctx->stencil_rows = (int64_t)h[0] * kSlice;
+    // the slices that stay in SELL form, in ascending order (built on the host: the order fixes which warp
+    // takes which slice and with it the order of the partial sums)
+    std::vector<int2> info((size_t)ctx->nslices);
+    CK(cudaMemcpyAsync(info.data(), ctx->slice_info, sizeof(int2) * info.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<int32_t> list;
+    for (int sl = 0; sl < ctx->nslices; ++sl)
+        if (info[(size_t)sl].x < 0) list.push_back(sl);
+    // the stencil slices in tile order: key = (group of DoF lines, column chunk, line in the group, kind), so
+    // that the 8 warps of a block take slices of one column range in neighbouring lines / kinds
+    {
+        const Mesh &m = L.mesh;
+        const int lines_per_tile = m.r == 1 ? 8 : 2;
+        std::vector<std::pair<uint64_t, int32_t>> keyed;
+        keyed.reserve((size_t)ctx->nslices - list.size());
+        const int64_t b0 = block_start(m, 1), bsz = m.r == 1 ? (m.nx + 1) : (4LL * m.nx + 2);
+        for (int sl = 0; sl < ctx->nslices; ++sl) {
+            const int2 si = info[(size_t)sl];
+            if (si.x < 0) continue;
+            uint64_t key;
+            if (si.y < 0) key = ~0ull - (uint64_t)(ctx->nslices - sl);  // rows not consecutive: keep at the end
+            else {
+                const int64_t g = (int64_t)si.y + L.row0;
+                const int64_t j = g < b0 ? 0 : 1 + (g - b0) / bsz;
+                const int64_t pos = g - block_start(m, (int)j);
+                int64_t i = pos;
+                if (m.r == 2 && j >= 1) {
+                    const int64_t seg[4] = {0, m.nx + 1, 2LL * m.nx + 1, 3LL * m.nx + 2};
+                    i = pos - seg[si.x];
+                }
+                key = ((uint64_t)(j / lines_per_tile) << 40) | ((uint64_t)(i / kSlice) << 16) |
+                      ((uint64_t)(j % lines_per_tile) << 4) | (uint64_t)si.x;
+            }
+            keyed.emplace_back(key, sl);
+        }
+        std::sort(keyed.begin(), keyed.end());
+        std::vector<int32_t> order(keyed.size());
+        for (size_t k = 0; k < keyed.size(); ++k) order[k] = keyed[k].second;
+        RET(dev_alloc(ctx, &ctx->st_order, order.size(), false));
+        if (!order.empty())
+            CK(cudaMemcpyAsync(ctx->st_order, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice,
+                               ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->A.st_order = ctx->st_order;
+        ctx->A.n_st = (int)order.size();
+    }
+    RET(dev_alloc(ctx, &ctx->sell_list, list.size(), false));
+    if (!list.empty())
+        CK(cudaMemcpyAsync(ctx->sell_list, list.data(), sizeof(int32_t) * list.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stencil_rows = (int64_t)h[0];
     ctx->sell_nnz = (int64_t)h[1];
     ctx->A.slice_info = ctx->slice_info;
-    ctx->A.st_meta = ctx->st_meta;
+    ctx->A.st_meta = ctx->h_st_meta.data();
+    ctx->A.sell_list = ctx->sell_list;
+    ctx->A.n_sell = (int)list.size();
     return WAVE_OK;
 }
 
@@ -1004,7 +1093,7 @@ int setup_peer_exchange(wave_ctx *ctx) {
     PeerComm pc{};
     pc.rank = rank;
     pc.nranks = R;
-    pc.status = &ctx->S->status;
+    pc.status = &ctx->S->peer_timeout;
     for (int r = 0; r < R; ++r) {
         if (r == rank) { pc.box[r] = ctx->mailbox; continue; }
         void *p = nullptr;
@@ -1157,9 +1246,9 @@ void wave_destroy(wave_ctx *ctx) {
     for (void *q : {(void *)ctx->fused.blk_c0, (void *)ctx->fused.blk_cn, (void *)ctx->fused.partials,
                     (void *)ctx->fused.pub})
         if (q) cudaFree(q);
-    void *ptrs[] = {ctx->st_tab, ctx->st_meta, ctx->slice_info, ctx->dprog, ctx->rowptr, ctx->slice_ptr, ctx->row_of, ctx->slot_of, ctx->col, ctx->c2i, ctx->i2c, ctx->tmp, ctx->M, ctx->K, ctx->S1, ctx->S2, ctx->dinv1, ctx->dinv2,
+    void *ptrs[] = {ctx->st_tab, ctx->st_meta, ctx->slice_info, ctx->sell_list, ctx->st_order, ctx->dprog, ctx->rowptr, ctx->slice_ptr, ctx->row_of, ctx->slot_of, ctx->col, ctx->c2i, ctx->i2c, ctx->tmp, ctx->M, ctx->K, ctx->S1, ctx->S2, ctx->dinv1, ctx->dinv2,
                     ctx->d0, ctx->u, ctx->v, ctx->a, ctx->unew, ctx->d, ctx->rhs, ctx->fvec, ctx->cellvec, ctx->g, ctx->h,
-                    ctx->scratch, ctx->brow, ctx->bx, ctx->by, ctx->partials, ctx->counter, ctx->S, ctx->res,
+                    ctx->scratch, ctx->brow, ctx->bx, ctx->by, ctx->partials, ctx->partials2, ctx->partials3, ctx->counter, ctx->S, ctx->res,
                     ctx->flush_buf};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -1282,7 +1371,7 @@ int wave_setup(wave_ctx *ctx) {
     CK(cudaFree(slice_cnt));
     RET(dev_alloc(ctx, &ctx->col, (size_t)ctx->nnz_pad, false));
     ctx->A = Sell{ctx->slice_ptr, ctx->col, ctx->row_of, ctx->slot_of, ctx->rowptr, ctx->nslices, L.nown,
-                  L.mesh.r == 1 ? 7 : 10, L.own_off, nullptr, nullptr};
+                  L.mesh.r == 1 ? 7 : 10, L.own_off, nullptr, nullptr, nullptr, 0, nullptr, 0};
     launch_fill_int(l, ctx->nnz_pad, L.own_off, ctx->col);  // padding entries: a valid column, value 0
     launch_fill_cols(l, L, ctx->A, ctx->col);
 
@@ -1354,6 +1443,8 @@ int wave_setup(wave_ctx *ctx) {
         const int64_t blocks = std::max<int64_t>({(cells + 127) / 128, (int64_t)(nslots / kSlice + 7) / 8,
                                                   (int64_t)reduction_blocks(L.nown)}) + 1;
         RET(dev_alloc(ctx, &ctx->partials, (size_t)blocks * 4));
+        RET(dev_alloc(ctx, &ctx->partials2, (size_t)blocks * 4));
+        RET(dev_alloc(ctx, &ctx->partials3, (size_t)blocks * 4));
     }
     RET(dev_alloc(ctx, &ctx->counter, 4));
     RET(dev_alloc(ctx, &ctx->S, 1));

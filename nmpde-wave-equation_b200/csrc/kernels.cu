@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include <cub/block/block_radix_sort.cuh>
 
@@ -111,29 +112,41 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// One-shot all-reduce of NV (<= 2) doubles, executed by the first warp of one block per rank.
-// `vals` holds the local totals in lane 0 on entry and the global totals in all lanes on return.
-// Lane r stores this rank's words into rank r's mailbox (one NVLink hop, no ordering needed) and polls
-// rank r's words in the local mailbox; the sum runs in rank order on every rank (bitwise identical).
+// One-shot all-reduce of NV (<= 2) doubles in two halves.  p2p_publish (first warp of one block per rank):
+// lane r stores this rank's totals into rank r's mailbox (one NVLink hop, no ordering needed, no waiting).
+// p2p_collect (first warp of any block): lane r polls rank r's words in the local mailbox; the sum runs in
+// rank order on every rank (bitwise identical everywhere).  Every 8-byte word carries 4 bytes of payload
+// and the low 32 bits of the sequence number, so a word validates itself.  The producer publishes in its
+// tail; the consumer kernel collects in its first instructions, so the NVLink flight time and the ranks'
+// skew overlap with the consumer's launch instead of extending the producer.
 template <int NV>
-__device__ __forceinline__ void p2p_allreduce(const PeerComm &pc, unsigned long long seq, double (&vals)[NV]) {
+__device__ __forceinline__ void p2p_publish(const PeerComm &pc, unsigned long long seq, const double (&vals)[NV]) {
     const int lane = threadIdx.x & 31;
     const int slot = (int)(seq & 1ull);
     const unsigned long long tag = (seq & 0xffffffffull) << 32;
+    double v[NV];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) vals[k] = __shfl_sync(kFull, vals[k], 0);
+    for (int k = 0; k < NV; ++k) v[k] = __shfl_sync(kFull, vals[k], 0);
+    if (lane < pc.nranks) {
+        unsigned long long *dst = pc.box[lane]->ll[slot][pc.rank];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(v[k]);
+            st_relaxed_sys(&dst[2 * k], (bits & 0xffffffffull) | tag);
+            st_relaxed_sys(&dst[2 * k + 1], (bits >> 32) | tag);
+        }
+    }
+}
+template <int NV>
+__device__ __forceinline__ void p2p_collect(const PeerComm &pc, unsigned long long seq, double (&out)[NV]) {
+    const int lane = threadIdx.x & 31;
+    const int slot = (int)(seq & 1ull);
+    const unsigned long long tag = (seq & 0xffffffffull) << 32;
     bool ok = true;
     double got[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) got[k] = 0.0;
     if (lane < pc.nranks) {
-        unsigned long long *dst = pc.box[lane]->ll[slot][pc.rank];
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[k]);
-            st_relaxed_sys(&dst[2 * k], (bits & 0xffffffffull) | tag);
-            st_relaxed_sys(&dst[2 * k + 1], (bits >> 32) | tag);
-        }
         const unsigned long long *src = pc.box[pc.rank]->ll[slot][lane];
         const long long t0 = clock64();
 #pragma unroll
@@ -153,17 +166,64 @@ __device__ __forceinline__ void p2p_allreduce(const PeerComm &pc, unsigned long 
     for (int k = 0; k < NV; ++k) {
         double t = 0.0;
         for (int r = 0; r < pc.nranks; ++r) t += __shfl_sync(kFull, got[k], r);  // rank order on every rank
-        vals[k] = t;
+        out[k] = ok ? t : __longlong_as_double(0x7ff8000000000000LL);  // NaN stops the solve (status 2)
     }
-    if (!ok && lane == 0) *pc.status = 3;
+    if (!ok && lane == 0) *pc.status = 1;
 }
-// grid_sum followed by the peer all-reduce when enabled; true in the finishing block, totals in thread 0
+
+// ---- sums handed from a producer kernel to its consumer (see SUM_* in kernels.cuh) --------------------
+// Producer tail.  SUM_PARTIALS: one partial per block and nothing else (no fence, no ticket, no second
+// pass).  SUM_MAILBOX: the last block adds the partials in block order and stores the rank's totals into
+// every rank's mailbox.  SUM_SCALAR: the last block writes the totals to `scalars`.
 template <int NV>
-__device__ __forceinline__ bool grid_sum_peers(double (&v)[NV], double *partials, unsigned *counter,
-                                               const PeerComm &pc, unsigned long long seq) {
-    const bool last = grid_sum<NV>(v, partials, counter);
-    if (last && pc.enabled && threadIdx.x < 32) p2p_allreduce<NV>(pc, seq, v);
-    return last;
+__device__ __forceinline__ void produce_sums(double (&v)[NV], int mode, double *partials, unsigned *counter,
+                                             const PeerComm &pc, unsigned long long seq, double *scalars) {
+    if (mode == SUM_PARTIALS) {
+        block_sum<NV>(v);
+        if (threadIdx.x == 0)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) partials[(size_t)blockIdx.x * NV + k] = v[k];
+        return;
+    }
+    if (!grid_sum<NV>(v, partials, counter)) return;
+    if (mode == SUM_MAILBOX) {
+        if (threadIdx.x < 32) p2p_publish<NV>(pc, seq, v);
+    } else if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) scalars[k] = v[k];
+    }
+}
+// Consumer head: the totals in every thread of every block, bitwise identical in all of them.
+template <int NV>
+__device__ __forceinline__ void consume_sums(const CgSumIo &in, const PeerComm &pc, const double *scalars,
+                                             double (&out)[NV]) {
+    __shared__ double s_bc[NV];
+    if (in.mode == SUM_SCALAR) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) out[k] = scalars[k];
+        return;
+    }
+    if (in.mode == SUM_PARTIALS) {
+        double v[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) v[k] = 0.0;
+        for (int b = threadIdx.x; b < in.blocks; b += blockDim.x)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) v[k] += __ldcg(&in.partials[(size_t)b * in.stride + k]);
+        block_sum<NV>(v);
+        if (threadIdx.x == 0)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) s_bc[k] = v[k];
+    } else if (threadIdx.x < 32) {
+        double v[NV];
+        p2p_collect<NV>(pc, in.seq, v);
+        if (threadIdx.x == 0)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) s_bc[k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) out[k] = s_bc[k];
 }
 
 // ---- sparsity pattern: DoFTools::make_sparsity_pattern + compress (src/WaveNewmark.cpp:33-35) ----
@@ -638,30 +698,49 @@ __global__ void k_bc_values(int mode, int nb, const int32_t *brow, const double 
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
 
+// row epilogue shared by both SpMV kernels: addends, damped-Jacobi update, CG residual start, fused dots
+__device__ __forceinline__ void spmv_epilogue(const SpmvArgs &a, int r, double s, double (&dots)[2]) {
+    if (a.add0) s += a.addc0 * a.add0[r];
+    if (a.add1) s += a.addc1 * a.add1[r];
+    if (a.jac_x) s = a.jac_x[r] + a.jac_omega * (a.dinv[r] * s);
+    if (a.y) a.y[r] = s;
+    double hv = 0.0;
+    if (a.h_out) {
+        hv = a.dinv[r] * s;
+        a.h_out[r] = hv;
+        a.d_out[r] = -hv;
+    }
+    if (a.dot_mode == 1) dots[0] += s * a.dotv[r];
+    else if (a.dot_mode == 2) { dots[0] += s * s; dots[1] += s * hv; }
+}
+__device__ __forceinline__ void spmv_tail(const SpmvArgs &a, double (&dots)[2]) {
+    if (!a.dot_mode) return;
+    if (a.dot_publish)  // CG iteration: the consumer kernel (k_cg_update) finishes the sum
+        produce_sums<2>(dots, a.pc.enabled ? SUM_MAILBOX : SUM_PARTIALS, a.partials, a.counter, a.pc, a.ar_seq, nullptr);
+    else if (grid_sum<2>(dots, a.partials, a.counter) && threadIdx.x == 0) {
+        a.result[0] = dots[0];
+        if (a.dot_mode == 2) a.result[1] = dots[1];
+    }
+}
+// wait (once per warp, lazily) for the neighbours' halo of this iteration's search direction
+__device__ __forceinline__ void halo_wait(const SpmvArgs &a, int lane) {
+    if (lane == 0) {
+        bool ok = true;
+        PeerMailbox *box = a.pc.box[a.pc.rank];
+        if (a.pc.rank > 0) ok = spin_until(&box->halo_flag[0], a.halo_wait_seq) && ok;
+        if (a.pc.rank < a.pc.nranks - 1) ok = spin_until(&box->halo_flag[1], a.halo_wait_seq) && ok;
+        if (!ok) *a.pc.status = 1;
+    }
+    __syncwarp();
+}
+
 template <int NT, bool TWOX, int CH, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) k_spmv(SpmvArgs a) {
-    __shared__ double s_tab[NT][kStencilKinds * kStencilMax];
-    __shared__ int s_meta[kStencilKinds * kStencilMax + kStencilKinds];
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
     if (a.skip_flag && *a.skip_flag != 0) return;
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (kThreads / 32);
-    // stencil slices take their column offsets and values from the tables (kernels.cuh); all terms of the
-    // launch must have one
-    bool stencil = a.A.slice_info != nullptr;
-#pragma unroll
-    for (int t = 0; t < NT; ++t) stencil = stencil && a.t[t].tab != nullptr;
-    if (stencil) {
-        for (int k = threadIdx.x; k < kStencilKinds * kStencilMax + kStencilKinds; k += kThreads) {
-            s_meta[k] = a.A.st_meta[k];
-            if (k < kStencilKinds * kStencilMax) {
-#pragma unroll
-                for (int t = 0; t < NT; ++t) s_tab[t][k] = a.t[t].tab[k];
-            }
-        }
-        __syncthreads();
-    }
     double dots[2] = {0.0, 0.0};
     // Persistent warps, grid-stride over slices.  Per chunk a lane issues CH col loads and CH*NT val
     // loads back to back (unconditional: a short tail re-reads the row's last entry and is masked out
@@ -677,12 +756,10 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmv(SpmvArgs a) {
     int slice = it + rot < a.A.nslices ? it + rot : it + rot - a.A.nslices;
     uint32_t b = 0, e = 0;
     int r = -1;
-    int2 si = make_int2(-1, -1);
     if (it < a.A.nslices) {
-        if (stencil) si = a.A.slice_info[slice];
         b = a.A.slice_ptr[slice];
         e = a.A.slice_ptr[slice + 1];
-        r = si.y >= 0 ? si.y + lane : a.A.row_of[slice * kSlice + lane];
+        r = a.A.row_of[slice * kSlice + lane];
     }
     while (it < a.A.nslices) {
         // metadata of this warp's next slice, requested before the long-latency work below
@@ -690,51 +767,29 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmv(SpmvArgs a) {
         const int nslice = nit + rot < a.A.nslices ? nit + rot : nit + rot - a.A.nslices;
         uint32_t nb = 0, ne = 0;
         int nr = -1;
-        int2 nsi = make_int2(-1, -1);
         if (nit < a.A.nslices) {
-            if (stencil) nsi = a.A.slice_info[nslice];
             nb = a.A.slice_ptr[nslice];
             ne = a.A.slice_ptr[nslice + 1];
-            nr = nsi.y >= 0 ? nsi.y + lane : a.A.row_of[nslice * kSlice + lane];
+            nr = a.A.row_of[nslice * kSlice + lane];
         }
         const bool ghosty = a.pc.enabled && (slice < a.ghost_lo_slices || slice >= a.ghost_hi_slice0);
         if (ghosty && !halo_ready) {  // warp-uniform
-            if (lane == 0) {
-                bool ok = true;
-                PeerMailbox *box = a.pc.box[a.pc.rank];
-                if (a.pc.rank > 0) ok = spin_until(&box->halo_flag[0], a.halo_wait_seq) && ok;
-                if (a.pc.rank < a.pc.nranks - 1) ok = spin_until(&box->halo_flag[1], a.halo_wait_seq) && ok;
-                if (!ok) *a.pc.status = 3;
-            }
-            __syncwarp();
+            halo_wait(a, lane);
             halo_ready = true;
         }
-        const int kind = si.x;  // warp-uniform; >= 0: every lane holds a row of that kind
-        const int len = kind >= 0 ? s_meta[kStencilKinds * kStencilMax + kind] : (int)((e - b) >> 5);
+        const int len = (int)((e - b) >> 5);
         const uint32_t base = b + lane;
-        const int cself = r + a.A.own_off;
-        const int tb = kind * kStencilMax;
         double s = 0.0;
         for (int k0 = 0; k0 < len; k0 += CH) {
             int c[CH];
             double v[NT][CH], x[NT][CH];
-            if (kind >= 0) {
 #pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    const int kk = min(k0 + k, len - 1);
-                    c[k] = cself + s_meta[tb + kk];
+            for (int k = 0; k < CH; ++k) {
+                const int kk = min(k0 + k, len - 1);
+                const uint32_t q = base + (uint32_t)kk * kSlice;
+                c[k] = ld_stream(&a.A.col[q]);
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) v[t][k] = s_tab[t][tb + kk];
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    const int kk = min(k0 + k, len - 1);
-                    const uint32_t q = base + (uint32_t)kk * kSlice;
-                    c[k] = ld_stream(&a.A.col[q]);
-#pragma unroll
-                    for (int t = 0; t < NT; ++t) v[t][k] = ld_stream(&a.t[t].val[q]);
-                }
+                for (int t = 0; t < NT; ++t) v[t][k] = ld_stream(&a.t[t].val[q]);
             }
 #pragma unroll
             for (int k = 0; k < CH; ++k)
@@ -757,28 +812,169 @@ __global__ void __launch_bounds__(kThreads, MINB) k_spmv(SpmvArgs a) {
                 }
             }
         }
-        if (r >= 0) {
-            if (a.add0) s += a.addc0 * a.add0[r];
-            if (a.add1) s += a.addc1 * a.add1[r];
-            if (a.jac_x) s = a.jac_x[r] + a.jac_omega * (a.dinv[r] * s);
-            if (a.y) a.y[r] = s;
-            double hv = 0.0;
-            if (a.h_out) {
-                hv = a.dinv[r] * s;
-                a.h_out[r] = hv;
-                a.d_out[r] = -hv;
+        if (r >= 0) spmv_epilogue(a, r, s, dots);
+        it = nit; slice = nslice; b = nb; e = ne; r = nr;
+    }
+    spmv_tail(a, dots);
+}
+
+// ---- K3s: the same operator with the translation-invariant rows served from tables (kernels.cuh) ------
+// Phase 1 walks all slices and takes the stencil ones.  The column offsets and values of the (at most
+// four) representative rows travel as a kernel parameter, i.e. in the constant bank: inside the
+// `switch (kind)` every row is a fully unrolled sequence with compile-time length (P1: 7; P2: 19 for a
+// vertex row, 9 for the three edge kinds) whose offsets and values are constant-bank operands of the
+// index add and of the multiply.  A row costs its x gathers (L1 / L2: every x entry is used by ~11 rows),
+// 8 B of y and the epilogue's vectors -- no matrix stream, ~5 instructions per entry.  All gathers of a
+// row are in flight before the sum, which runs over the same entries in the same order with the same
+// separate multiply / add roundings as the SELL path (multiplications by a coefficient of exactly 1 are
+// skipped: they are exact).  Phase 2 takes the few remaining slices (boundary rows, first DoF lines) from
+// the SELL arrays through a precomputed list, with short chunks.
+struct StencilParams {
+    int off[kStencilKinds][kStencilMax];
+    double val[2][kStencilKinds][kStencilMax];
+};
+template <int LEN, int BATCH, int NT, bool TWOX, bool UNIT, bool CG>
+__device__ __forceinline__ double stencil_row(const SpmvArgs &a, const StencilParams &p, const int kind, int cself) {
+    double s = 0.0;
+#pragma unroll
+    for (int k0 = 0; k0 < LEN; k0 += BATCH) {
+        double x[NT][BATCH];
+#pragma unroll
+        for (int k = 0; k < BATCH; ++k) {
+            if (k0 + k < LEN) {
+                const int idx = cself + p.off[kind][k0 + k];
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    double xv = CG ? __ldcg(&a.t[t].xa[idx]) : a.t[t].xa[idx];
+                    if (!UNIT) {
+                        xv = __dmul_rn(a.t[t].ca, xv);
+                        if (TWOX && a.t[t].xb)
+                            xv = __dadd_rn(xv, __dmul_rn(a.t[t].cb, CG ? __ldcg(&a.t[t].xb[idx]) : a.t[t].xb[idx]));
+                    }
+                    x[t][k] = xv;
+                }
             }
-            if (a.dot_mode == 1) dots[0] += s * a.dotv[r];
-            else if (a.dot_mode == 2) { dots[0] += s * s; dots[1] += s * hv; }
         }
-        it = nit; slice = nslice; b = nb; e = ne; r = nr; si = nsi;
-    }
-    if (a.dot_mode) {
-        if (grid_sum_peers<2>(dots, a.partials, a.counter, a.pc, a.ar_seq) && threadIdx.x == 0) {
-            a.result[0] = dots[0];
-            if (a.dot_mode == 2) a.result[1] = dots[1];
+#pragma unroll
+        for (int k = 0; k < BATCH; ++k) {
+            if (k0 + k < LEN) {
+                double prod = __dmul_rn(p.val[0][kind][k0 + k], x[0][k]);
+                if (!UNIT) {
+                    prod = __dmul_rn(a.t[0].coef, prod);
+#pragma unroll
+                    for (int t = 1; t < NT; ++t)
+                        prod = __dadd_rn(prod, __dmul_rn(a.t[t].coef, __dmul_rn(p.val[t][kind][k0 + k], x[t][k])));
+                }
+                s = __dadd_rn(s, prod);
+            }
         }
     }
+    return s;
+}
+template <bool P2, int NT, bool TWOX, bool UNIT, bool CG>
+__device__ __forceinline__ double stencil_row_of_kind(const SpmvArgs &a, const StencilParams &p, int kind, int cself) {
+    constexpr int B = NT == 1 ? 19 : 10;
+    if (!P2) return stencil_row<7, 7, NT, TWOX, UNIT, CG>(a, p, 0, cself);
+    switch (kind) {  // warp-uniform
+    case 0: return stencil_row<19, B, NT, TWOX, UNIT, CG>(a, p, 0, cself);
+    case 1: return stencil_row<9, 9, NT, TWOX, UNIT, CG>(a, p, 1, cself);
+    case 2: return stencil_row<9, 9, NT, TWOX, UNIT, CG>(a, p, 2, cself);
+    default: return stencil_row<9, 9, NT, TWOX, UNIT, CG>(a, p, 3, cself);
+    }
+}
+template <bool P2, int NT, bool TWOX, bool UNIT>
+__global__ void __launch_bounds__(kThreads, P2 ? 3 : 4) k_spmv_st(SpmvArgs a, const __grid_constant__ StencilParams p) {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+    if (a.skip_flag && *a.skip_flag != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (kThreads / 32);
+    const int warp0 = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+    double dots[2] = {0.0, 0.0};
+    const int rot = a.halo_wait_seq ? a.A.n_st / 2 : 0;  // see k_spmv: ghost-reading slices come mid-kernel
+    bool halo_ready = a.halo_wait_seq == 0;
+    // ---- phase 1: stencil slices, in tile order (st_order: the warps of a block take slices of the same
+    // column range in neighbouring DoF lines and kinds, so their x gathers share L1 lines) ---------------
+    {
+        const int n_st = a.A.n_st;
+        int it = warp0;
+        int2 si = make_int2(-1, -1);
+        int slice = -1;
+        if (it < n_st) {
+            slice = a.A.st_order[it + rot < n_st ? it + rot : it + rot - n_st];
+            si = a.A.slice_info[slice];
+        }
+        while (it < n_st) {
+            const int nit = it + nwarps;
+            int nslice = -1;
+            int2 nsi = make_int2(-1, -1);
+            if (nit < n_st) {
+                nslice = a.A.st_order[nit + rot < n_st ? nit + rot : nit + rot - n_st];
+                nsi = a.A.slice_info[nslice];
+            }
+            const int kind = si.x;
+            {
+                const int r = si.y >= 0 ? si.y + lane : a.A.row_of[slice * kSlice + lane];
+                const int cself = r + a.A.own_off;
+                const bool ghosty = a.pc.enabled && (slice < a.ghost_lo_slices || slice >= a.ghost_hi_slice0);
+                double s;
+                if (ghosty) {  // rare (both ends of a rank's rows): wait for the halo, gather through L2
+                    if (!halo_ready) {
+                        halo_wait(a, lane);
+                        halo_ready = true;
+                    }
+                    s = stencil_row_of_kind<P2, NT, TWOX, UNIT, true>(a, p, kind, cself);
+                } else
+                    s = stencil_row_of_kind<P2, NT, TWOX, UNIT, false>(a, p, kind, cself);
+                spmv_epilogue(a, r, s, dots);
+            }
+            it = nit; slice = nslice; si = nsi;
+        }
+    }
+    // ---- phase 2: the slices kept in SELL form -------------------------------------------------------
+    constexpr int CS = 4;
+    for (int q = warp0; q < a.A.n_sell; q += nwarps) {
+        const int slice = a.A.sell_list[q];
+        const bool ghosty = a.pc.enabled && (slice < a.ghost_lo_slices || slice >= a.ghost_hi_slice0);
+        if (ghosty && !halo_ready) {
+            halo_wait(a, lane);
+            halo_ready = true;
+        }
+        const uint32_t b = a.A.slice_ptr[slice], e = a.A.slice_ptr[slice + 1];
+        const int r = a.A.row_of[slice * kSlice + lane];
+        const int len = (int)((e - b) >> 5);
+        const uint32_t base = b + lane;
+        double s = 0.0;
+        for (int k0 = 0; k0 < len; k0 += CS) {
+            int c[CS];
+            double v[NT][CS];
+#pragma unroll
+            for (int k = 0; k < CS; ++k) {
+                const uint32_t qq = base + (uint32_t)min(k0 + k, len - 1) * kSlice;
+                c[k] = ld_stream(&a.A.col[qq]);
+#pragma unroll
+                for (int t = 0; t < NT; ++t) v[t][k] = ld_stream(&a.t[t].val[qq]);
+            }
+#pragma unroll
+            for (int k = 0; k < CS; ++k) {
+                if (k0 + k < len) {  // warp-uniform
+                    double prod = 0.0;
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) {
+                        const double xa = ghosty ? __ldcg(&a.t[t].xa[c[k]]) : a.t[t].xa[c[k]];
+                        double xv = __dmul_rn(a.t[t].ca, xa);
+                        if (TWOX && a.t[t].xb)
+                            xv = __dadd_rn(xv, __dmul_rn(a.t[t].cb, ghosty ? __ldcg(&a.t[t].xb[c[k]]) : a.t[t].xb[c[k]]));
+                        const double term = __dmul_rn(a.t[t].coef, __dmul_rn(v[t][k], xv));
+                        prod = t == 0 ? term : __dadd_rn(prod, term);
+                    }
+                    s = __dadd_rn(s, prod);
+                }
+            }
+        }
+        if (r >= 0) spmv_epilogue(a, r, s, dots);
+    }
+    spmv_tail(a, dots);
 }
 
 __global__ void k_zero_rows(int nb, const int32_t *brow, double *vec) {
@@ -795,71 +991,116 @@ __global__ void k_cg_start(CgScalars *S) {
     S->res = res0;
     S->reduced_tol = res0 * S->reduce;
     S->it = 0;
-    S->gh_old = S->gh_new;
-    S->status = (res0 <= S->reduced_tol || res0 <= S->tol) ? 1 : 0;
+    S->gh[0] = S->gh_new;
+    S->status[0] = (res0 <= S->reduced_tol || res0 <= S->tol) ? 1 : 0;
+    S->status[1] = 0;
 }
-// g += alpha h ; res^2 = g.g ; h = D^-1 g ; gh' = g.h   (one pass: 3 reads, 2 writes).  The x update of
-// this iteration (x += alpha d) is done by k_cg_direction, which reads d anyway.
-__global__ void __launch_bounds__(kThreads) k_cg_update(int n, CgScalars *S, double *__restrict__ g,
+// Iteration k, parity = k & 1.  alpha = gh / dAd ; g += alpha h ; res^2 = g.g ; h = D^-1 g ; gh' = g.h
+// (one pass: 3 reads, 2 writes).  The x update of this iteration (x += alpha d) is done by k_cg_direction,
+// which reads d anyway.  Four independent elements per thread and trip keep ~100 bytes in flight per thread.
+__global__ void __launch_bounds__(kThreads) k_cg_update(int n, int parity, CgScalars *S, double *__restrict__ g,
                                                         double *__restrict__ h, const double *__restrict__ dinv,
-                                                        double *partials, unsigned *counter, PeerComm pc,
-                                                        unsigned long long ar_seq) {
+                                                        CgSumIo in, double *out_partials, unsigned *counter,
+                                                        PeerComm pc, unsigned long long out_seq, int out_mode) {
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
-    if (S->status != 0) return;
-    const double alpha = S->gh_old / S->dAd;
+    if (S->status[parity] != 0) return;
+    double dAd[1];
+    consume_sums<1>(in, pc, &S->dAd, dAd);
+    const double alpha = S->gh[parity] / dAd[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) S->alpha = alpha;
     double acc[2] = {0.0, 0.0};
-    const int stride = gridDim.x * blockDim.x;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double gi = g[i] + alpha * h[i];
-        g[i] = gi;
-        acc[0] += gi * gi;
-        if (dinv) {  // Jacobi fused here; with the multigrid preconditioner h is produced by the V-cycle
-            const double hi = dinv[i] * gi;
-            h[i] = hi;
-            acc[1] += gi * hi;
+    const int stride = gridDim.x * kThreads * 4;
+    for (int i0 = blockIdx.x * kThreads * 4 + threadIdx.x; i0 < n; i0 += stride) {
+        double gv[4], hv[4], dv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kThreads;
+            if (i < n) {
+                gv[u] = g[i];
+                hv[u] = h[i];
+                dv[u] = dinv ? dinv[i] : 0.0;
+            }
         }
-    }
-    if (grid_sum_peers<2>(acc, partials, counter, pc, ar_seq) && threadIdx.x == 0) {
-        S->gg = acc[0];
-        if (dinv) S->gh_new = acc[1];
-    }
-}
-// x += alpha d ; iteration_status(it, res) ; beta = gh'/gh ; d = beta d - h   (3 reads, 2 writes)
-__global__ void __launch_bounds__(kThreads) k_cg_direction(int n, CgScalars *S, double *__restrict__ x,
-                                                           double *__restrict__ d, const double *__restrict__ h,
-                                                           unsigned *counter, PeerComm pc,
-                                                           unsigned long long halo_seq) {
-    cudaGridDependencySynchronize();
-    cudaTriggerProgrammaticLaunchCompletion();
-    if (S->status != 0) return;
-    const double alpha = S->gh_old / S->dAd;  // the step length of this iteration (set before k_cg_update)
-    const double res = sqrt(fabs(S->gg));
-    const int it = S->it + 1;
-    int status = 0;
-    if (res <= S->reduced_tol || res <= S->tol) status = 1;
-    else if (it >= S->maxit || isnan(res)) status = 2;
-    const double beta = S->gh_new / S->gh_old;
-    const int stride = gridDim.x * blockDim.x;
-    const int hi0 = n - pc.hi_count;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double dold = d[i];
-        x[i] += alpha * dold;
-        if (status == 0) {
-            const double di = beta * dold - h[i];
-            d[i] = di;
-            if (pc.enabled) {  // my first / last block is the neighbours' ghost block: store it there too
-                if (pc.d_lo && i < pc.lo_count) pc.d_lo[i] = di;
-                if (pc.d_hi && i >= hi0) pc.d_hi[i - hi0] = di;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kThreads;
+            if (i < n) {
+                const double gi = gv[u] + alpha * hv[u];
+                g[i] = gi;
+                acc[0] += gi * gi;
+                if (dinv) {  // Jacobi fused here; with the multigrid preconditioner h is produced by the V-cycle
+                    const double hi = dv[u] * gi;
+                    h[i] = hi;
+                    acc[1] += gi * hi;
+                }
             }
         }
     }
-    if (last_block_done(counter, pc.enabled != 0) && threadIdx.x == 0) {
+    produce_sums<2>(acc, out_mode, out_partials, counter, pc, out_seq, &S->gg);
+}
+// x += alpha d ; iteration_status(k + 1, res) ; beta = gh'/gh ; d = beta d - h   (3 reads, 2 writes).
+// Block 0 records the outcome in the other parity's slots: nothing it writes is read by this kernel.
+__global__ void __launch_bounds__(kThreads) k_cg_direction(int n, int k, CgScalars *S, double *__restrict__ x,
+                                                           double *__restrict__ d, const double *__restrict__ h,
+                                                           CgSumIo in, int gh_scalar, unsigned *counter, PeerComm pc,
+                                                           unsigned long long halo_seq) {
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+    const int parity = k & 1;
+    const int st = S->status[parity];
+    if (st != 0) {  // finished earlier: hand the outcome on to the slot the next iteration reads
+        if (blockIdx.x == 0 && threadIdx.x == 0) S->status[parity ^ 1] = st;
+        return;
+    }
+    double tot[2];
+    consume_sums<2>(in, pc, &S->gg, tot);
+    const double gh_new = gh_scalar ? S->gh_new : tot[1];
+    const double gh_old = S->gh[parity];
+    const double alpha = S->alpha;  // the step length of this iteration (k_cg_update)
+    const double res = sqrt(fabs(tot[0]));
+    const int it = k + 1;
+    int status = 0;
+    if (res <= S->reduced_tol || res <= S->tol) status = 1;
+    else if (it >= S->maxit || isnan(res)) status = 2;
+    const double beta = gh_new / gh_old;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         S->it = it;
         S->res = res;
-        S->status = status;
-        S->gh_old = S->gh_new;
-        if (pc.enabled && status == 0) {
+        S->gh[parity ^ 1] = gh_new;
+        S->status[parity ^ 1] = status;
+    }
+    const int hi0 = n - pc.hi_count;
+    const int stride = gridDim.x * kThreads * 4;
+    for (int i0 = blockIdx.x * kThreads * 4 + threadIdx.x; i0 < n; i0 += stride) {
+        double xv[4], dv[4], hv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kThreads;
+            if (i < n) {
+                xv[u] = x[i];
+                dv[u] = d[i];
+                hv[u] = status == 0 ? h[i] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kThreads;
+            if (i < n) {
+                x[i] = xv[u] + alpha * dv[u];
+                if (status == 0) {
+                    const double di = beta * dv[u] - hv[u];
+                    d[i] = di;
+                    if (pc.enabled) {  // my first / last block is the neighbours' ghost block: store it there too
+                        if (pc.d_lo && i < pc.lo_count) pc.d_lo[i] = di;
+                        if (pc.d_hi && i >= hi0) pc.d_hi[i - hi0] = di;
+                    }
+                }
+            }
+        }
+    }
+    if (pc.enabled && status == 0) {  // halo flag: after every block's halo stores (system-scope fence)
+        if (last_block_done(counter, true) && threadIdx.x == 0) {
             __threadfence_system();
             if (pc.rank > 0) st_release_sys(&pc.box[pc.rank - 1]->halo_flag[1], halo_seq);
             if (pc.rank < pc.nranks - 1) st_release_sys(&pc.box[pc.rank + 1]->halo_flag[0], halo_seq);
@@ -1259,17 +1500,57 @@ static int persistent_grid(Kernel kernel, int64_t blocks_needed) {
     return (int)(blocks_needed < cap ? (blocks_needed > 0 ? blocks_needed : 1) : cap);
 }
 template <int NT, bool TWOX, int CH, int MINB>
-static void launch_spmv_t(const Launcher &l, const SpmvArgs &a) {
+static int spmv_blocks_t(const SpmvArgs &a) {
     static int grid_cap = 0;
     if (!grid_cap) grid_cap = persistent_grid(k_spmv<NT, TWOX, CH, MINB>, 1 << 30);
     const int64_t need = blocks_for((int64_t)a.A.nslices * kSlice, kThreads);
-    launch_pdl(l, k_spmv<NT, TWOX, CH, MINB>, (int)std::min<int64_t>(need, grid_cap), kThreads, a);
+    return (int)std::min<int64_t>(need, grid_cap);
+}
+template <int NT, bool TWOX, int CH, int MINB>
+static void launch_spmv_t(const Launcher &l, const SpmvArgs &a) {
+    launch_pdl(l, k_spmv<NT, TWOX, CH, MINB>, spmv_blocks_t<NT, TWOX, CH, MINB>(a), kThreads, a);
+}
+
+template <bool P2, int NT, bool TWOX, bool UNIT>
+static int spmv_st_blocks_t(const SpmvArgs &a) {
+    static int grid_cap = 0;
+    if (!grid_cap) grid_cap = persistent_grid(k_spmv_st<P2, NT, TWOX, UNIT>, 1 << 30);
+    const int64_t need = blocks_for((int64_t)a.A.nslices * kSlice, kThreads);
+    return (int)std::min<int64_t>(need, grid_cap);
+}
+template <bool P2, int NT, bool TWOX, bool UNIT>
+static void launch_spmv_st_t(const Launcher &l, const SpmvArgs &a) {
+    StencilParams p;  // host tables -> kernel parameter (constant bank)
+    std::memcpy(p.off, a.A.st_meta, sizeof p.off);
+    for (int t = 0; t < 2; ++t)
+        if (t < NT) std::memcpy(p.val[t], a.t[t].tab, sizeof p.val[t]);
+        else std::memset(p.val[t], 0, sizeof p.val[t]);
+    launch_pdl(l, k_spmv_st<P2, NT, TWOX, UNIT>, spmv_st_blocks_t<P2, NT, TWOX, UNIT>(a), kThreads, a, p);
+}
+static bool use_stencil(const SpmvArgs &a) {
+    if (!a.A.slice_info || !a.t[0].tab) return false;
+    return a.t[1].val == nullptr || a.t[1].tab != nullptr;
+}
+static bool unit_coefficients(const SpmvArgs &a) {
+    return a.t[1].val == nullptr && a.t[0].xb == nullptr && a.t[0].ca == 1.0 && a.t[0].coef == 1.0;
+}
+// the grid of the variant the CG iteration launches (single term, single vector, unit coefficients)
+int spmv_launch_blocks(const SpmvArgs &a) {
+    if (use_stencil(a)) return a.A.chunk <= 7 ? spmv_st_blocks_t<false, 1, false, true>(a) : spmv_st_blocks_t<true, 1, false, true>(a);
+    return a.A.chunk <= 7 ? spmv_blocks_t<1, false, 7, 4>(a) : spmv_blocks_t<1, false, 10, 2>(a);
 }
 // chunk = the dominant row length of the element: P1 rows hold 7 entries, P2 rows 19 / 9
 void launch_spmv(const Launcher &l, const SpmvArgs &a) {
     const bool two_terms = a.t[1].val != nullptr;
     const bool twox = a.t[0].xb != nullptr || (two_terms && a.t[1].xb != nullptr);
     const bool p1 = a.A.chunk <= 7;
+    if (use_stencil(a)) {
+        if (unit_coefficients(a)) { if (p1) launch_spmv_st_t<false, 1, false, true>(l, a); else launch_spmv_st_t<true, 1, false, true>(l, a); }
+        else if (!two_terms && !twox) { if (p1) launch_spmv_st_t<false, 1, false, false>(l, a); else launch_spmv_st_t<true, 1, false, false>(l, a); }
+        else if (!two_terms) { if (p1) launch_spmv_st_t<false, 1, true, false>(l, a); else launch_spmv_st_t<true, 1, true, false>(l, a); }
+        else { if (p1) launch_spmv_st_t<false, 2, true, false>(l, a); else launch_spmv_st_t<true, 2, true, false>(l, a); }
+        return;
+    }
     // (CH, blocks/SM) measured on B200: P1 (7, 4) -> 1.05 of the measured copy bandwidth at Nel=4096,
     // P2 (10, 2) -> 0.97; higher occupancy with fewer loads in flight per lane was slower for both
     if (!two_terms && !twox) { if (p1) launch_spmv_t<1, false, 7, 4>(l, a); else launch_spmv_t<1, false, 10, 2>(l, a); }
@@ -1309,13 +1590,24 @@ void launch_dot_gz(const Launcher &l, int n, const double *g, const double *z, d
                    unsigned *counter, double *result, const int *skip_flag) {
     launch_pdl(l, k_dot_gz, stream_blocks(n), kThreads, n, g, z, d_or_null, partials, counter, result, skip_flag);
 }
-void launch_cg_update(const Launcher &l, int n, CgScalars *S, double *g, double *h, const double *dinv,
-                      double *partials, unsigned *counter, const PeerComm &pc, unsigned long long ar_seq) {
-    launch_pdl(l, k_cg_update, stream_blocks(n), kThreads, n, S, g, h, dinv, partials, counter, pc, ar_seq);
+// grid of the CG vector kernels: at most two blocks per SM (four elements per thread and trip), so that a
+// 1 M-row vector still gives every thread ~14 elements and the consumer sums at most 296 partials
+int cg_vector_blocks(int n) {
+    const int64_t need = ((int64_t)n + kThreads * 4 - 1) / (kThreads * 4);
+    const int64_t cap = (int64_t)kSMs * 2;
+    return (int)(need < cap ? (need > 0 ? need : 1) : cap);
 }
-void launch_cg_direction(const Launcher &l, int n, CgScalars *S, double *x, double *d, const double *h,
-                         unsigned *counter, const PeerComm &pc, unsigned long long halo_seq) {
-    launch_pdl(l, k_cg_direction, stream_blocks(n), kThreads, n, S, x, d, h, counter, pc, halo_seq);
+void launch_cg_update(const Launcher &l, int n, int parity, CgScalars *S, double *g, double *h, const double *dinv,
+                      const CgSumIo &in, double *out_partials, unsigned *counter, const PeerComm &pc,
+                      unsigned long long out_seq, int out_mode) {
+    launch_pdl(l, k_cg_update, cg_vector_blocks(n), kThreads, n, parity, S, g, h, dinv, in, out_partials, counter, pc,
+               out_seq, out_mode);
+}
+void launch_cg_direction(const Launcher &l, int n, int k, CgScalars *S, double *x, double *d, const double *h,
+                         const CgSumIo &in, int gh_scalar, unsigned *counter, const PeerComm &pc,
+                         unsigned long long halo_seq) {
+    launch_pdl(l, k_cg_direction, cg_vector_blocks(n), kThreads, n, k, S, x, d, h, in, gh_scalar, counter, pc,
+               halo_seq);
 }
 void launch_newmark_predict(const Launcher &l, int n, double dt, double c1, double c2, double *u, double *v,
                             const double *a) {

@@ -70,19 +70,34 @@ struct Sell {
     int chunk;                  // entries a lane keeps in flight: 7 (P1) or 10 (P2)
     int own_off;                // local column of owned row 0
     // stencil operator (null: none).  slice_info[s] = (kind or -1, first row or -1 when the slice's rows
-    // are not consecutive); st_meta = kStencilKinds x kStencilMax column offsets, then the kStencilKinds
-    // row lengths
+    // are not consecutive), device memory; st_meta = kStencilKinds x kStencilMax column offsets, then the
+    // kStencilKinds row lengths -- a HOST array: the launch copies it into the kernel's parameters
     const int2 *slice_info;
     const int32_t *st_meta;
+    const int32_t *sell_list;   // the slices that are not stencil slices, ascending
+    int n_sell;
+    const int32_t *st_order;    // the stencil slices in tile order (see k_spmv_st)
+    int n_st;
 };
 
-// device-resident CG state (deal.II SolverCG + ReductionControl, src/WaveNewmark.cpp:256-261)
+// device-resident CG state (deal.II SolverCG + ReductionControl, src/WaveNewmark.cpp:256-261).
+// gh and status are double-buffered by the parity of the iteration index: iteration k reads slot k & 1 and
+// its k_cg_direction writes slot (k + 1) & 1, so no kernel ever writes a word that other blocks of the same
+// kernel still read, and no kernel needs a last-block tail for the bookkeeping.
 struct CgScalars {
-    double dAd, gg, gh_new, gh_old;
+    double dAd, gg, gh_new;  // start residual: g.g, g.h (k_spmv result); NCCL-fallback sums; K6f's last values
+    double gh[2];            // g.h of the current residual
+    double alpha;            // step length of the running iteration (k_cg_update's block 0 -> k_cg_direction)
     double res0, reduced_tol, res;
     double tol, reduce;
-    int it, status, maxit, pad;  // status: 0 iterate, 1 success, 2 failure
+    int it, maxit;
+    int status[2];           // 0 iterate, 1 success, 2 failure
+    int peer_timeout, pad;   // a bounded wait on a peer ran out (reported as WAVE_ERR_CUDA)
 };
+// where a consumer kernel finds the sums its predecessor produced
+enum { SUM_PARTIALS = 0,  // per-block partials of the producer, summed by every consumer block in a fixed order
+       SUM_MAILBOX = 1,   // several ranks over NVLink: every rank's total arrives in the local mailbox
+       SUM_SCALAR = 2 };  // totals in CgScalars (NCCL fallback; the multigrid path's g.z)
 
 // ---- NVLink peer exchange inside the CG kernels (nranks > 1) --------------------------------------
 // Every rank owns a small mailbox in device memory that all peers map through CUDA IPC.  The two
@@ -105,14 +120,14 @@ struct PeerComm {
     PeerMailbox *box[kMaxPeers];  // box[rank] is the local mailbox
     double *d_lo, *d_hi;          // where my first / last owned block lives in the neighbours' ghost regions
     int lo_count, hi_count;
-    int *status;
+    int *status;  // &CgScalars::peer_timeout
 };
 
 struct SpmvTerm {
     const double *val;
     const double *xa, *xb;  // local-layout vectors; x = ca*xa + cb*xb
     double ca, cb, coef;
-    const double *tab;      // kStencilKinds x kStencilMax values of the translation-invariant rows (or null)
+    const double *tab;      // HOST array: kStencilKinds x kStencilMax values of the translation-invariant rows (or null)
 };
 struct SpmvArgs {
     Sell A;
@@ -131,7 +146,11 @@ struct SpmvArgs {
     const double *dotv;
     double *partials;
     unsigned *counter;
-    double *result;            // totals (1 or 2 doubles)
+    double *result;            // totals (1 or 2 doubles), written by the last block (null with dot_publish)
+    // dot_publish (CG iteration): leave the sum to the consumer kernel -- per-block partials on one rank
+    // (SUM_PARTIALS, no last-block tail), or this rank's total stored into every peer's mailbox without
+    // waiting (SUM_MAILBOX)
+    int dot_publish;
     const int *skip_flag;      // if non-null and *skip_flag != 0 the kernel returns at once
     // peer exchange (see PeerComm): all-reduce of the dot result, wait for the neighbours' halo
     PeerComm pc;
@@ -193,6 +212,9 @@ void launch_spmv(const Launcher &, const SpmvArgs &);
 void launch_zero_rows(const Launcher &, int nb, const int32_t *brow, double *vec);
 int spmv_grid_blocks(int nslices);
 void launch_cg_start(const Launcher &, CgScalars *S);
+// blocks a publishing SpMV launch uses (the consumer sums that many partials)
+int spmv_launch_blocks(const SpmvArgs &);
+int cg_vector_blocks(int n);
 // ---- multigrid V-cycle pieces (preconditioner WAVE_PRECOND_MG) -----------------------------------
 // x = omega * dinv * b
 void launch_scale_rows(const Launcher &, int n, double omega, const double *dinv, const double *b, double *x,
@@ -210,10 +232,24 @@ void launch_restrict_p2p1(const Launcher &, const Layout &Lf, const Layout &Lc, 
 // result[0] = g.z ; optionally d = -z (CG start)
 void launch_dot_gz(const Launcher &, int n, const double *g, const double *z, double *d_or_null, double *partials,
                    unsigned *counter, double *result, const int *skip_flag);
-void launch_cg_update(const Launcher &, int n, CgScalars *S, double *g, double *h, const double *dinv,
-                      double *partials, unsigned *counter, const PeerComm &pc, unsigned long long ar_seq);
-void launch_cg_direction(const Launcher &, int n, CgScalars *S, double *x, double *d, const double *h,
-                         unsigned *counter, const PeerComm &pc, unsigned long long halo_seq);
+// One CG iteration k (parity = k & 1) after the SpMV h = A d:
+//   k_cg_update:    alpha = gh / dAd ; g += alpha h ; res^2 = g.g ; h = D^-1 g ; gh' = g.h
+//   k_cg_direction: x += alpha d ; iteration_status ; beta = gh'/gh ; d = beta d - h (+ halo stores and flag)
+// dAd comes from `in` (SUM_* mode, partials of `in_blocks` producer blocks / mailbox sequence in_seq / S->dAd);
+// the update's sums go out through `out_partials` (+ mailbox out_seq, or S->gg / S->gh_new).
+struct CgSumIo {
+    int mode;                  // SUM_*
+    const double *partials;    // SUM_PARTIALS: producer's per-block partials
+    int blocks, stride;        // SUM_PARTIALS: number of producer blocks, doubles per block
+    unsigned long long seq;    // SUM_MAILBOX: sequence number of the exchange
+};
+void launch_cg_update(const Launcher &, int n, int parity, CgScalars *S, double *g, double *h, const double *dinv,
+                      const CgSumIo &in, double *out_partials, unsigned *counter, const PeerComm &pc,
+                      unsigned long long out_seq, int out_mode);
+// gh_scalar: take g.h' from S->gh_new (multigrid: k_dot_gz wrote it) instead of the second sum of `in`
+void launch_cg_direction(const Launcher &, int n, int parity, CgScalars *S, double *x, double *d, const double *h,
+                         const CgSumIo &in, int gh_scalar, unsigned *counter, const PeerComm &pc,
+                         unsigned long long halo_seq);
 void launch_newmark_predict(const Launcher &, int n, double dt, double c1, double c2, double *u, double *v,
                             const double *a);
 void launch_newmark_correct(const Launcher &, int n, double cu, double cv, double *u, double *v, const double *a,

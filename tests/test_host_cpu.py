@@ -255,7 +255,9 @@ def test_bench_reference_arm_contract():
     assert line["e2e"] == {"value": line["value"], "unit": "DoF-steps/s", "h2d_bytes_per_step": 0,
                            "d2h_bytes_per_step": 0}
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
-    assert line["config"]["workload"] == "c2-standing-newmark-1024-p1" and line["config"]["n_dofs"] == 49 * 49
+    # the default workload is the north star's P2 Newmark run (WAVE_BENCH_NEL shrinks the mesh for this test)
+    assert line["config"]["workload"] == "newmark-4096-p2" and line["config"]["n_dofs"] == 97 * 97
+    assert line["warmup"] == 3 and line["run"]["steps_timed"] == 2
     # ranks other than 0 print nothing and exit 0 (torchrun launch of the reference arm)
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1"],
                        capture_output=True, text=True, timeout=60, env=dict(env, RANK="1", WORLD_SIZE="2"))

@@ -21,12 +21,14 @@ def main():
     ap.add_argument("--dt", default="0.01")
     ap.add_argument("--cg", action="store_true")
     ap.add_argument("--steps", type=int, default=0)
+    ap.add_argument("--no-init", action="store_true", help="skip wave_init: only the SpMV launches (ncu captures)")
     args = ap.parse_args()
     from wavegpu import WaveSolver, api, problem
 
     p = problem("standing-mode-wsol", Nel=args.nel, R=args.r, Dt=args.dt)
     g = WaveSolver(p, args.scheme)
-    g.init()
+    if not args.no_init:
+        g.init()
     peak = 6549.4
     out = {"nel": args.nel, "r": args.r, "n": g.n, "nnz": g.nnz_local}
     ms, nbytes = g.bench_spmv(api.MAT_SYS1, reps=args.reps, flush_l2=False)
