@@ -133,7 +133,8 @@ struct wave_ctx {
     double *st_tab = nullptr;
     int32_t *st_meta = nullptr;
     int2 *slice_info = nullptr;
-    int32_t *sell_list = nullptr, *st_order = nullptr;
+    int32_t *sell_list = nullptr;
+    int2 *st_walk = nullptr;
     std::vector<int32_t> h_st_meta;  // host copies: the launches pass them as kernel parameters
     std::vector<double> h_tab;
     int64_t stencil_rows = 0, sell_nnz = 0;
@@ -968,16 +969,30 @@ int stencil_setup(wave_ctx *ctx) {
             }
             keyed.emplace_back(key, sl);
         }
+        const char *ord = std::getenv("WAVE_STENCIL_ORDER");  // experiment knob: "linear" = ascending slices
+        if (ord && std::string(ord) == "linear")
+            for (auto &kv : keyed) kv.first = (uint64_t)kv.second;
         std::sort(keyed.begin(), keyed.end());
-        std::vector<int32_t> order(keyed.size());
-        for (size_t k = 0; k < keyed.size(); ++k) order[k] = keyed[k].second;
-        RET(dev_alloc(ctx, &ctx->st_order, order.size(), false));
-        if (!order.empty())
-            CK(cudaMemcpyAsync(ctx->st_order, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice,
-                               ctx->stream));
+        // several ranks: rotate the walk by half its length (ghost-reading slices mid-kernel) and mark them
+        const int nr = ctx->cfg.nranks, rk = ctx->cfg.rank;
+        int lo_count = 0, hi_count = 0;
+        if (nr > 1 && rk > 0) lo_count = (int)(block_start(m, L.jq0 + 1) - block_start(m, L.jq0));
+        if (nr > 1 && rk < nr - 1) hi_count = (int)(block_start(m, L.jq1) - block_start(m, L.jq1 - 1));
+        const int ghost_lo = lo_count ? ((lo_count + kWindow - 1) / kWindow) * (kWindow / kSlice) : 0;
+        const int ghost_hi0 = hi_count ? ((L.nown - hi_count) / kWindow) * (kWindow / kSlice) : ctx->nslices;
+        const size_t n_st = keyed.size(), rot = nr > 1 ? n_st / 2 : 0;
+        std::vector<int2> order(n_st + (size_t)kStencilPad, make_int2(-1, -1));
+        for (size_t k = 0; k < n_st; ++k) {
+            const int32_t sl = keyed[(k + rot) % n_st].second;
+            const int ghost = (sl < ghost_lo || sl >= ghost_hi0) ? 1 : 0;
+            order[k] = make_int2(sl | (ghost << 27) | (info[(size_t)sl].x << 28), info[(size_t)sl].y);
+        }
+        RET(dev_alloc(ctx, &ctx->st_walk, order.size(), false));
+        CK(cudaMemcpyAsync(ctx->st_walk, order.data(), sizeof(int2) * order.size(), cudaMemcpyHostToDevice,
+                           ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        ctx->A.st_order = ctx->st_order;
-        ctx->A.n_st = (int)order.size();
+        ctx->A.st_walk = ctx->st_walk;
+        ctx->A.n_st = (int)n_st;
     }
     RET(dev_alloc(ctx, &ctx->sell_list, list.size(), false));
     if (!list.empty())
@@ -1246,7 +1261,7 @@ void wave_destroy(wave_ctx *ctx) {
     for (void *q : {(void *)ctx->fused.blk_c0, (void *)ctx->fused.blk_cn, (void *)ctx->fused.partials,
                     (void *)ctx->fused.pub})
         if (q) cudaFree(q);
-    void *ptrs[] = {ctx->st_tab, ctx->st_meta, ctx->slice_info, ctx->sell_list, ctx->st_order, ctx->dprog, ctx->rowptr, ctx->slice_ptr, ctx->row_of, ctx->slot_of, ctx->col, ctx->c2i, ctx->i2c, ctx->tmp, ctx->M, ctx->K, ctx->S1, ctx->S2, ctx->dinv1, ctx->dinv2,
+    void *ptrs[] = {ctx->st_tab, ctx->st_meta, ctx->slice_info, ctx->sell_list, ctx->st_walk, ctx->dprog, ctx->rowptr, ctx->slice_ptr, ctx->row_of, ctx->slot_of, ctx->col, ctx->c2i, ctx->i2c, ctx->tmp, ctx->M, ctx->K, ctx->S1, ctx->S2, ctx->dinv1, ctx->dinv2,
                     ctx->d0, ctx->u, ctx->v, ctx->a, ctx->unew, ctx->d, ctx->rhs, ctx->fvec, ctx->cellvec, ctx->g, ctx->h,
                     ctx->scratch, ctx->brow, ctx->bx, ctx->by, ctx->partials, ctx->partials2, ctx->partials3, ctx->counter, ctx->S, ctx->res,
                     ctx->flush_buf};
@@ -1810,9 +1825,13 @@ int wave_bench_spmv(wave_ctx *ctx, int which, int reps, int flush_l2, double *ms
     const double *val = mat_ptr(ctx, which);
     if (!val || reps < 1) return fail(ctx, WAVE_ERR_ARG, "bad matrix id / reps");
     if (flush_l2) RET(ensure_flush(ctx));
+    // the launch of the CG iteration: y = A x with the fused x . y (per-block partials left for a consumer)
     SpmvArgs a = spmv_base(ctx);
     a.t[0] = {val, ctx->u, nullptr, 1.0, 0.0, 1.0};
     a.y = ctx->h;
+    a.dot_mode = 1;
+    a.dotv = ctx->u + ctx->L.own_off;
+    a.dot_publish = 1;
     cudaEvent_t e0 = ctx->ev[2 * PH_COUNT + 2], e1 = ctx->ev[2 * PH_COUNT + 3];
     for (int w = 0; w < 3; ++w) spmv(ctx, ctx->launcher, a);
     CK(cudaStreamSynchronize(ctx->stream));

@@ -882,8 +882,13 @@ __device__ __forceinline__ double stencil_row_of_kind(const SpmvArgs &a, const S
     default: return stencil_row<9, 9, NT, TWOX, UNIT, CG>(a, p, 3, cself);
     }
 }
-template <bool P2, int NT, bool TWOX, bool UNIT>
-__global__ void __launch_bounds__(kThreads, P2 ? 3 : 4) k_spmv_st(SpmvArgs a, const __grid_constant__ StencilParams p) {
+__device__ __forceinline__ void prefetch_l2(const double *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// CGEPI: the CG iteration's launch (y = A d, d . y) gets a two-instruction epilogue instead of the generic one
+template <bool P2, int NT, bool TWOX, bool UNIT, bool CGEPI>
+__global__ void __launch_bounds__(kThreads, (P2 && !(UNIT && NT == 1)) ? 3 : 4) k_spmv_st(
+    SpmvArgs a, const __grid_constant__ StencilParams p) {
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
     if (a.skip_flag && *a.skip_flag != 0) return;
@@ -891,44 +896,43 @@ __global__ void __launch_bounds__(kThreads, P2 ? 3 : 4) k_spmv_st(SpmvArgs a, co
     const int nwarps = gridDim.x * (kThreads / 32);
     const int warp0 = (blockIdx.x * kThreads + threadIdx.x) >> 5;
     double dots[2] = {0.0, 0.0};
-    const int rot = a.halo_wait_seq ? a.A.n_st / 2 : 0;  // see k_spmv: ghost-reading slices come mid-kernel
     bool halo_ready = a.halo_wait_seq == 0;
-    // ---- phase 1: stencil slices, in tile order (st_order: the warps of a block take slices of the same
-    // column range in neighbouring DoF lines and kinds, so their x gathers share L1 lines) ---------------
+    // ---- phase 1: stencil slices, in the order of st_walk.  The host lays the walk out in tiles (the warps
+    // of a block take slices of one column range in neighbouring DoF lines and kinds, so their x gathers
+    // share L1 lines), rotates it for several ranks so that the ghost-reading slices at both ends of the
+    // rank's rows are reached mid-kernel (their halo has long arrived by then), and terminates it with
+    // sentinel entries, so a warp just follows a pointer.  Every x entry is some row's own column: each
+    // warp asks L2 for the own-column segment of the slice it will take kStencilPrefetch trips later, so
+    // the gathers find their lines in L2 instead of paying the HBM latency with a line or two in flight.
     {
-        const int n_st = a.A.n_st;
-        int it = warp0;
-        int2 si = make_int2(-1, -1);
-        int slice = -1;
-        if (it < n_st) {
-            slice = a.A.st_order[it + rot < n_st ? it + rot : it + rot - n_st];
-            si = a.A.slice_info[slice];
-        }
-        while (it < n_st) {
-            const int nit = it + nwarps;
-            int nslice = -1;
-            int2 nsi = make_int2(-1, -1);
-            if (nit < n_st) {
-                nslice = a.A.st_order[nit + rot < n_st ? nit + rot : nit + rot - n_st];
-                nsi = a.A.slice_info[nslice];
-            }
-            const int kind = si.x;
-            {
-                const int r = si.y >= 0 ? si.y + lane : a.A.row_of[slice * kSlice + lane];
-                const int cself = r + a.A.own_off;
-                const bool ghosty = a.pc.enabled && (slice < a.ghost_lo_slices || slice >= a.ghost_hi_slice0);
-                double s;
-                if (ghosty) {  // rare (both ends of a rank's rows): wait for the halo, gather through L2
-                    if (!halo_ready) {
-                        halo_wait(a, lane);
-                        halo_ready = true;
-                    }
-                    s = stencil_row_of_kind<P2, NT, TWOX, UNIT, true>(a, p, kind, cself);
-                } else
-                    s = stencil_row_of_kind<P2, NT, TWOX, UNIT, false>(a, p, kind, cself);
+        const int2 *w = a.A.st_walk + warp0;
+        const size_t step = (size_t)nwarps;
+        int2 wm = *w;                                  // (slice | ghost << 27 | kind << 28, first row or -1)
+        int pf_row = w[step * kStencilPrefetch].y;
+        while (wm.x >= 0) {
+            w += step;
+            const int2 nwm = *w;
+            if (pf_row >= 0) prefetch_l2(a.t[0].xa + (pf_row + lane + a.A.own_off));
+            pf_row = w[step * kStencilPrefetch].y;
+            const int kind = wm.x >> 28;
+            int r = wm.y + lane;
+            if (wm.y < 0) r = a.A.row_of[(wm.x & 0x07ffffff) * kSlice + lane];
+            const int cself = r + a.A.own_off;
+            double s;
+            if (wm.x & (1 << 27)) {  // reads ghost entries (several ranks): wait for the halo, gather through L2
+                if (!halo_ready) {
+                    halo_wait(a, lane);
+                    halo_ready = true;
+                }
+                s = stencil_row_of_kind<P2, NT, TWOX, UNIT, true>(a, p, kind, cself);
+            } else
+                s = stencil_row_of_kind<P2, NT, TWOX, UNIT, false>(a, p, kind, cself);
+            if (CGEPI) {
+                a.y[r] = s;
+                dots[0] += s * a.dotv[r];
+            } else
                 spmv_epilogue(a, r, s, dots);
-            }
-            it = nit; slice = nslice; si = nsi;
+            wm = nwm;
         }
     }
     // ---- phase 2: the slices kept in SELL form -------------------------------------------------------
@@ -1511,21 +1515,21 @@ static void launch_spmv_t(const Launcher &l, const SpmvArgs &a) {
     launch_pdl(l, k_spmv<NT, TWOX, CH, MINB>, spmv_blocks_t<NT, TWOX, CH, MINB>(a), kThreads, a);
 }
 
-template <bool P2, int NT, bool TWOX, bool UNIT>
+template <bool P2, int NT, bool TWOX, bool UNIT, bool CGEPI = false>
 static int spmv_st_blocks_t(const SpmvArgs &a) {
     static int grid_cap = 0;
-    if (!grid_cap) grid_cap = persistent_grid(k_spmv_st<P2, NT, TWOX, UNIT>, 1 << 30);
+    if (!grid_cap) grid_cap = persistent_grid(k_spmv_st<P2, NT, TWOX, UNIT, CGEPI>, 1 << 30);
     const int64_t need = blocks_for((int64_t)a.A.nslices * kSlice, kThreads);
     return (int)std::min<int64_t>(need, grid_cap);
 }
-template <bool P2, int NT, bool TWOX, bool UNIT>
+template <bool P2, int NT, bool TWOX, bool UNIT, bool CGEPI = false>
 static void launch_spmv_st_t(const Launcher &l, const SpmvArgs &a) {
     StencilParams p;  // host tables -> kernel parameter (constant bank)
     std::memcpy(p.off, a.A.st_meta, sizeof p.off);
     for (int t = 0; t < 2; ++t)
         if (t < NT) std::memcpy(p.val[t], a.t[t].tab, sizeof p.val[t]);
         else std::memset(p.val[t], 0, sizeof p.val[t]);
-    launch_pdl(l, k_spmv_st<P2, NT, TWOX, UNIT>, spmv_st_blocks_t<P2, NT, TWOX, UNIT>(a), kThreads, a, p);
+    launch_pdl(l, k_spmv_st<P2, NT, TWOX, UNIT, CGEPI>, spmv_st_blocks_t<P2, NT, TWOX, UNIT, CGEPI>(a), kThreads, a, p);
 }
 static bool use_stencil(const SpmvArgs &a) {
     if (!a.A.slice_info || !a.t[0].tab) return false;
@@ -1534,9 +1538,14 @@ static bool use_stencil(const SpmvArgs &a) {
 static bool unit_coefficients(const SpmvArgs &a) {
     return a.t[1].val == nullptr && a.t[0].xb == nullptr && a.t[0].ca == 1.0 && a.t[0].coef == 1.0;
 }
+// the CG iteration's launch: y = A d and d . y, nothing else in the epilogue
+static bool cg_epilogue(const SpmvArgs &a) {
+    return unit_coefficients(a) && a.y && a.dot_mode == 1 && !a.add0 && !a.add1 && !a.jac_x && !a.h_out;
+}
 // the grid of the variant the CG iteration launches (single term, single vector, unit coefficients)
 int spmv_launch_blocks(const SpmvArgs &a) {
-    if (use_stencil(a)) return a.A.chunk <= 7 ? spmv_st_blocks_t<false, 1, false, true>(a) : spmv_st_blocks_t<true, 1, false, true>(a);
+    if (use_stencil(a))
+        return a.A.chunk <= 7 ? spmv_st_blocks_t<false, 1, false, true, true>(a) : spmv_st_blocks_t<true, 1, false, true, true>(a);
     return a.A.chunk <= 7 ? spmv_blocks_t<1, false, 7, 4>(a) : spmv_blocks_t<1, false, 10, 2>(a);
 }
 // chunk = the dominant row length of the element: P1 rows hold 7 entries, P2 rows 19 / 9
@@ -1545,7 +1554,8 @@ void launch_spmv(const Launcher &l, const SpmvArgs &a) {
     const bool twox = a.t[0].xb != nullptr || (two_terms && a.t[1].xb != nullptr);
     const bool p1 = a.A.chunk <= 7;
     if (use_stencil(a)) {
-        if (unit_coefficients(a)) { if (p1) launch_spmv_st_t<false, 1, false, true>(l, a); else launch_spmv_st_t<true, 1, false, true>(l, a); }
+        if (cg_epilogue(a)) { if (p1) launch_spmv_st_t<false, 1, false, true, true>(l, a); else launch_spmv_st_t<true, 1, false, true, true>(l, a); }
+        else if (unit_coefficients(a)) { if (p1) launch_spmv_st_t<false, 1, false, true>(l, a); else launch_spmv_st_t<true, 1, false, true>(l, a); }
         else if (!two_terms && !twox) { if (p1) launch_spmv_st_t<false, 1, false, false>(l, a); else launch_spmv_st_t<true, 1, false, false>(l, a); }
         else if (!two_terms) { if (p1) launch_spmv_st_t<false, 1, true, false>(l, a); else launch_spmv_st_t<true, 1, true, false>(l, a); }
         else { if (p1) launch_spmv_st_t<false, 2, true, false>(l, a); else launch_spmv_st_t<true, 2, true, false>(l, a); }

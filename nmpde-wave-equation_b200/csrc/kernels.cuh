@@ -60,6 +60,8 @@ constexpr int kWindow = 1024;
 // arrays.  The sum of a row runs over the same entries in the same order with the same arithmetic.
 constexpr int kStencilMax = 20;  // entries of the longest translation-invariant row (P2 vertex row: 19)
 constexpr int kStencilKinds = 4;
+constexpr int kStencilPrefetch = 3;                                  // trips between the L2 prefetch and the use
+constexpr int kStencilPad = (kStencilPrefetch + 1) * 148 * 8 * 8;    // >= (prefetch + 1) x warps of the largest grid
 struct Sell {
     const uint32_t *slice_ptr;  // nslices + 1, element offsets (multiples of 32)
     const int32_t *col;         // padded local column indices (padding: a valid column, value 0)
@@ -76,7 +78,9 @@ struct Sell {
     const int32_t *st_meta;
     const int32_t *sell_list;   // the slices that are not stencil slices, ascending
     int n_sell;
-    const int32_t *st_order;    // the stencil slices in tile order (see k_spmv_st)
+    // the stencil slices in walk order (see k_spmv_st): (slice | ghost << 27 | kind << 28, first row or -1),
+    // followed by kStencilPad sentinel entries (-1, -1)
+    const int2 *st_walk;
     int n_st;
 };
 
