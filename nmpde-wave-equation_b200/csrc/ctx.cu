@@ -31,6 +31,7 @@ namespace {
 constexpr int kSMsFallback = 148;  // B200
 
 thread_local std::string g_create_error;
+thread_local void *g_child_comm = nullptr;  // mg_setup -> wave_create: the parent's communicator for a multigrid level
 
 // ---- NCCL, loaded on demand (single-GPU contexts never touch it) ----------------------------------
 struct Nccl {
@@ -180,6 +181,7 @@ struct wave_ctx {
 
     // NCCL + NVLink peer exchange
     Nccl::comm_t comm = nullptr;
+    bool own_comm = true;                // multigrid levels borrow the solver context's communicator
     PeerComm pc{};                       // enabled only for 1 < nranks <= kMaxPeers
     PeerMailbox *mailbox = nullptr;
     void *ipc_opened[2 * kMaxPeers]{};   // mapped peer allocations (closed in wave_destroy)
@@ -378,57 +380,67 @@ void spmv(const wave_ctx *owner, const Launcher &l, SpmvArgs &a) {
 // SolverCG::solve (src/WaveNewmark.cpp:256-261): Jacobi-PCG on the BC-modified matrix `Sval`,
 // start vector x (local layout), right-hand side b (row-indexed).
 // V-cycle on level l: lev.x <- approximate solution of S x = lev.b from x = 0 (all launches asynchronous)
-void mg_smooth(wave_ctx *ctx, MgLevel &lv, int sweeps, bool x_is_zero, const int *skip) {
+// x, x2, r of a level are local-layout vectors (ghost blocks included), b is row-indexed.  With several
+// ranks every SpMV is preceded by the halo exchange of its input (NCCL send/recv of the two ghost blocks).
+int mg_smooth(wave_ctx *ctx, MgLevel &lv, int sweeps, bool x_is_zero, const int *skip) {
     wave_ctx *c = lv.c;
+    const int off = c->L.own_off;
     for (int sw = 0; sw < sweeps; ++sw) {
         if (sw == 0 && x_is_zero) {
-            launch_scale_rows(ctx->launcher, c->L.nown, lv.omega, lv.dinv, lv.b, lv.x, skip);
+            launch_scale_rows(ctx->launcher, c->L.nown, lv.omega, lv.dinv, lv.b, lv.x + off, skip);
             continue;
         }
+        RET(halo_exchange(c, lv.x));
         SpmvArgs a = spmv_base(c);
         a.partials = ctx->partials;
         a.counter = ctx->counter;
         a.t[0] = {lv.S, lv.x, nullptr, 1.0, 0.0, -1.0};
         a.add0 = lv.b; a.addc0 = 1.0;
-        a.dinv = lv.dinv; a.jac_x = lv.x; a.jac_omega = lv.omega;
-        a.y = lv.x2;
+        a.dinv = lv.dinv; a.jac_x = lv.x + off; a.jac_omega = lv.omega;
+        a.y = lv.x2 + off;
         a.skip_flag = skip;
         spmv(c, ctx->launcher, a);
         std::swap(lv.x, lv.x2);
     }
+    return WAVE_OK;
 }
-void mg_vcycle(wave_ctx *ctx, int l, const int *skip) {
+int mg_vcycle(wave_ctx *ctx, int l, const int *skip) {
     Mg &m = *ctx->mg;
     MgLevel &lv = m.lev[l];
-    if (l == m.nlev - 1) { mg_smooth(ctx, lv, m.nu_coarse, true, skip); return; }
-    mg_smooth(ctx, lv, m.nu, true, skip);
+    if (l == m.nlev - 1) return mg_smooth(ctx, lv, m.nu_coarse, true, skip);
+    RET(mg_smooth(ctx, lv, m.nu, true, skip));
     {   // r = b - S x
+        RET(halo_exchange(lv.c, lv.x));
         SpmvArgs a = spmv_base(lv.c);
         a.partials = ctx->partials;
         a.counter = ctx->counter;
         a.t[0] = {lv.S, lv.x, nullptr, 1.0, 0.0, -1.0};
         a.add0 = lv.b; a.addc0 = 1.0;
-        a.y = lv.r;
+        a.y = lv.r + lv.c->L.own_off;
         a.skip_flag = skip;
         spmv(lv.c, ctx->launcher, a);
     }
     MgLevel &cv = m.lev[l + 1];
     const bool p_coarsening = lv.c->L.mesh.r == 2;
+    RET(halo_exchange(lv.c, lv.r));  // restriction reads the fine residual of the upper ghost block
     if (p_coarsening) launch_restrict_p2p1(ctx->launcher, lv.c->L, cv.c->L, lv.r, cv.b, skip);
     else launch_restrict_p1(ctx->launcher, lv.c->L, cv.c->L, lv.r, cv.b, skip);
-    mg_vcycle(ctx, l + 1, skip);
+    RET(mg_vcycle(ctx, l + 1, skip));
+    RET(halo_exchange(cv.c, cv.x));  // prolongation reads the coarse correction of the lower ghost block
     if (p_coarsening) launch_prolong_add_p2p1(ctx->launcher, lv.c->L, cv.c->L, cv.x, lv.x, skip);
     else launch_prolong_add_p1(ctx->launcher, lv.c->L, cv.c->L, cv.x, lv.x, skip);
-    mg_smooth(ctx, lv, m.nu, false, skip);
+    return mg_smooth(ctx, lv, m.nu, false, skip);
 }
-// z = V-cycle(g) on the fine level; returns the vector holding z
-const double *mg_apply(wave_ctx *ctx, const double *Sval, const double *dinv, const double *g, const int *skip) {
+// z = V-cycle(g) on the fine level; *z = the (row-indexed) vector holding it
+int mg_apply(wave_ctx *ctx, const double *Sval, const double *dinv, const double *g, const int *skip,
+             const double **z) {
     MgLevel &f = ctx->mg->lev[0];
     f.S = Sval;
     f.dinv = dinv;
     f.b = const_cast<double *>(g);
-    mg_vcycle(ctx, 0, skip);
-    return f.x;
+    RET(mg_vcycle(ctx, 0, skip));
+    *z = f.x + ctx->L.own_off;
+    return WAVE_OK;
 }
 
 int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, const double *b, int slot,
@@ -452,7 +464,8 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
         spmv(ctx, l, a);
     }
     if (use_mg) {  // h = V-cycle(g) ; d = -h ; gh = g.h
-        const double *z = mg_apply(ctx, Sval, dinv, ctx->g, &ctx->S->status[0]);
+        const double *z = nullptr;
+        RET(mg_apply(ctx, Sval, dinv, ctx->g, &ctx->S->status[0], &z));
         launch_dot_gz(l, L.nown, ctx->g, z, ctx->d + L.own_off, ctx->partials, ctx->counter, &ctx->S->gh_new, nullptr);
     }
     RET(allreduce(ctx, &ctx->S->gg, 2));
@@ -534,10 +547,11 @@ int cg_solve(wave_ctx *ctx, const double *Sval, const double *dinv, double *x, c
                                  ctx->counter, p2p ? ctx->pc : PeerComm{}, seq_b, sum_mode);
             }
             const double *z = ctx->h;
-            if (use_mg) {  // h' = V-cycle(g) ; gh' = g.h'
-                z = mg_apply(ctx, Sval, dinv, ctx->g, &ctx->S->status[parity]);
+            if (use_mg) {  // h' = V-cycle(g) ; gh' = g.h' (all-reduced over NCCL: a handful of iterations per solve)
+                RET(mg_apply(ctx, Sval, dinv, ctx->g, &ctx->S->status[parity], &z));
                 launch_dot_gz(l, L.nown, ctx->g, z, nullptr, ctx->partials3, ctx->counter, &ctx->S->gh_new,
                               &ctx->S->status[parity]);
+                if (sum_mode != SUM_SCALAR) RET(allreduce(ctx, &ctx->S->gh_new, 1));
             }
             if (sum_mode == SUM_SCALAR) RET(allreduce(ctx, &ctx->S->gg, 2));
             const unsigned long long seq_h = p2p ? ++ctx->halo_seq : 0ull;
@@ -1024,7 +1038,7 @@ int mg_setup(wave_ctx *ctx, double s) {
     for (int k = 0; k < 3; ++k)
         if (!ctx->mg_buf[k]) RET(dev_alloc(ctx, &ctx->mg_buf[k], (size_t)L.nloc));
     m->lev[0].c = ctx;
-    m->lev[0].x = ctx->mg_buf[0];
+    m->lev[0].x = ctx->mg_buf[0];   // local layout (nloc), as x2 and r
     m->lev[0].x2 = ctx->mg_buf[1];
     m->lev[0].r = ctx->mg_buf[2];
     m->lev[0].omega = L.mesh.r == 2 ? 0.5 : 0.8;
@@ -1038,6 +1052,16 @@ int mg_setup(wave_ctx *ctx, double s) {
             const double dx = (ctx->cfg.x1 - ctx->cfg.x0) / nx, dy = (ctx->cfg.y1 - ctx->cfg.y0) / ny;
             const bool matters = s * c0 * c0 / (dx * dy) > 0.25;
             if (!(matters && nx % 2 == 0 && ny % 2 == 0 && std::min(nx, ny) / 2 >= 2)) break;
+            // several ranks: coarse quad row J covers the fine quad rows 2J, 2J+1, so every strip must begin
+            // and end at an even quad row and keep at least two coarse quad rows (same decision on all ranks)
+            bool strips_ok = true;
+            for (int rk = 0; rk < ctx->cfg.nranks && ctx->cfg.nranks > 1; ++rk) {
+                int j0, j1, c0r, c1r;
+                quad_row_split(ny, rk, ctx->cfg.nranks, j0, j1);
+                quad_row_split(ny / 2, rk, ctx->cfg.nranks, c0r, c1r);
+                strips_ok = strips_ok && j0 % 2 == 0 && j1 % 2 == 0 && c0r == j0 / 2 && c1r == j1 / 2 && c1r - c0r >= 2;
+            }
+            if (!strips_ok) break;
             nnx = nx / 2;
             nny = ny / 2;
         }
@@ -1045,7 +1069,7 @@ int mg_setup(wave_ctx *ctx, double s) {
         wave_config cfg = ctx->cfg;
         cfg.nx = nnx; cfg.ny = nny; cfg.r = 1;
         cfg.scheme = WAVE_SCHEME_NEWMARK;
-        cfg.rank = 0; cfg.nranks = 1; cfg.nccl_unique_id = nullptr; cfg.device = -1;
+        cfg.nccl_unique_id = nullptr; cfg.device = -1;  // rank / nranks of the solver context, its communicator
         cfg.precond = WAVE_PRECOND_JACOBI;
         cfg.flags = kFlagChild | (ctx->cfg.flags & WAVE_FLAG_NO_STENCIL);
         cfg.stream = ctx->stream;
@@ -1054,7 +1078,10 @@ int mg_setup(wave_ctx *ctx, double s) {
             for (int l = 1; l < m->nlev; ++l) wave_destroy(m->lev[l].c);
             delete m;
         };
-        if (wave_create(&cfg, &c) != WAVE_OK) { drop_levels(); return fail(ctx, WAVE_ERR_CUDA, wave_last_error(nullptr)); }
+        g_child_comm = ctx->comm;
+        const int crc = wave_create(&cfg, &c);
+        g_child_comm = nullptr;
+        if (crc != WAVE_OK) { drop_levels(); return fail(ctx, WAVE_ERR_CUDA, wave_last_error(nullptr)); }
         const Program zero = compile_expression("0.0", "x, y, t", "");
         for (int k = 0; k < WAVE_EXPR_SOLUTION; ++k) {
             c->hprog[k] = k == WAVE_EXPR_C ? ctx->hprog[k] : zero;
@@ -1076,7 +1103,7 @@ int mg_setup(wave_ctx *ctx, double s) {
         lv.x = c->u;
         lv.x2 = c->unew;
         lv.b = c->rhs;
-        lv.r = c->g;
+        lv.r = c->d;  // local layout: the restriction reads its upper ghost block
         lv.omega = 0.8;
         ctx->launches += c->launches;
         nx = nnx; ny = nny; r = 1;
@@ -1091,7 +1118,7 @@ int mg_setup(wave_ctx *ctx, double s) {
 // when WAVE_NO_P2P is set.
 int setup_peer_exchange(wave_ctx *ctx) {
     const int R = ctx->cfg.nranks, rank = ctx->cfg.rank;
-    if (R == 1 || R > kMaxPeers || std::getenv("WAVE_NO_P2P")) return WAVE_OK;
+    if (R == 1 || R > kMaxPeers || std::getenv("WAVE_NO_P2P") || (ctx->cfg.flags & kFlagChild)) return WAVE_OK;
     RET(dev_alloc(ctx, &ctx->mailbox, 1));
     struct Handles { cudaIpcMemHandle_t box, d; };
     std::vector<Handles> all((size_t)R);
@@ -1192,8 +1219,6 @@ int wave_create(const wave_config *cfg, wave_ctx **out) {
     if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks)
         return fail(nullptr, WAVE_ERR_ARG, "bad rank / nranks");
     if (cfg->ny < cfg->nranks) return fail(nullptr, WAVE_ERR_ARG, "need at least one quad row per rank");
-    if (cfg->precond == WAVE_PRECOND_MG && cfg->nranks > 1)
-        return fail(nullptr, WAVE_ERR_UNSUPPORTED, "the multigrid preconditioner runs on a single rank");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(nullptr, WAVE_ERR_CUDA, "no CUDA device: libwavegpu has no CPU fallback");
@@ -1229,7 +1254,11 @@ int wave_create(const wave_config *cfg, wave_ctx **out) {
         ctx->err = "local problem exceeds 32-bit CSR offsets: partition over more GPUs";
         return bail(WAVE_ERR_UNSUPPORTED);
     }
-    if (cfg->nranks > 1) {
+    if (cfg->nranks > 1 && (cfg->flags & kFlagChild)) {
+        ctx->comm = (Nccl::comm_t)g_child_comm;
+        ctx->own_comm = false;
+        if (!ctx->comm) { ctx->err = "multigrid level without a communicator"; return bail(WAVE_ERR_ARG); }
+    } else if (cfg->nranks > 1) {
         if (!cfg->nccl_unique_id) { ctx->err = "nccl_unique_id required for nranks > 1"; return bail(WAVE_ERR_ARG); }
         if (!g_nccl.load(ctx->err)) return bail(WAVE_ERR_CUDA);
         Nccl::Uid id;
@@ -1269,7 +1298,7 @@ void wave_destroy(wave_ctx *ctx) {
         if (p) cudaFree(p);
     if (ctx->hS) cudaFreeHost(ctx->hS);
     if (ctx->hres) cudaFreeHost(ctx->hres);
-    if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
+    if (ctx->comm && ctx->own_comm) g_nccl.CommDestroy(ctx->comm);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
     for (auto &e : ctx->spmv_ev)

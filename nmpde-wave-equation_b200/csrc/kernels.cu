@@ -1125,71 +1125,94 @@ __global__ void k_scale_rows(int n, double omega, const double *__restrict__ din
     const int stride = gridDim.x * blockDim.x;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = omega * (dinv[i] * b[i]);
 }
-__global__ void k_prolong_add_p1(Mesh mf, Mesh mc, const double *__restrict__ ec, double *__restrict__ xf,
+// All four transfers are written for a rank's strip: one thread per owned DoF of the target level; the
+// source vector is in local layout (ghost blocks valid: the caller exchanged its halo).  Restriction needs
+// the fine level's upper ghost block, prolongation the coarse level's lower one (coarse quad row J covers
+// the fine quad rows 2J, 2J+1, so both levels split at the same physical lines).
+__global__ void k_prolong_add_p1(Layout Lf, Layout Lc, const double *__restrict__ ec, double *__restrict__ xf,
                                  const int *skip_flag) {
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
     if (skip_flag && *skip_flag != 0) return;
+    const Mesh &mf = Lf.mesh, &mc = Lc.mesh;
+    const SlotRange s = owned_slots(Lf);
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)(mf.nx + 1) * (mf.ny + 1)) return;
-    const int I = (int)(t % (mf.nx + 1)), J = (int)(t / (mf.nx + 1));
+    if (t >= slot_count(Lf, s)) return;
+    int I, J, kind;
+    decode_slot(Lf, s, t, I, J, kind);
+    const int64_t dof = dof_V(mf, I, J);
+    if (dof < Lf.row0 || dof >= Lf.row0 + Lf.nown) return;
+    auto c = [&](int i, int j) { return ec[dof_V(mc, i, j) - Lc.col0]; };
     double v;
-    if (!(I & 1) && !(J & 1)) v = ec[dof_V(mc, I / 2, J / 2)];
-    else if ((I & 1) && !(J & 1)) v = 0.5 * (ec[dof_V(mc, (I - 1) / 2, J / 2)] + ec[dof_V(mc, (I + 1) / 2, J / 2)]);
-    else if (!(I & 1)) v = 0.5 * (ec[dof_V(mc, I / 2, (J - 1) / 2)] + ec[dof_V(mc, I / 2, (J + 1) / 2)]);
-    else v = 0.5 * (ec[dof_V(mc, (I + 1) / 2, (J - 1) / 2)] + ec[dof_V(mc, (I - 1) / 2, (J + 1) / 2)]);
-    xf[dof_V(mf, I, J)] += v;
+    if (!(I & 1) && !(J & 1)) v = c(I / 2, J / 2);
+    else if ((I & 1) && !(J & 1)) v = 0.5 * (c((I - 1) / 2, J / 2) + c((I + 1) / 2, J / 2));
+    else if (!(I & 1)) v = 0.5 * (c(I / 2, (J - 1) / 2) + c(I / 2, (J + 1) / 2));
+    else v = 0.5 * (c((I + 1) / 2, (J - 1) / 2) + c((I - 1) / 2, (J + 1) / 2));
+    xf[dof - Lf.col0] += v;
 }
-__global__ void k_restrict_p1(Mesh mf, Mesh mc, const double *__restrict__ rf, double *__restrict__ bc,
+__global__ void k_restrict_p1(Layout Lf, Layout Lc, const double *__restrict__ rf, double *__restrict__ bc,
                               const int *skip_flag) {
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
     if (skip_flag && *skip_flag != 0) return;
+    const Mesh &mf = Lf.mesh, &mc = Lc.mesh;
+    const SlotRange s = owned_slots(Lc);
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)(mc.nx + 1) * (mc.ny + 1)) return;
-    const int i = (int)(t % (mc.nx + 1)), j = (int)(t / (mc.nx + 1));
-    double s = 0.0;
+    if (t >= slot_count(Lc, s)) return;
+    int i, j, kind;
+    decode_slot(Lc, s, t, i, j, kind);
+    const int64_t dof = dof_V(mc, i, j);
+    if (dof < Lc.row0 || dof >= Lc.row0 + Lc.nown) return;
+    auto f = [&](int I, int J) { return rf[dof_V(mf, I, J) - Lf.col0]; };
+    double sum = 0.0;
     if (i > 0 && i < mc.nx && j > 0 && j < mc.ny) {
         const int I = 2 * i, J = 2 * j;
-        s = rf[dof_V(mf, I, J)] +
-            0.5 * (rf[dof_V(mf, I - 1, J)] + rf[dof_V(mf, I + 1, J)] + rf[dof_V(mf, I, J - 1)] +
-                   rf[dof_V(mf, I, J + 1)] + rf[dof_V(mf, I + 1, J - 1)] + rf[dof_V(mf, I - 1, J + 1)]);
+        sum = f(I, J) + 0.5 * (f(I - 1, J) + f(I + 1, J) + f(I, J - 1) + f(I, J + 1) + f(I + 1, J - 1) + f(I - 1, J + 1));
     }
-    bc[dof_V(mc, i, j)] = s;
+    bc[dof - Lc.row0] = sum;
 }
-__global__ void k_prolong_add_p2p1(Mesh mf, Mesh mc, const double *__restrict__ ec, double *__restrict__ xf,
+__global__ void k_prolong_add_p2p1(Layout Lf, Layout Lc, const double *__restrict__ ec, double *__restrict__ xf,
                                    const int *skip_flag) {
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
     if (skip_flag && *skip_flag != 0) return;
+    const Mesh &mf = Lf.mesh, &mc = Lc.mesh;
+    const SlotRange s = owned_slots(Lf);
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 4LL * (mf.nx + 1) * (mf.ny + 1)) return;
-    const int kind = (int)(t & 3);
-    const int64_t q = t >> 2;
-    const int i = (int)(q % (mf.nx + 1)), j = (int)(q / (mf.nx + 1));
+    if (t >= slot_count(Lf, s)) return;
+    int i, j, kind;
+    decode_slot(Lf, s, t, i, j, kind);
     const int64_t dof = entity_dof_internal(mf, i, j, kind);
-    if (dof < 0) return;
+    if (dof < Lf.row0 || dof >= Lf.row0 + Lf.nown) return;
+    auto c = [&](int ci, int cj) { return ec[dof_V(mc, ci, cj) - Lc.col0]; };
     double v;
-    if (kind == 0) v = ec[dof_V(mc, i, j)];
-    else if (kind == 1) v = 0.5 * (ec[dof_V(mc, i, j)] + ec[dof_V(mc, i + 1, j)]);
-    else if (kind == 2) v = 0.5 * (ec[dof_V(mc, i, j)] + ec[dof_V(mc, i, j + 1)]);
-    else v = 0.5 * (ec[dof_V(mc, i + 1, j)] + ec[dof_V(mc, i, j + 1)]);
-    xf[dof] += v;
+    if (kind == 0) v = c(i, j);
+    else if (kind == 1) v = 0.5 * (c(i, j) + c(i + 1, j));
+    else if (kind == 2) v = 0.5 * (c(i, j) + c(i, j + 1));
+    else v = 0.5 * (c(i + 1, j) + c(i, j + 1));
+    xf[dof - Lf.col0] += v;
 }
-__global__ void k_restrict_p2p1(Mesh mf, Mesh mc, const double *__restrict__ rf, double *__restrict__ bc,
+__global__ void k_restrict_p2p1(Layout Lf, Layout Lc, const double *__restrict__ rf, double *__restrict__ bc,
                                 const int *skip_flag) {
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
     if (skip_flag && *skip_flag != 0) return;
+    const Mesh &mf = Lf.mesh, &mc = Lc.mesh;
+    const SlotRange s = owned_slots(Lc);
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)(mc.nx + 1) * (mc.ny + 1)) return;
-    const int i = (int)(t % (mc.nx + 1)), j = (int)(t / (mc.nx + 1));
-    double s = 0.0;
-    if (i > 0 && i < mc.nx && j > 0 && j < mc.ny)
-        s = rf[idof_V(mf, i, j)] +
-            0.5 * (rf[idof_B(mf, i - 1, j)] + rf[idof_B(mf, i, j)] + rf[idof_L(mf, i, j - 1)] + rf[idof_L(mf, i, j)] +
-                   rf[idof_D(mf, i - 1, j)] + rf[idof_D(mf, i, j - 1)]);
-    bc[dof_V(mc, i, j)] = s;
+    if (t >= slot_count(Lc, s)) return;
+    int i, j, kind;
+    decode_slot(Lc, s, t, i, j, kind);
+    const int64_t dof = dof_V(mc, i, j);
+    if (dof < Lc.row0 || dof >= Lc.row0 + Lc.nown) return;
+    double sum = 0.0;
+    if (i > 0 && i < mc.nx && j > 0 && j < mc.ny) {
+        const int64_t o = Lf.col0;
+        sum = rf[idof_V(mf, i, j) - o] +
+              0.5 * (rf[idof_B(mf, i - 1, j) - o] + rf[idof_B(mf, i, j) - o] + rf[idof_L(mf, i, j - 1) - o] +
+                     rf[idof_L(mf, i, j) - o] + rf[idof_D(mf, i - 1, j) - o] + rf[idof_D(mf, i, j - 1) - o]);
+    }
+    bc[dof - Lc.row0] = sum;
 }
 __global__ void __launch_bounds__(kThreads) k_dot_gz(int n, const double *__restrict__ g, const double *__restrict__ z,
                                                      double *d, double *partials, unsigned *counter, double *result,
@@ -1578,23 +1601,23 @@ void launch_scale_rows(const Launcher &l, int n, double omega, const double *din
 }
 void launch_prolong_add_p1(const Launcher &l, const Layout &Lf, const Layout &Lc, const double *ec, double *xf,
                            const int *skip_flag) {
-    const int64_t n = (int64_t)(Lf.mesh.nx + 1) * (Lf.mesh.ny + 1);
-    launch_pdl(l, k_prolong_add_p1, blocks_for(n, kThreads), kThreads, Lf.mesh, Lc.mesh, ec, xf, skip_flag);
+    const int64_t n = slot_count(Lf, owned_slots(Lf));
+    launch_pdl(l, k_prolong_add_p1, blocks_for(n, kThreads), kThreads, Lf, Lc, ec, xf, skip_flag);
 }
 void launch_restrict_p1(const Launcher &l, const Layout &Lf, const Layout &Lc, const double *rf, double *bc,
                         const int *skip_flag) {
-    const int64_t n = (int64_t)(Lc.mesh.nx + 1) * (Lc.mesh.ny + 1);
-    launch_pdl(l, k_restrict_p1, blocks_for(n, kThreads), kThreads, Lf.mesh, Lc.mesh, rf, bc, skip_flag);
+    const int64_t n = slot_count(Lc, owned_slots(Lc));
+    launch_pdl(l, k_restrict_p1, blocks_for(n, kThreads), kThreads, Lf, Lc, rf, bc, skip_flag);
 }
 void launch_prolong_add_p2p1(const Launcher &l, const Layout &Lf, const Layout &Lc, const double *ec, double *xf,
                              const int *skip_flag) {
-    const int64_t n = 4LL * (Lf.mesh.nx + 1) * (Lf.mesh.ny + 1);
-    launch_pdl(l, k_prolong_add_p2p1, blocks_for(n, kThreads), kThreads, Lf.mesh, Lc.mesh, ec, xf, skip_flag);
+    const int64_t n = slot_count(Lf, owned_slots(Lf));
+    launch_pdl(l, k_prolong_add_p2p1, blocks_for(n, kThreads), kThreads, Lf, Lc, ec, xf, skip_flag);
 }
 void launch_restrict_p2p1(const Launcher &l, const Layout &Lf, const Layout &Lc, const double *rf, double *bc,
                           const int *skip_flag) {
-    const int64_t n = (int64_t)(Lc.mesh.nx + 1) * (Lc.mesh.ny + 1);
-    launch_pdl(l, k_restrict_p2p1, blocks_for(n, kThreads), kThreads, Lf.mesh, Lc.mesh, rf, bc, skip_flag);
+    const int64_t n = slot_count(Lc, owned_slots(Lc));
+    launch_pdl(l, k_restrict_p2p1, blocks_for(n, kThreads), kThreads, Lf, Lc, rf, bc, skip_flag);
 }
 void launch_dot_gz(const Launcher &l, int n, const double *g, const double *z, double *d_or_null, double *partials,
                    unsigned *counter, double *result, const int *skip_flag) {

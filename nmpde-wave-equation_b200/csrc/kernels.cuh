@@ -223,7 +223,9 @@ int cg_vector_blocks(int n);
 // x = omega * dinv * b
 void launch_scale_rows(const Launcher &, int n, double omega, const double *dinv, const double *b, double *x,
                        const int *skip_flag);
-// P1 on mesh Lc (Nel/2) <-> P1 on mesh Lf: x_f += P e_c ; b_c = P^T r_f with Dirichlet rows zeroed
+// P1 on mesh Lc (Nel/2) <-> P1 on mesh Lf: x_f += P e_c ; b_c = P^T r_f with Dirichlet rows zeroed.
+// Strip-aware: the source vector (ec / rf) is in local layout with valid ghost blocks, the target is the
+// owned part of xf (local layout) / bc (row-indexed)
 void launch_prolong_add_p1(const Launcher &, const Layout &Lf, const Layout &Lc, const double *ec, double *xf,
                            const int *skip_flag);
 void launch_restrict_p1(const Launcher &, const Layout &Lf, const Layout &Lc, const double *rf, double *bc,

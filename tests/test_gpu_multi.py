@@ -22,13 +22,13 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, nccl_id, name, scheme, over, nsteps, q):
+def _worker(rank, world, nccl_id, name, scheme, over, nsteps, q, cg=None):
     sys.path.insert(0, str(ROOT))
     sys.path.insert(0, str(ROOT / "nmpde-wave-equation_b200"))
     from wavegpu import WaveSolver, api, problem
 
     torch.cuda.set_device(rank)
-    g = WaveSolver(problem(name, **over), scheme, rank=rank, nranks=world, nccl_id=nccl_id, device=rank)
+    g = WaveSolver(problem(name, **over), scheme, rank=rank, nranks=world, nccl_id=nccl_id, device=rank, cg=cg)
     g.init()
     its = []
     for _ in range(nsteps):
@@ -95,3 +95,57 @@ def test_ranks_match_one_rank(name, scheme, over, world):
     assert np.allclose(nrm2, nrm1, rtol=1e-10)
     if err1 is not None:
         assert np.allclose([err2[0], err2[2]], [err1[0], err1[2]], rtol=1e-8)
+
+
+MG_CASES = [
+    # Nel_y divisible by ranks * 2^levels, so that the strips coarsen exactly like the single-rank hierarchy
+    ("standing-mode-wsol", "newmark", dict(Nel="64", R=1, Dt="0.1")),
+    ("standing-mode-wsol", "newmark", dict(Nel="32, 64", R=2, Dt="0.05")),
+    ("ricker-wavelet", "theta", dict(Nel="64", R=2, Dt="0.02", Theta="1.0")),
+    ("traveling-square-bump", "newmark", dict(Nel="48, 64", R=1, Dt="0.05",
+                                              C={"Function constants": "", "Variable names": "x, y, t",
+                                                 "Function expression": "1.0 + 0.25*sin(2*pi*x/3)*sin(2*pi*y/3)"})),
+]
+
+
+@pytest.mark.parametrize("world", _world_sizes())
+@pytest.mark.parametrize("name,scheme,over", MG_CASES)
+def test_multigrid_over_strips_matches_oracle(name, scheme, over, world):
+    """The V-cycle preconditioner over strips (coarse strips owned by the fine strip's owner, halo exchange
+    before every smoothing sweep and transfer): the oracle's multigrid-PCG iteration counts and solution."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+
+    from oracle import oracle as O
+    from wavegpu import api, problem
+
+    mg = dict(precond=2)
+    nsteps = 6
+    p = problem(name, **over)
+    o = O.Oracle.from_params(p)
+    o.set_cg(**mg)
+    dt = float(p["Dt"])
+    if scheme == "newmark":
+        o.newmark_init(dt, float(p["Beta"]), float(p["Gamma"]))
+    else:
+        o.theta_init(dt, float(p["Theta"]))
+    its1 = []
+    for _ in range(nsteps):
+        (o.newmark_step if scheme == "newmark" else o.theta_step)()
+        its1.append(tuple(o.iterations()))
+    nccl_id = api.comm_unique_id()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(rk, world, nccl_id, name, scheme, over, nsteps, q, mg))
+             for rk in range(world)]
+    for pr in procs:
+        pr.start()
+    u2, v2, e2, err2, its2, nrm2 = q.get(timeout=300)
+    for pr in procs:
+        pr.join(120)
+    assert all(pr.exitcode == 0 for pr in procs)
+    assert [tuple(i) for i in its2] == its1
+    uo, vo = o.vector(O.Oracle.U), o.vector(O.Oracle.V)
+    assert np.abs(u2 - uo).max() <= 1e-10 * max(np.abs(uo).max(), 1e-300)
+    assert np.abs(v2 - vo).max() <= 1e-10 * max(np.abs(vo).max(), 1e-300)
