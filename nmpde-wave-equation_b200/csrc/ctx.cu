@@ -855,44 +855,58 @@ int dev_alloc(wave_ctx *ctx, T **p, size_t count, bool zero = true) {
 int fused_plan(wave_ctx *ctx) {
     auto &f = ctx->fused;
     f.ok = false;
-    // default: on for a single rank whenever the rows fit on chip (measured on B200, c2: 32 us per iteration
-    // against 48 us of the three-kernel path); WAVE_CG_FUSED=0 switches it off, =1 also selects it for
-    // several ranks (over the NVLink mailboxes).  Multigrid levels (internal child contexts) never use it.
+    // default: on whenever the rows fit on chip -- one rank, or 2..8 ranks over the NVLink mailboxes (measured
+    // on B200: c2, one GPU: 32 us per iteration against 48 us of the round-1 three-kernel path; 1 M-DoF strips
+    // on 8 GPUs: 47 us against 55 us); WAVE_CG_FUSED=0 switches it off.  Multigrid levels never use it.
     const char *env = std::getenv("WAVE_CG_FUSED");
     const int want = env ? std::atoi(env) : -1;
     if (want == 0 || (ctx->cfg.flags & kFlagChild)) return WAVE_OK;
-    if (ctx->cfg.nranks != 1 && want != 1) return WAVE_OK;
     if (ctx->cfg.precond != WAVE_PRECOND_JACOBI) return WAVE_OK;
     if (ctx->cfg.nranks != 1 && !ctx->pc.enabled) return WAVE_OK;  // several ranks: only over the NVLink mailboxes
+    // every rank evaluates its own strip; with several ranks all of them must agree (the kernel's sums and
+    // halo flags pair up across ranks), so the local verdicts are combined below
     const int nwin = ctx->nslices / (kWindow / kSlice);
     int sms = kSMsFallback;
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int wpb = (nwin + sms - 1) / sms;
-    if (wpb > kFusedMaxWin) return WAVE_OK;
     const int grid = (nwin + wpb - 1) / wpb;
-    DevTmp<int32_t> cmin, cmax;
-    RET(dev_alloc(ctx, &cmin.p, (size_t)nwin, false));
-    RET(dev_alloc(ctx, &cmax.p, (size_t)nwin, false));
-    launch_window_col_range(ctx->launcher, ctx->A, nwin, cmin.p, cmax.p);
-    std::vector<int32_t> lo(nwin), hi(nwin), c0(grid), cn(grid);
-    CK(cudaMemcpyAsync(lo.data(), cmin.p, sizeof(int32_t) * nwin, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(hi.data(), cmax.p, sizeof(int32_t) * nwin, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    bool can = wpb <= kFusedMaxWin;
+    std::vector<int32_t> c0((size_t)grid), cn((size_t)grid);
     int stage = 1;
-    for (int b = 0; b < grid; ++b) {
-        int32_t l = INT32_MAX, h = -1;
-        for (int w = b * wpb; w < std::min(nwin, (b + 1) * wpb); ++w) {
-            l = std::min(l, lo[w]);
-            h = std::max(h, hi[w]);
+    size_t smem = 0;
+    if (can) {
+        DevTmp<int32_t> cmin, cmax;
+        RET(dev_alloc(ctx, &cmin.p, (size_t)nwin, false));
+        RET(dev_alloc(ctx, &cmax.p, (size_t)nwin, false));
+        launch_window_col_range(ctx->launcher, ctx->A, nwin, cmin.p, cmax.p);
+        std::vector<int32_t> lo(nwin), hi(nwin);
+        CK(cudaMemcpyAsync(lo.data(), cmin.p, sizeof(int32_t) * nwin, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(hi.data(), cmax.p, sizeof(int32_t) * nwin, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int b = 0; b < grid; ++b) {
+            int32_t l = INT32_MAX, h = -1;
+            for (int w = b * wpb; w < std::min(nwin, (b + 1) * wpb); ++w) {
+                l = std::min(l, lo[w]);
+                h = std::max(h, hi[w]);
+            }
+            if (h < l) { l = ctx->L.own_off; h = ctx->L.own_off; }  // a block of padding only
+            c0[b] = l;
+            cn[b] = h - l + 1;
+            stage = std::max(stage, (int)cn[b]);
         }
-        if (h < l) { l = ctx->L.own_off; h = ctx->L.own_off; }  // a block of padding only
-        c0[b] = l;
-        cn[b] = h - l + 1;
-        stage = std::max(stage, (int)cn[b]);
+        smem = cg_fused_smem_bytes(wpb, stage);
+        can = cg_fused_supported(grid, smem);
     }
-    const size_t smem = cg_fused_smem_bytes(wpb, stage);
-    if (!cg_fused_supported(grid, smem)) return WAVE_OK;
+    if (ctx->cfg.nranks > 1) {  // unanimous or not at all
+        ctx->hres[0] = can ? 1.0 : 0.0;
+        CK(cudaMemcpyAsync(ctx->res, ctx->hres, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        RET(allreduce(ctx, ctx->res, 1));
+        CK(cudaMemcpyAsync(ctx->hres, ctx->res, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        can = ctx->hres[0] == (double)ctx->cfg.nranks;
+    }
+    if (!can) return WAVE_OK;
     RET(dev_alloc(ctx, &f.blk_c0, (size_t)grid, false));
     RET(dev_alloc(ctx, &f.blk_cn, (size_t)grid, false));
     RET(dev_alloc(ctx, &f.partials, (size_t)grid * 4));

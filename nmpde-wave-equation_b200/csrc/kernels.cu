@@ -157,6 +157,7 @@ __device__ __forceinline__ void p2p_collect(const PeerComm &pc, unsigned long lo
                 hi = ld_relaxed_sys(&src[2 * k + 1]);
                 if ((lo & 0xffffffff00000000ull) == tag && (hi & 0xffffffff00000000ull) == tag) break;
                 if (clock64() - t0 > 6000000000LL) { ok = false; break; }  // ~3 s: give up, do not hang
+                if (blockIdx.x != 0) __nanosleep(100);  // hundreds of blocks poll one line: leave it to block 0
             }
             got[k] = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
         }
@@ -1074,14 +1075,39 @@ __global__ void __launch_bounds__(kThreads) k_cg_direction(int n, int k, CgScala
         S->gh[parity ^ 1] = gh_new;
         S->status[parity ^ 1] = status;
     }
-    const int hi0 = n - pc.hi_count;
+    // Several ranks: the first / last owned block is the neighbours' ghost block.  Those elements are updated
+    // first and stored into the neighbours' vectors at once; every block then checks in (system-scope fence +
+    // ticket) and the last one to arrive raises the halo flags -- a few microseconds into the kernel instead
+    // of at its end, so the neighbours' next SpMV never waits and this kernel has no tail.
+    int mid0 = 0, mid1 = n;
+    if (pc.enabled && status == 0) {
+        const int hi0 = n - pc.hi_count;
+        mid0 = pc.lo_count;
+        mid1 = hi0 > mid0 ? hi0 : mid0;
+        for (int part = 0; part < 2; ++part) {
+            const int b = part == 0 ? 0 : mid1, e = part == 0 ? mid0 : n;
+            for (int i = b + blockIdx.x * kThreads + threadIdx.x; i < e; i += gridDim.x * kThreads) {
+                const double dold = d[i];
+                x[i] += alpha * dold;
+                const double di = beta * dold - h[i];
+                d[i] = di;
+                if (pc.d_lo && i < pc.lo_count) pc.d_lo[i] = di;
+                if (pc.d_hi && i >= hi0) pc.d_hi[i - hi0] = di;
+            }
+        }
+        if (last_block_done(counter, true) && threadIdx.x == 0) {
+            __threadfence_system();
+            if (pc.rank > 0) st_release_sys(&pc.box[pc.rank - 1]->halo_flag[1], halo_seq);
+            if (pc.rank < pc.nranks - 1) st_release_sys(&pc.box[pc.rank + 1]->halo_flag[0], halo_seq);
+        }
+    }
     const int stride = gridDim.x * kThreads * 4;
-    for (int i0 = blockIdx.x * kThreads * 4 + threadIdx.x; i0 < n; i0 += stride) {
+    for (int i0 = mid0 + blockIdx.x * kThreads * 4 + threadIdx.x; i0 < mid1; i0 += stride) {
         double xv[4], dv[4], hv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int i = i0 + u * kThreads;
-            if (i < n) {
+            if (i < mid1) {
                 xv[u] = x[i];
                 dv[u] = d[i];
                 hv[u] = status == 0 ? h[i] : 0.0;
@@ -1090,24 +1116,10 @@ __global__ void __launch_bounds__(kThreads) k_cg_direction(int n, int k, CgScala
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int i = i0 + u * kThreads;
-            if (i < n) {
+            if (i < mid1) {
                 x[i] = xv[u] + alpha * dv[u];
-                if (status == 0) {
-                    const double di = beta * dv[u] - hv[u];
-                    d[i] = di;
-                    if (pc.enabled) {  // my first / last block is the neighbours' ghost block: store it there too
-                        if (pc.d_lo && i < pc.lo_count) pc.d_lo[i] = di;
-                        if (pc.d_hi && i >= hi0) pc.d_hi[i - hi0] = di;
-                    }
-                }
+                if (status == 0) d[i] = beta * dv[u] - hv[u];
             }
-        }
-    }
-    if (pc.enabled && status == 0) {  // halo flag: after every block's halo stores (system-scope fence)
-        if (last_block_done(counter, true) && threadIdx.x == 0) {
-            __threadfence_system();
-            if (pc.rank > 0) st_release_sys(&pc.box[pc.rank - 1]->halo_flag[1], halo_seq);
-            if (pc.rank < pc.nranks - 1) st_release_sys(&pc.box[pc.rank + 1]->halo_flag[0], halo_seq);
         }
     }
 }
