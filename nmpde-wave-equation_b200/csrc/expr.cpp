@@ -270,17 +270,31 @@ std::string trimmed(std::string x) {
 
 }  // namespace
 
+// src/ParameterReader.cpp:244-265: "pi" (any case), or <number> * pi where <number> matches the reference's
+// pattern [0-9]*\.?[0-9]+ (digits, no sign, no exponent, no trailing dot); everything else goes through
+// std::stod, which parses the longest numeric prefix ("-2*pi" -> -2, "1e3*pi" -> 1000, "2.*pi" -> 2) and
+// throws std::invalid_argument when there is none -- the same values the host ParameterReader produces.
+static bool plain_decimal(const std::string &t) {
+    size_t i = 0, n = t.size();
+    while (i < n && std::isdigit((unsigned char)t[i])) ++i;
+    const size_t int_digits = i;
+    if (i < n && t[i] == '.') {
+        size_t j = i + 1;
+        while (j < n && std::isdigit((unsigned char)t[j])) ++j;
+        if (j > i + 1) return j == n;      // digits after the dot: [0-9]*\.[0-9]+
+        return false;                      // "2." or "." : the pattern needs digits after the dot
+    }
+    return int_digits > 0 && i == n;       // [0-9]+
+}
 double parse_value_with_pi(std::string value) {
-    value = trimmed(value);
+    const std::string t = trimmed(value);
     std::string low;
-    for (char c : value) low.push_back((char)std::tolower((unsigned char)c));
+    for (char c : t) low.push_back((char)std::tolower((unsigned char)c));
     if (low == "pi") return M_PI;
     const auto star = low.find('*');
     if (star != std::string::npos && trimmed(low.substr(star + 1)) == "pi") {
         const std::string lhs = trimmed(low.substr(0, star));
-        size_t used = 0;
-        const double c = std::stod(lhs, &used);
-        if (used == lhs.size()) return c * M_PI;
+        if (plain_decimal(lhs)) return std::stod(lhs) * M_PI;
     }
     return std::stod(value);  // throws std::invalid_argument like the reference (:264)
 }

@@ -105,10 +105,25 @@ void WaveEquationBase::create_context(int scheme, double theta, double beta, dou
     unsigned char comm_id[128] = {};
     if (mpi_size > 1)
     {
+        // One GPU per rank.  Every rank evaluates the same condition before the id is published, so either
+        // all of them stop here or none does (a single rank that threw would leave the others waiting in the
+        // communicator set-up).  Ranks per node: the launcher's count when it exports one, else all ranks.
         const int n_devices = wave_device_count();
-        if (n_devices > 0 && mpi_size > static_cast<unsigned int>(n_devices) && launch.local_rank >= static_cast<unsigned int>(n_devices))
-            throw std::runtime_error("rank " + std::to_string(mpi_rank) + " of " + std::to_string(mpi_size) +
-                                     " has no GPU of its own: " + std::to_string(n_devices) +
+        unsigned int per_node = mpi_size;
+        for (const char* name : { "WAVE_LOCAL_NRANKS", "OMPI_COMM_WORLD_LOCAL_SIZE", "MPI_LOCALNRANKS", "SLURM_NTASKS_PER_NODE",
+                                  "LOCAL_WORLD_SIZE" })
+            if (const char* v = std::getenv(name))
+            {
+                const long x = std::strtol(v, nullptr, 10);
+                if (x > 0)
+                {
+                    per_node = static_cast<unsigned int>(x);
+                    break;
+                }
+            }
+        if (n_devices > 0 && per_node > static_cast<unsigned int>(n_devices))
+            throw std::runtime_error("rank " + std::to_string(mpi_rank) + " of " + std::to_string(mpi_size) + ": " +
+                                     std::to_string(per_node) + " ranks on this node but " + std::to_string(n_devices) +
                                      " device(s) visible; launch at most one rank per GPU");
         if (mpi_rank == 0 && wave_comm_unique_id(comm_id) != WAVE_OK)
             throw std::runtime_error(std::string("wave_comm_unique_id: ") + wave_last_error(nullptr));

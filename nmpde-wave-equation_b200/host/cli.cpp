@@ -163,6 +163,9 @@ int wave_cli_main(int argc, char* argv[], Scheme scheme)
     catch (const std::invalid_argument& e)
     {
         pcout << "Error while initializing or running " << tr.class_name << ": " << e.what() << std::endl;
+        if (launch.rank != 0)
+            std::cerr << "rank " << launch.rank << ": error while initializing or running " << tr.class_name << ": "
+                      << e.what() << std::endl;
         pcout << "Likely cause: a non-numeric or malformed value in the parameter file (stod failure)." << std::endl;
         pcout << "Please verify fields like 'R', 'T', " << joined(tr.scalars, true)
               << ", 'Dt' and function definitions C/F/U0/V0/G/DGDT in " << parameters_file << std::endl;
@@ -171,6 +174,8 @@ int wave_cli_main(int argc, char* argv[], Scheme scheme)
     catch (const std::exception& e)
     {
         pcout << "Unexpected error: " << e.what() << std::endl;
+        if (launch.rank != 0) // pcout is rank 0's: a failure of any other rank must not be silent
+            std::cerr << "rank " << launch.rank << ": unexpected error: " << e.what() << std::endl;
         return 1;
     }
     return 0;

@@ -1,12 +1,15 @@
 // launch_env.cpp -- see launch_env.hpp.
 #include "launch_env.hpp"
 
+#include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <fstream>
 #include <stdexcept>
 #include <thread>
@@ -14,7 +17,16 @@
 namespace
 {
 constexpr size_t kIdBytes = 128;
-constexpr char kMagic[8] = { 'W', 'A', 'V', 'E', 'I', 'D', '0', '1' };
+constexpr char kMagic[8] = { 'W', 'A', 'V', 'E', 'I', 'D', '0', '2' };
+// the record rank 0 publishes: magic, number of ranks, communicator id.  A reader accepts it only when the
+// rank count matches and the file is fresh (a leftover of a crashed earlier run is ignored).
+struct Record
+{
+    char magic[8];
+    unsigned int nranks;
+    unsigned int reserved;
+    unsigned char id[kIdBytes];
+};
 
 bool read_unsigned(const char* name, unsigned int& out)
 {
@@ -109,14 +121,21 @@ void share_communicator_id(const LaunchEnvironment& env, unsigned char id[128], 
         return;
     if (env.rank == 0)
     {
-        // write beside the final name and rename: readers see nothing or the complete record
+        // A record left behind by an earlier run must never be read as this run's: remove it first.  The
+        // new record is written beside the final name (exclusive create, no symlink following, owner-only)
+        // and renamed, so readers see nothing or the complete record.
+        ::unlink(env.rendezvous.c_str());
         const std::string staging = env.rendezvous + ".part";
-        std::FILE* f = std::fopen(staging.c_str(), "wb");
-        if (!f)
+        ::unlink(staging.c_str());
+        const int fd = ::open(staging.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW | O_CLOEXEC, 0600);
+        if (fd < 0)
             throw std::runtime_error("cannot create the rendezvous file " + staging);
-        const bool ok = std::fwrite(kMagic, 1, sizeof kMagic, f) == sizeof kMagic &&
-                        std::fwrite(id, 1, kIdBytes, f) == kIdBytes;
-        if (std::fclose(f) != 0 || !ok || std::rename(staging.c_str(), env.rendezvous.c_str()) != 0)
+        Record rec{};
+        std::memcpy(rec.magic, kMagic, sizeof kMagic);
+        rec.nranks = env.size;
+        std::memcpy(rec.id, id, kIdBytes);
+        const bool ok = ::write(fd, &rec, sizeof rec) == static_cast<ssize_t>(sizeof rec);
+        if (::close(fd) != 0 || !ok || std::rename(staging.c_str(), env.rendezvous.c_str()) != 0)
         {
             std::remove(staging.c_str());
             throw std::runtime_error("cannot publish the communicator id in " + env.rendezvous);
@@ -126,17 +145,18 @@ void share_communicator_id(const LaunchEnvironment& env, unsigned char id[128], 
     const auto deadline = std::chrono::steady_clock::now() + std::chrono::duration<double>(timeout_s);
     for (;;)
     {
-        if (std::FILE* f = std::fopen(env.rendezvous.c_str(), "rb"))
+        const int fd = ::open(env.rendezvous.c_str(), O_RDONLY | O_NOFOLLOW | O_CLOEXEC);
+        if (fd >= 0)
         {
-            char magic[sizeof kMagic];
-            unsigned char buf[kIdBytes];
-            const bool ok = std::fread(magic, 1, sizeof magic, f) == sizeof magic &&
-                            std::memcmp(magic, kMagic, sizeof magic) == 0 &&
-                            std::fread(buf, 1, kIdBytes, f) == kIdBytes;
-            std::fclose(f);
-            if (ok)
+            Record rec{};
+            struct stat st{};
+            const bool read_ok = ::read(fd, &rec, sizeof rec) == static_cast<ssize_t>(sizeof rec) && ::fstat(fd, &st) == 0;
+            ::close(fd);
+            // fresh = written within this wait (plus slack for ranks that started late)
+            const bool fresh = read_ok && std::difftime(std::time(nullptr), st.st_mtime) <= timeout_s + 60.0;
+            if (read_ok && fresh && std::memcmp(rec.magic, kMagic, sizeof kMagic) == 0 && rec.nranks == env.size)
             {
-                std::memcpy(id, buf, kIdBytes);
+                std::memcpy(id, rec.id, kIdBytes);
                 return;
             }
         }

@@ -419,9 +419,17 @@ static int parse_value_with_pi(const char *value, double *out) {
         strcpy(rhs, star + 1);
         trim(lhs); trim(rhs);
         if (!strcmp(rhs, "pi")) {
-            char *end;
-            double c = strtod(lhs, &end);
-            if (end != lhs && *end == 0) { *out = c * M_PI; return 0; }
+            /* the reference's pattern for <num>: [0-9]*\.?[0-9]+ -- digits only, no sign, no exponent,
+               no trailing dot; anything else falls through to the numeric-prefix parse below */
+            size_t a = 0, n = strlen(lhs), ok = 0;
+            while (a < n && isdigit((unsigned char)lhs[a])) ++a;
+            if (a < n && lhs[a] == '.') {
+                size_t b = a + 1;
+                while (b < n && isdigit((unsigned char)lhs[b])) ++b;
+                ok = (b > a + 1 && b == n);
+            } else
+                ok = (a > 0 && a == n);
+            if (ok) { *out = strtod(lhs, NULL) * M_PI; return 0; }
         }
     }
     char *end;

@@ -22,7 +22,9 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, nccl_id, name, scheme, over, nsteps, q, cg=None):
+def _worker(rank, world, nccl_id, name, scheme, over, nsteps, q, cg=None, fused=None):
+    if fused is not None:
+        os.environ["WAVE_CG_FUSED"] = fused
     sys.path.insert(0, str(ROOT))
     sys.path.insert(0, str(ROOT / "nmpde-wave-equation_b200"))
     from wavegpu import WaveSolver, api, problem
@@ -56,9 +58,12 @@ def _world_sizes():
 
 
 @pytest.mark.parametrize("world", _world_sizes())
+@pytest.mark.parametrize("fused", ["0", "1"])
 @pytest.mark.parametrize("name,scheme,over", CASES)
-def test_ranks_match_one_rank(name, scheme, over, world):
-    """2 ranks exercise the end strips; 4 and 8 ranks also the strips with two neighbours."""
+def test_ranks_match_one_rank(name, scheme, over, fused, world):
+    """2 ranks exercise the end strips; 4 and 8 ranks also the strips with two neighbours.  fused = "0": the
+    three-kernel iteration with its sums over the NVLink mailboxes; "1": the cooperative kernel K6f (the
+    default at these sizes)."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
@@ -79,7 +84,7 @@ def test_ranks_match_one_rank(name, scheme, over, world):
     nccl_id = api.comm_unique_id()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(rk, world, nccl_id, name, scheme, over, nsteps, q))
+    procs = [ctx.Process(target=_worker, args=(rk, world, nccl_id, name, scheme, over, nsteps, q, None, fused))
              for rk in range(world)]
     for p in procs:
         p.start()

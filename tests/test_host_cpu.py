@@ -106,6 +106,25 @@ def test_constants_with_pi():
     assert api.lib().wave_expr_value(h, 0, 0, 0) == pytest.approx(3.5 * np.pi + 0.1, rel=1e-15)
 
 
+@pytest.mark.parametrize("text,expect", [
+    ("2*pi", 2 * np.pi), (".5*pi", 0.5 * np.pi), ("2.5 * PI", 2.5 * np.pi), ("pi", np.pi),
+    # outside the reference's pattern [0-9]*\\.?[0-9]+ (src/ParameterReader.cpp:253): std::stod's prefix parse
+    ("-2*pi", -2.0), ("1e3*pi", 1000.0), ("2.*pi", 2.0), ("+3*pi", 3.0), ("4", 4.0),
+])
+def test_constant_multiples_of_pi_follow_the_reference_pattern(text, expect):
+    """One 'Function constants' string must mean the same in the library (device functions), the oracle and
+    the reference's ParameterReader (the host FunctionParser shares the pattern: host_selftest)."""
+    blk = {"Function expression": "k", "Variable names": "x, y", "Function constants": f"k={text}"}
+    rc, h, err = _expr(blk)
+    assert rc == 0, err
+    assert api.lib().wave_expr_value(h, 0, 0, 0) == pytest.approx(expect, rel=1e-15)
+    api.lib().wave_expr_destroy(h)
+    p = problem("standing-mode-wsol", Nel=2)
+    p["U0"] = dict(blk)
+    o = O.Oracle.from_params(p)
+    assert o.eval(O.EXPR_NAMES.index("U0"), 0.1, 0.2, 0.0) == pytest.approx(expect, rel=1e-15)
+
+
 @pytest.mark.parametrize("nx,ny,r,nranks", [(8, 8, 1, 2), (8, 8, 2, 3), (5, 9, 2, 4), (16, 8, 1, 8), (7, 2, 2, 2)])
 def test_partition_plan_is_consistent(nx, ny, r, nranks):
     o = O.Oracle.from_params(problem("standing-mode-wsol", Nel=f"{nx}, {ny}", R=r))
