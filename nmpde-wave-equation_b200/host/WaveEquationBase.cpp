@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <sstream>
 #include <stdexcept>
+#include <utility>
 
 namespace
 {
@@ -100,6 +101,18 @@ void WaveEquationBase::create_context(int scheme, double theta, double beta, dou
         else if (v == "none" || v == "1")
             cfg.precond = WAVE_PRECOND_NONE;
     }
+    // WAVE_CG_REDUCE / WAVE_CG_TOL override ReductionControl's reduction factor and absolute tolerance
+    // (src/WaveNewmark.cpp:256: 1e-6, 1e-12) -- e.g. to reproduce the printed digits of the reference's
+    // convergence tables, which its AMG-preconditioned solves reach far below the stopping bar
+    for (const auto& opt : { std::make_pair("WAVE_CG_REDUCE", &cfg.cg_reduce), std::make_pair("WAVE_CG_TOL", &cfg.cg_tol) })
+        if (const char* v = std::getenv(opt.first))
+        {
+            char* end = nullptr;
+            const double x = std::strtod(v, &end);
+            if (end == v || !(x > 0.0))
+                throw std::invalid_argument(std::string(opt.first) + "='" + v + "' is not a positive number");
+            *opt.second = x;
+        }
     // several ranks: one GPU each, strips of quad rows, the communicator id broadcast through the
     // launcher's rendezvous file (the reference's MPI_COMM_WORLD needs no such step)
     unsigned char comm_id[128] = {};

@@ -158,3 +158,47 @@ def test_cli_save_solution_writes_vtu(tmp_path):
     # step 0 holds the initial condition
     _, _, _, _, d0 = read_vtu(run_dir / "solution_0000.0.vtu")
     assert np.abs(d0["u"] - np.sin(np.pi * sx[corner]) * np.sin(np.pi * sy[corner])).max() < 1e-12
+
+
+def test_convergence_sweep_recipe_through_the_launcher(tmp_path):
+    """The recipe of the reference's scripts/convergence_sweep.py:165-210 against its own result table: a
+    parameter file written the way `write_param_file` does (Nel, R, Dt, T, Save Solution / Enable Logging
+    off, Log Every 0, scheme overrides), started as `<launcher> -np 1 <binary> <file>` from build/ with the
+    MPI options the script may add, and `../results/<method>-<stem>/convergence.csv` read back -- rows of
+    analysis/data/convergence-results.csv (tests/golden/convergence_rows.json) within their printed digits."""
+    import json
+    import os
+
+    shim = ROOT / "tools" / "mpirun-shim"
+    rows = json.loads((ROOT / "tests" / "golden" / "convergence_rows.json").read_text())
+    picked = [r for r in rows if r["Nel"] == 20 and r["Dt"] == "0.01" and r["R"] in (1, 2)
+              and r["scheme"] in ("theta", "newmark")]
+    picked = [r for r in picked if (r.get("Theta") in (0.5, 1.0)) or (r.get("Beta") == 0.25)][:6]
+    assert len(picked) >= 4
+    build = tmp_path / "build"
+    build.mkdir()
+    (tmp_path / "parameters").mkdir()
+    base = problem("standing-mode-wsol")
+    env = dict(os.environ, WAVE_CG_REDUCE="1e-13", WAVE_CG_TOL="1e-30")
+    for k, row in enumerate(picked):
+        params = dict(base)
+        params.update({"Nel": str(row["Nel"]), "R": str(row["R"]), "Dt": str(row["Dt"]), "T": str(row["T"]),
+                       "Save Solution": False, "Enable Logging": False, "Log Every": 0})
+        for key in ("Theta", "Beta", "Gamma"):
+            if row.get(key) is not None:
+                params[key] = str(row[key])
+        pf = tmp_path / "parameters" / "convergence-params.json"
+        write_json(pf, params)
+        exe = BIN / ("main-theta" if row["scheme"] == "theta" else "main-newmark")
+        cmd = [str(shim), "-np", "1", "--bind-to", "core", "--map-by", "socket", str(exe), str(pf)]
+        r = subprocess.run(cmd, cwd=build, capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0, r.stdout + r.stderr
+        conv = tmp_path / "results" / f"{row['scheme']}-convergence-params" / "convergence.csv"
+        lines = list(csv.reader(conv.open()))
+        assert lines[0][:4] == ["h", "N_el_x", "N_el_y", "r"] and lines[0][-3:-1] == ["rel_L2_error_final",
+                                                                                     "rel_H1_error_final"]
+        last = lines[-1]
+        assert int(last[1]) == row["Nel"] and int(last[3]) == row["R"]
+        l2, h1 = float(last[-3]), float(last[-2])
+        assert abs(l2 - row["rel_L2"]) <= 3e-6 * row["rel_L2"], (row, l2)
+        assert abs(h1 - row["rel_H1"]) <= 3e-6 * row["rel_H1"], (row, h1)
