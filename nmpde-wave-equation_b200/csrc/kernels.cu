@@ -701,6 +701,7 @@ __device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
 
 // row epilogue shared by both SpMV kernels: addends, damped-Jacobi update, CG residual start, fused dots
 __device__ __forceinline__ void spmv_epilogue(const SpmvArgs &a, int r, double s, double (&dots)[2]) {
+    if (a.negate) s = -s;
     if (a.add0) s += a.addc0 * a.add0[r];
     if (a.add1) s += a.addc1 * a.add1[r];
     if (a.jac_x) s = a.jac_x[r] + a.jac_omega * (a.dinv[r] * s);
@@ -1573,6 +1574,12 @@ static bool use_stencil(const SpmvArgs &a) {
 static bool unit_coefficients(const SpmvArgs &a) {
     return a.t[1].val == nullptr && a.t[0].xb == nullptr && a.t[0].ca == 1.0 && a.t[0].coef == 1.0;
 }
+// coefficient -1 on a single vector (-K z of the right-hand side, b - S x of the multigrid smoother): every
+// term -(v x) is the exact negation of (v x) and rounding is symmetric, so the row sum is the exact negation
+// of the unit-coefficient sum -- the stencil kernel runs its unit variant and the epilogue flips the sign
+static bool unit_negative(const SpmvArgs &a) {
+    return a.t[1].val == nullptr && a.t[0].xb == nullptr && a.t[0].ca == 1.0 && a.t[0].coef == -1.0;
+}
 // the CG iteration's launch: y = A d and d . y, nothing else in the epilogue
 static bool cg_epilogue(const SpmvArgs &a) {
     return unit_coefficients(a) && a.y && a.dot_mode == 1 && !a.add0 && !a.add1 && !a.jac_x && !a.h_out;
@@ -1588,6 +1595,13 @@ void launch_spmv(const Launcher &l, const SpmvArgs &a) {
     const bool two_terms = a.t[1].val != nullptr;
     const bool twox = a.t[0].xb != nullptr || (two_terms && a.t[1].xb != nullptr);
     const bool p1 = a.A.chunk <= 7;
+    if (use_stencil(a) && unit_negative(a)) {
+        SpmvArgs b = a;
+        b.t[0].coef = 1.0;
+        b.negate = 1;
+        if (p1) launch_spmv_st_t<false, 1, false, true>(l, b); else launch_spmv_st_t<true, 1, false, true>(l, b);
+        return;
+    }
     if (use_stencil(a)) {
         if (cg_epilogue(a)) { if (p1) launch_spmv_st_t<false, 1, false, true, true>(l, a); else launch_spmv_st_t<true, 1, false, true, true>(l, a); }
         else if (unit_coefficients(a)) { if (p1) launch_spmv_st_t<false, 1, false, true>(l, a); else launch_spmv_st_t<true, 1, false, true>(l, a); }

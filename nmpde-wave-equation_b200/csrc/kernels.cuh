@@ -156,6 +156,7 @@ struct SpmvArgs {
     // waiting (SUM_MAILBOX)
     int dot_publish;
     const int *skip_flag;      // if non-null and *skip_flag != 0 the kernel returns at once
+    int negate;                // set by launch_spmv: coefficient -1 handled as the exact negation of the unit sum
     // peer exchange (see PeerComm): all-reduce of the dot result, wait for the neighbours' halo
     PeerComm pc;
     unsigned long long ar_seq, halo_wait_seq;
