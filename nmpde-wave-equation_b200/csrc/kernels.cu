@@ -137,8 +137,10 @@ __device__ __forceinline__ void p2p_publish(const PeerComm &pc, unsigned long lo
         }
     }
 }
+// `self` (may be null): this rank's own totals, taken from registers instead of the mailbox
 template <int NV>
-__device__ __forceinline__ void p2p_collect(const PeerComm &pc, unsigned long long seq, double (&out)[NV]) {
+__device__ __forceinline__ void p2p_collect(const PeerComm &pc, unsigned long long seq, double (&out)[NV],
+                                            const double *self = nullptr) {
     const int lane = threadIdx.x & 31;
     const int slot = (int)(seq & 1ull);
     const unsigned long long tag = (seq & 0xffffffffull) << 32;
@@ -146,7 +148,10 @@ __device__ __forceinline__ void p2p_collect(const PeerComm &pc, unsigned long lo
     double got[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) got[k] = 0.0;
-    if (lane < pc.nranks) {
+    if (self && lane == pc.rank) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) got[k] = self[k];
+    } else if (lane < pc.nranks) {
         const unsigned long long *src = pc.box[pc.rank]->ll[slot][lane];
         const long long t0 = clock64();
 #pragma unroll
@@ -173,28 +178,29 @@ __device__ __forceinline__ void p2p_collect(const PeerComm &pc, unsigned long lo
 }
 
 // ---- sums handed from a producer kernel to its consumer (see SUM_* in kernels.cuh) --------------------
-// Producer tail.  SUM_PARTIALS: one partial per block and nothing else (no fence, no ticket, no second
-// pass).  SUM_MAILBOX: the last block adds the partials in block order and stores the rank's totals into
-// every rank's mailbox.  SUM_SCALAR: the last block writes the totals to `scalars`.
+// Producer tail.  SUM_PARTIALS and SUM_MAILBOX: one partial per block and nothing else (no fence, no
+// ticket, no second pass) -- the consumer finishes the sum.  SUM_SCALAR: the last block adds the partials
+// in block order and writes the totals to `scalars` (an NCCL all-reduce follows).
 template <int NV>
 __device__ __forceinline__ void produce_sums(double (&v)[NV], int mode, double *partials, unsigned *counter,
-                                             const PeerComm &pc, unsigned long long seq, double *scalars) {
-    if (mode == SUM_PARTIALS) {
+                                             double *scalars) {
+    if (mode != SUM_SCALAR) {
         block_sum<NV>(v);
         if (threadIdx.x == 0)
 #pragma unroll
             for (int k = 0; k < NV; ++k) partials[(size_t)blockIdx.x * NV + k] = v[k];
         return;
     }
-    if (!grid_sum<NV>(v, partials, counter)) return;
-    if (mode == SUM_MAILBOX) {
-        if (threadIdx.x < 32) p2p_publish<NV>(pc, seq, v);
-    } else if (threadIdx.x == 0) {
+    if (grid_sum<NV>(v, partials, counter) && threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < NV; ++k) scalars[k] = v[k];
     }
 }
-// Consumer head: the totals in every thread of every block, bitwise identical in all of them.
+// Consumer head: the totals in every thread of every block, bitwise identical in all of them.  Every block
+// adds the producer's per-block partials in the same fixed order.  With several ranks (SUM_MAILBOX) block 0
+// then stores this rank's total into every peer's mailbox and all blocks collect the other ranks' totals
+// from the local mailbox and add them in rank order (their own from registers): the exchange starts the
+// moment the producer grid has drained -- one NVLink flight on the critical path, no producer tail.
 template <int NV>
 __device__ __forceinline__ void consume_sums(const CgSumIo &in, const PeerComm &pc, const double *scalars,
                                              double (&out)[NV]) {
@@ -204,23 +210,27 @@ __device__ __forceinline__ void consume_sums(const CgSumIo &in, const PeerComm &
         for (int k = 0; k < NV; ++k) out[k] = scalars[k];
         return;
     }
-    if (in.mode == SUM_PARTIALS) {
-        double v[NV];
+    double v[NV];
 #pragma unroll
-        for (int k = 0; k < NV; ++k) v[k] = 0.0;
-        for (int b = threadIdx.x; b < in.blocks; b += blockDim.x)
+    for (int k = 0; k < NV; ++k) v[k] = 0.0;
+    for (int b = threadIdx.x; b < in.blocks; b += blockDim.x)
 #pragma unroll
-            for (int k = 0; k < NV; ++k) v[k] += __ldcg(&in.partials[(size_t)b * in.stride + k]);
-        block_sum<NV>(v);
-        if (threadIdx.x == 0)
+        for (int k = 0; k < NV; ++k) v[k] += __ldcg(&in.partials[(size_t)b * in.stride + k]);
+    block_sum<NV>(v);  // totals of this rank in thread 0
+    if (in.mode == SUM_MAILBOX) {
+        if (threadIdx.x < 32) {
+            double loc[NV], tot[NV];
 #pragma unroll
-            for (int k = 0; k < NV; ++k) s_bc[k] = v[k];
-    } else if (threadIdx.x < 32) {
-        double v[NV];
-        p2p_collect<NV>(pc, in.seq, v);
-        if (threadIdx.x == 0)
+            for (int k = 0; k < NV; ++k) loc[k] = __shfl_sync(kFull, v[k], 0);
+            if (blockIdx.x == 0) p2p_publish<NV>(pc, in.seq, loc);
+            p2p_collect<NV>(pc, in.seq, tot, loc);
+            if (threadIdx.x == 0)
 #pragma unroll
-            for (int k = 0; k < NV; ++k) s_bc[k] = v[k];
+                for (int k = 0; k < NV; ++k) s_bc[k] = tot[k];
+        }
+    } else if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) s_bc[k] = v[k];
     }
     __syncthreads();
 #pragma unroll
@@ -718,7 +728,7 @@ __device__ __forceinline__ void spmv_epilogue(const SpmvArgs &a, int r, double s
 __device__ __forceinline__ void spmv_tail(const SpmvArgs &a, double (&dots)[2]) {
     if (!a.dot_mode) return;
     if (a.dot_publish)  // CG iteration: the consumer kernel (k_cg_update) finishes the sum
-        produce_sums<2>(dots, a.pc.enabled ? SUM_MAILBOX : SUM_PARTIALS, a.partials, a.counter, a.pc, a.ar_seq, nullptr);
+        produce_sums<2>(dots, SUM_PARTIALS, a.partials, a.counter, nullptr);
     else if (grid_sum<2>(dots, a.partials, a.counter) && threadIdx.x == 0) {
         a.result[0] = dots[0];
         if (a.dot_mode == 2) a.result[1] = dots[1];
@@ -1043,7 +1053,7 @@ __global__ void __launch_bounds__(kThreads) k_cg_update(int n, int parity, CgSca
             }
         }
     }
-    produce_sums<2>(acc, out_mode, out_partials, counter, pc, out_seq, &S->gg);
+    produce_sums<2>(acc, out_mode, out_partials, counter, &S->gg);
 }
 // x += alpha d ; iteration_status(k + 1, res) ; beta = gh'/gh ; d = beta d - h   (3 reads, 2 writes).
 // Block 0 records the outcome in the other parity's slots: nothing it writes is read by this kernel.

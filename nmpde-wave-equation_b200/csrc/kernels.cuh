@@ -100,18 +100,19 @@ struct CgScalars {
 };
 // where a consumer kernel finds the sums its predecessor produced
 enum { SUM_PARTIALS = 0,  // per-block partials of the producer, summed by every consumer block in a fixed order
-       SUM_MAILBOX = 1,   // several ranks over NVLink: every rank's total arrives in the local mailbox
+       SUM_MAILBOX = 1,   // several ranks over NVLink: partials as above + the ranks' totals through the mailboxes
        SUM_SCALAR = 2 };  // totals in CgScalars (NCCL fallback; the multigrid path's g.z)
 
 // ---- NVLink peer exchange inside the CG kernels (nranks > 1) --------------------------------------
 // Every rank owns a small mailbox in device memory that all peers map through CUDA IPC.  The two
-// per-iteration reductions are one-shot all-reduces done by the last block of the producing kernel:
-// it stores its partial sums and a sequence number into every peer's mailbox (P2P stores over
-// NVLink), waits until all ranks' numbers arrived in its own mailbox and adds the partials in rank
-// order, so all ranks obtain bitwise identical totals without a separate collective launch.  The
+// per-iteration reductions are one-shot all-reduces split over producer and consumer kernel: the producer
+// leaves one partial per block; block 0 of the consumer adds them and stores the rank's total, tagged with
+// a sequence number, into every peer's mailbox (P2P stores over NVLink, no waiting); all blocks of the
+// consumer collect the other ranks' totals from the local mailbox and add them in rank order, so all ranks
+// obtain bitwise identical totals without a separate collective launch and without a producer tail.  The
 // halo of the search direction is written by k_cg_direction straight into the neighbours' ghost
 // blocks, followed by a flag the next SpMV waits on.  Sequence numbers come from the host and are
-// identical on all ranks; waits are bounded (status 3 on timeout) so a lost peer cannot hang a GPU.
+// identical on all ranks; waits are bounded (peer_timeout) so a lost peer cannot hang a GPU.
 constexpr int kMaxPeers = 8;
 struct PeerMailbox {
     // all-reduce slots, "LL" style: every 8-byte word carries 4 bytes of payload and the low 32 bits of
@@ -151,9 +152,8 @@ struct SpmvArgs {
     double *partials;
     unsigned *counter;
     double *result;            // totals (1 or 2 doubles), written by the last block (null with dot_publish)
-    // dot_publish (CG iteration): leave the sum to the consumer kernel -- per-block partials on one rank
-    // (SUM_PARTIALS, no last-block tail), or this rank's total stored into every peer's mailbox without
-    // waiting (SUM_MAILBOX)
+    // dot_publish (CG iteration): leave the sum to the consumer kernel -- per-block partials, no last-block
+    // tail (SUM_PARTIALS / SUM_MAILBOX; with several ranks the consumer also exchanges the ranks' totals)
     int dot_publish;
     const int *skip_flag;      // if non-null and *skip_flag != 0 the kernel returns at once
     int negate;                // set by launch_spmv: coefficient -1 handled as the exact negation of the unit sum
