@@ -436,8 +436,65 @@ void ParameterHandler::parse_input(const std::string& filename)
         throw std::runtime_error("Cannot open parameter file " + filename);
     const auto dot = filename.find_last_of('.');
     const std::string ext = dot == std::string::npos ? "" : filename.substr(dot);
+    if (ext == ".prm")
+    {
+        // [deal.II] ParameterHandler's native format: "set <name> = <value>", "subsection <name>" ... "end",
+        // '#' comments, a trailing backslash continues the line
+        std::vector<std::string> sections;
+        std::string line, logical;
+        int line_no = 0;
+        auto strip = [](std::string t) {
+            const auto b = t.find_first_not_of(" \t\r");
+            if (b == std::string::npos)
+                return std::string();
+            const auto e = t.find_last_not_of(" \t\r");
+            return t.substr(b, e - b + 1);
+        };
+        while (std::getline(in, line))
+        {
+            ++line_no;
+            const auto hash = line.find('#');
+            if (hash != std::string::npos)
+                line.erase(hash);
+            line = strip(line);
+            if (!line.empty() && line.back() == '\\')
+            {
+                line.pop_back();
+                logical += strip(line) + " ";
+                continue;
+            }
+            logical += line;
+            const std::string stmt = strip(logical);
+            logical.clear();
+            if (stmt.empty())
+                continue;
+            if (stmt.rfind("subsection", 0) == 0 && (stmt.size() == 10 || std::isspace(static_cast<unsigned char>(stmt[10]))))
+                sections.push_back(strip(stmt.substr(10)));
+            else if (stmt == "end" || stmt == "END")
+            {
+                if (sections.empty())
+                    throw std::runtime_error(filename + ":" + std::to_string(line_no) + ": 'end' without a subsection");
+                sections.pop_back();
+            }
+            else if (stmt.rfind("set", 0) == 0 && stmt.size() > 3 && std::isspace(static_cast<unsigned char>(stmt[3])))
+            {
+                const auto eq = stmt.find('=');
+                if (eq == std::string::npos)
+                    throw std::runtime_error(filename + ":" + std::to_string(line_no) + ": 'set' without '='");
+                std::string full;
+                for (const auto& sct : sections)
+                    full += sct + "/";
+                set_checked(full + strip(stmt.substr(3, eq - 3)), strip(stmt.substr(eq + 1)));
+            }
+            else
+                throw std::runtime_error(filename + ":" + std::to_string(line_no) + ": cannot parse '" + stmt + "'");
+        }
+        if (!sections.empty())
+            throw std::runtime_error(filename + ": subsection '" + sections.back() + "' is not closed");
+        return;
+    }
     if (ext != ".json")
-        throw std::runtime_error("Unknown input file type '" + ext + "': only .json parameter files are supported");
+        throw std::runtime_error("Unknown input file name extension '" + ext + "': .json and .prm parameter files are supported");
     std::stringstream buf;
     buf << in.rdbuf();
     const std::string text = buf.str();

@@ -164,6 +164,53 @@ int main(int argc, char** argv)
     g.set_time(0.75);
     check(g.value(Point<2>(0.05, 0.0)) == 0.0, "G after the window");
 
+    // the same entries from a deal.II .prm file (set / subsection / end, comments, continued lines):
+    // dealii::ParameterHandler::parse_input picks the format by the extension (src/ParameterReader.cpp:134-137)
+    {
+        std::ofstream f(dir + "/selftest.prm");
+        f << "# wave equation parameters\n"
+             "set Geometry = [-1.0, 1.0] x [0.0, 3.5]\n"
+             "set Nel      = 180, 60   # two values\n"
+             "set R = 2\nset T = 1.5\nset Dt = 0.005\nset Save Solution = false\nset Log Every = 0\n"
+             "subsection U0\n  set Function constants  = A=2.0\n  set Function expression = A*sin(pi*x) \\\n"
+             "                            *y\n  set Variable names = x, y\nend\n"
+             "subsection C\n  set Function expression = 1.0\n  set Variable names = x, y, t\nend\n"
+             "subsection F\n  set Function expression = 0.0\n  set Variable names = x, y, t\nend\n"
+             "subsection V0\n  set Function expression = 0.0\n  set Variable names = x, y\nend\n"
+             "subsection G\n  set Function expression = 0.0\n  set Variable names = x, y, t\nend\n"
+             "subsection DGDT\n  set Function expression = 0.0\n  set Variable names = x, y, t\nend\n";
+    }
+    {
+        ParameterHandler p3;
+        ParameterReader r3(p3);
+        r3.declare(names);
+        r3.parse(dir + "/selftest.prm");
+        check(p3.get_integer("R") == 2 && p3.get_double("Dt") == 0.005 && !p3.get_bool("Save Solution") &&
+                  p3.get_integer("Log Every") == 0 && p3.get_double("Beta") == 0.25,
+              "prm scalars and defaults");
+        const auto nel3 = r3.get_nel();
+        check(nel3.first == 180 && nel3.second == 60, "prm Nel with a trailing comment");
+        FunctionParser<2> c3, f3, u3, v3, g3, d3, s3;
+        r3.load_functions(names, { &c3, &f3, &u3, &v3, &g3, &d3, &s3 });
+        check(std::fabs(u3.value(Point<2>(0.5, 3.0)) - 6.0) < 1e-14, "prm subsection with a continued line");
+    }
+    check(throws<std::runtime_error>([&] {
+              ParameterHandler p2;
+              ParameterReader r2(p2);
+              r2.declare(names);
+              std::ofstream(dir + "/open.prm") << "subsection U0\n set Function expression = 1.0\n";
+              r2.parse(dir + "/open.prm");
+          }),
+          "unclosed subsection in a prm file");
+    check(throws<std::runtime_error>([&] {
+              ParameterHandler p2;
+              ParameterReader r2(p2);
+              r2.declare(names);
+              std::ofstream(dir + "/x.yaml") << "R: 2\n";
+              r2.parse(dir + "/x.yaml");
+          }),
+          "unknown file name extension");
+
     // error behaviour
     check(throws<std::invalid_argument>([&] {
               ParameterHandler p2;

@@ -139,7 +139,7 @@ class ConditionalOStream
     bool active;
 };
 
-/// Declared-entry parameter store with JSON input: the subset of dealii::ParameterHandler the
+/// Declared-entry parameter store with JSON and PRM input: the subset of dealii::ParameterHandler the
 /// reference uses (declare_entry / enter_subsection / get* / parse_input).
 class ParameterHandler
 {
@@ -164,7 +164,8 @@ class ParameterHandler
     long get_integer(const std::string& name) const;
     double get_double(const std::string& name) const;
     bool get_bool(const std::string& name) const;
-    /// Reads a .json parameter file (the only input format the reference exercises).
+    /// Reads a .json parameter file (the format every shipped file and script of the reference uses) or a
+    /// deal.II .prm file (set / subsection / end), chosen by the extension like dealii::ParameterHandler.
     void parse_input(const std::string& filename);
 
   private:
