@@ -1420,9 +1420,12 @@ static inline void note_launch(const Launcher &l) {
         note_launch(l);                                               \
     } while (0)
 
-// Launch with programmatic dependent launch: the kernel starts with cudaGridDependencySynchronize(), so
-// its blocks may be scheduled while the previous kernel of the stream drains (hides the launch gap
-// between the three short kernels of a CG iteration).
+// Launch through cudaLaunchKernelEx with the programmatic-stream-serialization attribute as an option
+// (WAVE_PDL=1): the kernels start with cudaGridDependencySynchronize(), so their blocks may be scheduled
+// while the previous kernel of the stream drains.  Round 1 measured -11 % step time with it at c2 size; with
+// the round-2 kernels (no last-block tails, consumer-side sums) it no longer pays: measured on B200 it costs
+// 1-2 % at 2-8 M rows, 9 % at 67 M rows (early-resident blocks of the next kernel take registers and L1 from
+// the running one) and 16 us per CG iteration with several ranks, so it is off by default.
 template <class... KArgs, class... Args>
 static void launch_pdl(const Launcher &l, void (*kernel)(KArgs...), int grid, int block, Args... args) {
     cudaLaunchConfig_t cfg{};
@@ -1432,7 +1435,7 @@ static void launch_pdl(const Launcher &l, void (*kernel)(KArgs...), int grid, in
     cfg.stream = l.stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    static const int pdl = std::getenv("WAVE_NO_PDL") ? 0 : 1;
+    static const int pdl = (std::getenv("WAVE_PDL") && std::atoi(std::getenv("WAVE_PDL")) != 0) ? 1 : 0;
     attr[0].val.programmaticStreamSerializationAllowed = pdl;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
