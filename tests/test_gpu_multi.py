@@ -22,9 +22,11 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, nccl_id, name, scheme, over, nsteps, q, cg=None, fused=None):
+def _worker(rank, world, nccl_id, name, scheme, over, nsteps, q, cg=None, fused=None, no_p2p=False):
     if fused is not None:
         os.environ["WAVE_CG_FUSED"] = fused
+    if no_p2p:
+        os.environ["WAVE_NO_P2P"] = "1"
     sys.path.insert(0, str(ROOT))
     sys.path.insert(0, str(ROOT / "nmpde-wave-equation_b200"))
     from wavegpu import WaveSolver, api, problem
@@ -160,3 +162,37 @@ def test_multigrid_over_strips_matches_oracle(case, world):
     uo, vo = o.vector(O.Oracle.U), o.vector(O.Oracle.V)
     assert np.abs(u2 - uo).max() <= 1e-10 * max(np.abs(uo).max(), 1e-300)
     assert np.abs(v2 - vo).max() <= 1e-10 * max(np.abs(vo).max(), 1e-300)
+
+
+@pytest.mark.parametrize("cg", [None, dict(precond=2)])
+def test_nccl_fallback_matches_one_rank(cg):
+    """WAVE_NO_P2P=1 (also the path for more than 8 ranks): no NVLink mailboxes, the sums of an iteration are
+    NCCL all-reduces of device scalars and the halo of the search direction an NCCL exchange per iteration --
+    the same iterates as one rank, with Jacobi and with the multigrid V-cycle."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    from wavegpu import WaveSolver, api, problem
+
+    name, scheme, over = "standing-mode-wsol", "newmark", dict(Nel="32, 64", R=2, Dt="0.05")
+    nsteps = 6
+    g = WaveSolver(problem(name, **over), scheme, cg=cg)
+    g.init()
+    its1 = [g.step()[0] for _ in range(nsteps)]
+    u1, e1 = g.vector(api.VEC_U), g.energy()
+    g.close()
+    nccl_id = api.comm_unique_id()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(rk, 2, nccl_id, name, scheme, over, nsteps, q, cg, None, True))
+             for rk in range(2)]
+    for p in procs:
+        p.start()
+    u2, v2, e2, err2, its2, nrm2 = q.get(timeout=300)
+    for p in procs:
+        p.join(120)
+    assert all(p.exitcode == 0 for p in procs)
+    assert [tuple(i) for i in its2] == [tuple(i) for i in its1]
+    assert np.abs(u2 - u1).max() <= 1e-10 * max(np.abs(u1).max(), 1e-300)
+    assert abs(e2 - e1) <= 1e-10 * max(abs(e1), 1e-300)
