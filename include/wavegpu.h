@@ -211,8 +211,9 @@ int wave_kernel_timing(wave_ctx *ctx, int on, double launches[3], double ms_tota
    out = {rows served by the translation-invariant stencil tables (constant wave speed, structured mesh),
    rows kept in SELL form, pattern entries of those rows, algorithmic bytes of one SpMV launch}. */
 int wave_operator_info(const wave_ctx *ctx, int64_t out[4]);
-/* 1 when this context runs its Jacobi-PCG solves as one cooperative kernel (experimental, selected
-   with WAVE_CG_FUSED=1 in the environment of wave_setup when the problem fits on chip), else 0. */
+/* 1 when this context runs its Jacobi-PCG solves as one cooperative kernel (K6f, csrc/cg_fused.cu): the
+   default whenever the rank's rows fit on chip (about 1.2 M rows per GPU; WAVE_CG_FUSED=0 in the
+   environment of wave_setup keeps the three-kernel iteration), else 0. */
 int wave_cg_fused_active(const wave_ctx *ctx);
 /* Device-time and iteration statistics of the CG solves since the last reset:
    out = {solves, iterations, spmv_launches, ms_total}. */

@@ -2,7 +2,8 @@
 # compute-sanitizer over one tiny pass of the hot path (one tool per call, as the profiling guide asks):
 #   tools/sanitize.sh memcheck|racecheck|initcheck|synccheck [out-dir]
 # Runs __graft_entry__.smoke() (P2 Newmark, Nel=24, 5 steps, oracle-checked) under the tool and keeps the
-# log under gpurun_out/ (copy the summary to profiles/).  Not yet run in round 1 (GPU budget spent).
+# log under gpurun_out/ (copy the summary to profiles/).  Round 2: compute-sanitizer is closed on the GPU pool
+# ("runs under it have left GPUs needing a reset"), so this recipe could not be executed there.
 set -euo pipefail
 tool="${1:-memcheck}"
 out="${2:-gpurun_out}"
