@@ -228,6 +228,13 @@ typedef struct {
 } wave_partition;
 int wave_partition_plan(int32_t nx, int32_t ny, int32_t r, int32_t rank, int32_t nranks,
                         wave_partition *out);
+/* Coarse levels of the multigrid V-cycle (WAVE_PRECOND_MG; stands in for PreconditionAMG,
+   src/WaveNewmark.cpp:246-251) for the scheme matrix M + s K on cfg's mesh, wave speed c0 at the centre of
+   the box: fills (nx, ny) of the levels below the fine one -- P1 on the same mesh first when R = 2, then
+   the halved meshes -- and returns their number (< 0: error).  Host only; depends on cfg->nranks (every
+   strip must keep whole coarse quad rows) but not on cfg->rank: all ranks plan the same hierarchy. */
+int wave_mg_plan(const wave_config *cfg, double s, double c0, int32_t *nx_out, int32_t *ny_out,
+                 int32_t max_levels);
 
 #ifdef __cplusplus
 }

@@ -922,6 +922,38 @@ int fused_plan(wave_ctx *ctx) {
     return WAVE_OK;
 }
 
+// The coarse levels of the V-cycle for the scheme matrix bc(M + s K) on cfg's mesh, as a pure function of the
+// configuration (host only; exported as wave_mg_plan for the CPU tests): [P1 on the same mesh when R = 2,
+// then] P1 on Nel/2, Nel/4, ... while the stiffness part still matters (s c0^2 / (dx dy) > 1/4), the mesh
+// halves evenly and -- with several ranks -- every strip begins and ends at an even quad row and keeps at
+// least two coarse quad rows (coarse quad row J covers the fine quad rows 2J, 2J+1, so fine and coarse
+// strips then split at the same physical lines).  Every rank takes the same decisions.
+struct MgPlanLevel { int nx, ny, r; };
+int mg_plan(const wave_config &cfg, double s, double c0, MgPlanLevel *out, int max_levels) {
+    int nx = cfg.nx, ny = cfg.ny, r = cfg.r, n = 0;
+    while (n < max_levels) {
+        int nnx = nx, nny = ny;
+        if (r == 1) {
+            const double dx = (cfg.x1 - cfg.x0) / nx, dy = (cfg.y1 - cfg.y0) / ny;
+            const bool matters = s * c0 * c0 / (dx * dy) > 0.25;
+            if (!(matters && nx % 2 == 0 && ny % 2 == 0 && std::min(nx, ny) / 2 >= 2)) break;
+            bool strips_ok = true;
+            for (int rk = 0; rk < cfg.nranks && cfg.nranks > 1; ++rk) {
+                int j0, j1, c0r, c1r;
+                quad_row_split(ny, rk, cfg.nranks, j0, j1);
+                quad_row_split(ny / 2, rk, cfg.nranks, c0r, c1r);
+                strips_ok = strips_ok && j0 % 2 == 0 && j1 % 2 == 0 && c0r == j0 / 2 && c1r == j1 / 2 && c1r - c0r >= 2;
+            }
+            if (!strips_ok) break;
+            nnx = nx / 2;
+            nny = ny / 2;
+        }
+        out[n++] = MgPlanLevel{nnx, nny, 1};
+        nx = nnx; ny = nny; r = 1;
+    }
+    return n;
+}
+
 // Detect the translation-invariant rows of M and K (kernels.cuh) and switch the SpMV of those slices to
 // the table-driven path.  Off with WAVE_FLAG_NO_STENCIL / WAVE_NO_STENCIL=1, on meshes too small to have a
 // generic middle quad, and when fewer than half of the rows match (variable wave speed).
@@ -1059,27 +1091,10 @@ int mg_setup(wave_ctx *ctx, double s) {
     m->nlev = 1;
     const double cx = 0.5 * (ctx->cfg.x0 + ctx->cfg.x1), cy = 0.5 * (ctx->cfg.y0 + ctx->cfg.y1);
     const double c0 = eval(&ctx->hprog[WAVE_EXPR_C], cx, cy, 0.0);
-    int nx = L.mesh.nx, ny = L.mesh.ny, r = L.mesh.r;
-    for (;;) {
-        int nnx = nx, nny = ny;
-        if (r == 1) {
-            const double dx = (ctx->cfg.x1 - ctx->cfg.x0) / nx, dy = (ctx->cfg.y1 - ctx->cfg.y0) / ny;
-            const bool matters = s * c0 * c0 / (dx * dy) > 0.25;
-            if (!(matters && nx % 2 == 0 && ny % 2 == 0 && std::min(nx, ny) / 2 >= 2)) break;
-            // several ranks: coarse quad row J covers the fine quad rows 2J, 2J+1, so every strip must begin
-            // and end at an even quad row and keep at least two coarse quad rows (same decision on all ranks)
-            bool strips_ok = true;
-            for (int rk = 0; rk < ctx->cfg.nranks && ctx->cfg.nranks > 1; ++rk) {
-                int j0, j1, c0r, c1r;
-                quad_row_split(ny, rk, ctx->cfg.nranks, j0, j1);
-                quad_row_split(ny / 2, rk, ctx->cfg.nranks, c0r, c1r);
-                strips_ok = strips_ok && j0 % 2 == 0 && j1 % 2 == 0 && c0r == j0 / 2 && c1r == j1 / 2 && c1r - c0r >= 2;
-            }
-            if (!strips_ok) break;
-            nnx = nx / 2;
-            nny = ny / 2;
-        }
-        if (m->nlev >= 12) break;
+    MgPlanLevel plan[12];
+    const int n_coarse = mg_plan(ctx->cfg, s, c0, plan, 11);
+    for (int lev = 0; lev < n_coarse; ++lev) {
+        const int nnx = plan[lev].nx, nny = plan[lev].ny;
         wave_config cfg = ctx->cfg;
         cfg.nx = nnx; cfg.ny = nny; cfg.r = 1;
         cfg.scheme = WAVE_SCHEME_NEWMARK;
@@ -1120,7 +1135,6 @@ int mg_setup(wave_ctx *ctx, double s) {
         lv.r = c->d;  // local layout: the restriction reads its upper ghost block
         lv.omega = 0.8;
         ctx->launches += c->launches;
-        nx = nnx; ny = nny; r = 1;
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->mg = m;
@@ -2022,6 +2036,14 @@ int wave_quadrature(int32_t n_points_1d, double *xi, double *eta, double *w) {
     } catch (const std::exception &) {
         return WAVE_ERR_ARG;
     }
+}
+
+int wave_mg_plan(const wave_config *cfg, double s, double c0, int32_t *nx_out, int32_t *ny_out, int32_t max_levels) {
+    if (!cfg || !nx_out || !ny_out || max_levels < 1 || cfg->nx < 1 || cfg->ny < 1 || cfg->nranks < 1) return WAVE_ERR_ARG;
+    MgPlanLevel plan[12];
+    const int n = mg_plan(*cfg, s, c0, plan, std::min<int>(max_levels, 11));
+    for (int k = 0; k < n; ++k) { nx_out[k] = plan[k].nx; ny_out[k] = plan[k].ny; }
+    return n;
 }
 
 int wave_partition_plan(int32_t nx, int32_t ny, int32_t r, int32_t rank, int32_t nranks, wave_partition *out) {

@@ -110,6 +110,7 @@ def lib():
         L.wave_kernel_timing.argtypes = [vp, C.c_int, dp, dp]
         L.wave_partition_plan.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.POINTER(WavePartition)]
+        L.wave_mg_plan.argtypes = [C.POINTER(WaveConfig), C.c_double, C.c_double, ip, ip, C.c_int32]
         _lib = L
     return _lib
 
@@ -144,6 +145,20 @@ def partition_plan(nx, ny, r, rank, nranks):
     if rc:
         raise WaveError(rc, "wave_partition_plan")
     return out
+
+
+def mg_plan(nx, ny, r, s, c0=1.0, nranks=1, rank=0, box=(0.0, 1.0, 0.0, 1.0)):
+    """(nx, ny) of the V-cycle's coarse levels for M + s K on an nx x ny mesh of `box` (host only)."""
+    cfg = WaveConfig()
+    lib().wave_default_config(C.byref(cfg))
+    cfg.nx, cfg.ny, cfg.r = nx, ny, r
+    cfg.x0, cfg.x1, cfg.y0, cfg.y1 = box
+    cfg.rank, cfg.nranks = rank, nranks
+    ox, oy = (C.c_int32 * 16)(), (C.c_int32 * 16)()
+    n = lib().wave_mg_plan(C.byref(cfg), s, c0, ox, oy, 16)
+    if n < 0:
+        raise WaveError(n, "wave_mg_plan")
+    return [(ox[k], oy[k]) for k in range(n)]
 
 
 def cell_dofs(nx, ny, r):

@@ -148,6 +148,30 @@ def test_partition_plan_is_consistent(nx, ny, r, nranks):
     assert prev_end == o.n
 
 
+def test_multigrid_plan_over_strips():
+    """Level planning of the V-cycle (host logic of the multi-GPU multigrid): the hierarchy follows the
+    stiffness criterion s c^2 / (dx dy) > 1/4, a P2 problem starts with P1 on the same mesh, and with several
+    ranks coarsening stops where a strip would lose whole coarse quad rows -- the same plan on every rank."""
+    s = 0.25 * 0.1 ** 2                              # Newmark beta dt^2 at dt = 0.1
+    assert api.mg_plan(64, 64, 1, s) == [(32, 32), (16, 16), (8, 8)]
+    assert api.mg_plan(64, 64, 2, s) == [(64, 64), (32, 32), (16, 16), (8, 8)]
+    assert api.mg_plan(64, 64, 1, 1e-9) == []        # mass dominated: Jacobi sweeps on the fine level only
+    assert api.mg_plan(48, 36, 1, 1.0) == [(24, 18), (12, 9)]   # odd ny stops the halving
+    # several ranks: 64 quad rows over 8 ranks = 8 per rank -> 4 -> 2, then a strip would drop to one coarse row
+    assert api.mg_plan(64, 64, 1, s, nranks=8) == [(32, 32), (16, 16)]
+    assert api.mg_plan(64, 64, 1, s, nranks=2) == [(32, 32), (16, 16), (8, 8)]
+    assert api.mg_plan(64, 128, 1, s, nranks=8, box=(0.0, 1.0, 0.0, 2.0)) == [(32, 64), (16, 32), (8, 16)]
+    # strips that do not start at even quad rows cannot be coarsened at all: 30 rows over 4 ranks = 7, 8, 7, 8
+    assert api.mg_plan(64, 30, 1, 1.0, nranks=4) == []
+    for nranks in (2, 3, 4, 8):
+        plans = {tuple(api.mg_plan(96, 96, 2, 1.0, nranks=nranks, rank=rk)) for rk in range(nranks)}
+        assert len(plans) == 1
+        for nx, ny in next(iter(plans))[1:]:
+            for rk in range(nranks):  # every strip of every coarse level holds whole quad rows, at least two
+                pl = partition_plan(nx, ny, 1, rk, nranks)
+                assert pl.quad_row_end - pl.quad_row_begin >= 2
+
+
 def _run(exe, param_path, cwd):
     return subprocess.run([str(BIN / exe), str(param_path)], cwd=cwd, capture_output=True, text=True, timeout=120)
 
