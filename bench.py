@@ -208,7 +208,10 @@ def workload_config(workload, params, scheme, n_dofs, precond="jacobi"):
     """The part of `config` that names the workload: identical for the GPU arm and the reference arm."""
     return {"workload": workload, "problem": WORKLOADS[workload][0], "scheme": scheme, "Nel": params["Nel"],
             "R": str(params["R"]), "Dt": params["Dt"], "n_dofs": int(n_dofs), "preconditioner": precond,
-            "cg_stop": "ReductionControl(10000, 1e-12, 1e-6)"}
+            "cg_stop": "ReductionControl(10000, 1e-12, 1e-6)",
+            "timing": "GPU arm: CUDA events around every step on the context's stream, L2 flushed between steps "
+                      "(256 MiB write; the working set is far larger than L2 anyway); reference arm: host wall "
+                      "clock around every step"}
 
 
 def full_n_dofs(params):
