@@ -485,6 +485,15 @@ def main():
                     "launches_timed": cgs["iterations"],
                     "share_of_step_time": cgs["ms_total"] / total_ms if total_ms else None,
                     "timed_over": "all CG solves of the timed steps: device ms per solve / iterations"}
+    if roofline is not None and info["stencil_rows"] and kernels:
+        # the stencil SpMV computes the product a CSR kernel would stream 12 nnz + 20 n bytes for
+        csr_bytes = 12.0 * nnz + 20.0 * g.nown
+        sp = kernels[0]
+        roofline["spmv_csr_equivalent"] = {
+            "bytes": csr_bytes, "GB/s": csr_bytes / (sp["avg_launch_ms_in_step"] * 1e-3) / 1e9,
+            "x_peak": csr_bytes / (sp["avg_launch_ms_in_step"] * 1e-3) / 1e9 / peak,
+            "note": "k_spmv's frac is against the 16 B/row the table-driven operator still has to move "
+                    "(x in, y out); run with --no-stencil for the SELL kernel's own roofline"}
     if roofline is not None:
         roofline["spmv_l2_flushed_single_launch"] = {"ms": ms_fl, "GB/s": by_fl / ms_fl / 1e6,
                                                      "frac": by_fl / ms_fl / 1e6 / peak, "algorithmic_bytes": by_fl}
