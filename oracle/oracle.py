@@ -68,6 +68,7 @@ def lib():
         L.oracle_errors.argtypes = [vp, C.c_double, dp]
         L.oracle_probe.restype = C.c_double
         L.oracle_probe.argtypes = [vp]
+        L.oracle_mg_levels.argtypes = [vp]
         for name in ("oracle_n", "oracle_nnz", "oracle_nb", "oracle_ncells"):
             getattr(L, name).restype = C.c_int64
             getattr(L, name).argtypes = [vp]
@@ -238,6 +239,10 @@ class Oracle:
         its = (C.c_int * 2)()
         self.L.oracle_last_iterations(self.h, its)
         return its[0], its[1]
+
+    def mg_levels(self):
+        """Levels of the multigrid hierarchy built by the last *_init with precond=2 (0: none)."""
+        return int(self.L.oracle_mg_levels(self.h))
 
     def energy(self):
         return self.L.oracle_energy(self.h)

@@ -157,6 +157,14 @@ def test_multigrid_plan_over_strips():
     assert api.mg_plan(64, 64, 2, s) == [(64, 64), (32, 32), (16, 16), (8, 8)]
     assert api.mg_plan(64, 64, 1, 1e-9) == []        # mass dominated: Jacobi sweeps on the fine level only
     assert api.mg_plan(48, 36, 1, 1.0) == [(24, 18), (12, 9)]   # odd ny stops the halving
+    # the oracle builds its hierarchy independently (oracle/wave_oracle.c mg_setup): same number of levels
+    for nel, r, dt in (("64", 1, 0.1), ("32", 2, 0.05), ("48, 24", 2, 0.05), ("40", 1, 0.05), ("36, 12", 1, 0.05)):
+        p = problem("standing-mode-wsol", Nel=nel, R=r, Dt=str(dt))
+        o = O.Oracle.from_params(p)
+        o.set_cg(precond=2)
+        o.newmark_init(dt, 0.25, 0.5)
+        nx, ny = api.parse_nel(nel)
+        assert o.mg_levels() == 1 + len(api.mg_plan(nx, ny, r, 0.25 * dt * dt)), (nel, r, dt)
     # several ranks: 64 quad rows over 8 ranks = 8 per rank -> 4 -> 2, then a strip would drop to one coarse row
     assert api.mg_plan(64, 64, 1, s, nranks=8) == [(32, 32), (16, 16)]
     assert api.mg_plan(64, 64, 1, s, nranks=2) == [(32, 32), (16, 16), (8, 8)]
