@@ -511,19 +511,31 @@ def main():
     if world == 1 and not args.no_extras:
         Kx = max(3, min(K, 10))
         extras = []
+        # the headline line must not depend on an extra: a failure there is reported in its place
+        def safely(name, **kw):
+            try:
+                return extra_workload(name, stream, flush, torch, Kx, peak, **kw)
+            except Exception as ex:  # noqa: BLE001
+                torch.cuda.synchronize()
+                return {"workload": name, "error": f"{type(ex).__name__}: {ex}", **kw}
+
         for name in EXTRAS:
             if name != workload:
-                extras.append(extra_workload(name, stream, flush, torch, Kx, peak))
+                extras.append(safely(name))
         if args.precond == "jacobi":
-            extras.append(extra_workload(workload, stream, flush, torch, Kx, peak, precond="mg"))
+            extras.append(safely(workload, precond="mg"))
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        sample, what = cpu_sample_params(params)
-        r = time_oracle(sample, scheme, budget_s=25.0, max_steps=10, precond=2 if args.precond == "mg" else 0)
-        cpu = {"value": r["n"] * r["steps"] / r["seconds"], "unit": "DoF-steps/s", "cores": r["threads"],
-               "kind": "port", "cg_its_per_step": r["cg_its_per_step"],
-               "sample": f"{what}: {r['n']} DoFs, {r['steps']} time steps on the host "
-                         f"(oracle/wave_oracle.c, OpenMP, {r['threads']} threads)"}
+        try:
+            sample, what = cpu_sample_params(params)
+            r = time_oracle(sample, scheme, budget_s=25.0, max_steps=10, precond=2 if args.precond == "mg" else 0)
+            cpu = {"value": r["n"] * r["steps"] / r["seconds"], "unit": "DoF-steps/s", "cores": r["threads"],
+                   "kind": "port", "cg_its_per_step": r["cg_its_per_step"],
+                   "sample": f"{what}: {r['n']} DoFs, {r['steps']} time steps on the host "
+                             f"(oracle/wave_oracle.c, OpenMP, {r['threads']} threads)"}
+        except Exception as ex:  # noqa: BLE001
+            cpu = {"value": None, "unit": "DoF-steps/s", "cores": 0, "kind": "port",
+                   "sample": f"CPU leg failed: {type(ex).__name__}: {ex}"}
 
     line = {
         "metric": "dof_steps_per_sec", "value": value, "unit": "DoF-steps/s", "n_gpus": n_gpus, "steps": K,
