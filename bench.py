@@ -300,6 +300,41 @@ def extra_workload(name, stream, flush, torch, K, peak, precond=None):
     return out
 
 
+def measure_e2e(g, api, torch, dist, world, scheme, n, K, barrier):
+    """The stateless host-buffer entry point: H2D of u, v, a from pinned memory + step + D2H every step."""
+    def pinned(vec):
+        t = torch.empty(n, dtype=torch.float64).pin_memory()
+        t.numpy()[g.row0:g.row0 + g.nown] = vec
+        return t.numpy()
+
+    # every rank keeps (global-length) host arrays and moves its own rows each step
+    if world == 1:
+        u0_, v0_ = g.vector(api.VEC_U), g.vector(api.VEC_V)
+        a0_ = g.vector(api.VEC_A) if scheme == "newmark" else None
+    else:
+        u0_, v0_ = g.vector_owned(api.VEC_U), g.vector_owned(api.VEC_V)
+        a0_ = g.vector_owned(api.VEC_A) if scheme == "newmark" else None
+    u, v = pinned(u0_), pinned(v0_)
+    a = pinned(a0_) if scheme == "newmark" else None
+    nvec = 3 if scheme == "newmark" else 2
+    for _ in range(2):
+        g.step_host(u, v, a)
+    barrier()
+    Ke = max(3, min(K, 10))
+    t0 = time.time()
+    for _ in range(Ke):
+        g.step_host(u, v, a)
+    barrier()
+    e2e_s = time.time() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    return {"value": n * Ke / e2e_s, "unit": "DoF-steps/s", "h2d_bytes_per_step": nvec * 8 * n,
+            "d2h_bytes_per_step": nvec * 8 * n + 16 * world, "steps": Ke,
+            "api": "wave_step_host (pinned host u, v, a in; u, v, a, norms out; every rank moves its own rows)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -409,38 +444,14 @@ def main():
 
     # ---- e2e: the stateless host-buffer entry point, H2D + D2H of the state every step -------------
     e2e = None
-    if K > 0:
-        def pinned(vec):
-            t = torch.empty(n, dtype=torch.float64).pin_memory()
-            t.numpy()[g.row0:g.row0 + g.nown] = vec
-            return t.numpy()
-
-        # every rank keeps (global-length) host arrays and moves its own rows each step
-        if world == 1:
-            u0_, v0_, a0_ = g.vector(api.VEC_U), g.vector(api.VEC_V), g.vector(api.VEC_A) if scheme == "newmark" else None
-        else:
-            u0_, v0_ = g.vector_owned(api.VEC_U), g.vector_owned(api.VEC_V)
-            a0_ = g.vector_owned(api.VEC_A) if scheme == "newmark" else None
-        u, v = pinned(u0_), pinned(v0_)
-        a = pinned(a0_) if scheme == "newmark" else None
-        nvec = 3 if scheme == "newmark" else 2
-        for _ in range(2):
-            g.step_host(u, v, a)
-        barrier()
-        Ke = max(3, min(K, 10))
-        t0 = time.time()
-        for _ in range(Ke):
-            g.step_host(u, v, a)
-        barrier()
-        e2e_s = time.time() - t0
+    try:
+        e2e = measure_e2e(g, api, torch, dist if world > 1 else None, world, scheme, n, K, barrier)
+    except Exception as ex:  # noqa: BLE001
         if world > 1:
-            tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e_s = float(tt.item())
-        e2e = {"value": n * Ke / e2e_s, "unit": "DoF-steps/s", "h2d_bytes_per_step": nvec * 8 * n,
-               "d2h_bytes_per_step": nvec * 8 * n + 16 * world, "steps": Ke,
-               "api": "wave_step_host (pinned host u, v, a in; u, v, a, norms out; every rank moves its own rows)"}
-        del u, v, a
+            raise  # the other ranks are inside the same collective calls
+        torch.cuda.synchronize()
+        e2e = {"value": None, "unit": "DoF-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "error": f"{type(ex).__name__}: {ex}"}
 
     # ---- roofline of the dominant kernel, timed live inside the steps above --------------------------
     peak, peak_src = hbm_peak()
