@@ -427,8 +427,7 @@ def main():
     launches = g.launch_count() - launches0
     cgs = g.cg_stats()
     # second pass over further steps of the same run with every kernel of the CG iterations bracketed by
-    # events on the context stream (kept out of the pass above: the brackets cost ~1 us per launch and
-    # switch off the programmatic overlap of consecutive kernels)
+    # events on the context stream (kept out of the pass above: the brackets cost ~1 us per launch)
     g.kernel_timing(True)
     Kr = max(3, min(K, 10))
     ms2, _ = timed_steps(g, stream, Kr, flush, torch)
@@ -508,8 +507,9 @@ def main():
     if roofline is not None:
         roofline["spmv_l2_flushed_single_launch"] = {"ms": ms_fl, "GB/s": by_fl / ms_fl / 1e6,
                                                      "frac": by_fl / ms_fl / 1e6 / peak, "algorithmic_bytes": by_fl}
-        roofline["cg_iteration"] = {"ms": ms_it, "algorithmic_bytes": by_it, "GB/s": by_it / ms_it / 1e6,
-                                    "frac": by_it / ms_it / 1e6 / peak}
+        roofline["cg_iteration"] = None if cg_fused else {"ms": ms_it, "algorithmic_bytes": by_it,
+                                                         "GB/s": by_it / ms_it / 1e6,
+                                                         "frac": by_it / ms_it / 1e6 / peak}
         roofline["operator"] = info
     g.close()
     if rank != 0:
