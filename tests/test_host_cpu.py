@@ -386,3 +386,26 @@ def test_vtu_writer_round_trip(tmp_path):
     assert [p.attrib["Source"] for p in rec.findall("PUnstructuredGrid/Piece")] == ["solution_0007.0.vtu"]
     assert [a.attrib["Name"] for a in rec.findall("PUnstructuredGrid/PPointData/PDataArray")] == ["u", "partitioning"]
     assert not (tmp_path / "bad.vtu").exists() or (tmp_path / "bad.vtu").stat().st_size == 0
+
+
+def test_bench_cpu_sample_is_a_squeezed_strip_of_the_workload():
+    """bench.py's bounded CPU sample: same dx, dy and Dt on a strip of the mesh, functions squeezed in y so
+    the data stay compatible with the strip's boundary (only the stand-alone variable y is rewritten)."""
+    import sys
+
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    p, scheme, scaling = bench.make_params("newmark-4096-p2", 1)
+    q, what = bench.cpu_sample_params(p)
+    assert scaling == "strong" and q["Nel"] == "4096, 256" and q["Dt"] == p["Dt"]
+    x0, x1, y0, y1 = api.parse_geometry(q["Geometry"])
+    assert (x0, x1, y0) == (0.0, 1.0, 0.0) and y1 == pytest.approx(1.0 / 16.0)
+    assert q["U0"]["Function expression"] == "sin(pi*x)*sin(pi*(0.0 + 16.0*(y - 0.0)))"
+    assert p["U0"]["Function expression"] == "sin(pi*x)*sin(pi*y)"          # the workload itself is untouched
+    p4, _, _ = bench.make_params("c4-ricker-be-4096-p2", 1)
+    q4, _ = bench.cpu_sample_params(p4)
+    assert "ys" in q4["F"]["Function expression"] and "(0.0 + 16.0*(y - 0.0))-ys" in q4["F"]["Function expression"]
+    small, what_small = bench.cpu_sample_params(bench.make_params("c2-standing-newmark-1024-p1", 1)[0])
+    assert what_small == "the whole workload" and small["Nel"] == "1024"
+    assert bench.full_n_dofs(p) == 67125249
