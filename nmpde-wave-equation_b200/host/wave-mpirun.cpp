@@ -163,6 +163,14 @@ int main(int argc, char** argv)
     ::sigaction(SIGINT, &sa, nullptr);
     ::sigaction(SIGTERM, &sa, nullptr);
 
+    // SIGINT / SIGTERM stay blocked from before the fork until the child has put the default actions back:
+    // a stop request that arrives between fork and exec (a sibling rank failed at once) then stays pending and
+    // terminates the child, instead of being swallowed by the handler it inherited from the launcher
+    sigset_t stop_signals, previous_mask;
+    ::sigemptyset(&stop_signals);
+    ::sigaddset(&stop_signals, SIGINT);
+    ::sigaddset(&stop_signals, SIGTERM);
+    ::sigprocmask(SIG_BLOCK, &stop_signals, &previous_mask);
     children.assign(static_cast<size_t>(ranks), -1);
     for (long r = 0; r < ranks; ++r)
     {
@@ -175,6 +183,9 @@ int main(int argc, char** argv)
         }
         if (pid == 0)
         {
+            ::signal(SIGINT, SIG_DFL);
+            ::signal(SIGTERM, SIG_DFL);
+            ::sigprocmask(SIG_SETMASK, &previous_mask, nullptr);
             ::setenv("WAVE_RANK", std::to_string(r).c_str(), 1);
             ::setenv("WAVE_LOCAL_RANK", std::to_string(r).c_str(), 1);
             ::execvp(cl.program[0], cl.program.data());
@@ -183,6 +194,7 @@ int main(int argc, char** argv)
         }
         children[static_cast<size_t>(r)] = pid;
     }
+    ::sigprocmask(SIG_SETMASK, &previous_mask, nullptr);
 
     // the first failure decides the exit status; the surviving ranks would wait for the lost one in
     // their next collective, so they are told to stop
