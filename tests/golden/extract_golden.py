@@ -10,6 +10,7 @@ Sources (reference artefacts, read-only):
       recipe: scripts/dissipation_dispersion_sweep.py:179-198
 Outputs: tests/golden/convergence_rows.json, tests/golden/dissdisp_rows.json (the rows the test suite
 runs) and, with --all, convergence_rows_all.json / dissdisp_rows_all.json (every row, for the offline sweeps)
+and scalability_seconds.json (mean wall seconds per scheme and rank count of analysis/data/scalability-results.csv)
 """
 import csv
 import json
@@ -78,6 +79,18 @@ def main_all():
                           "final_rel_H1": float(row["final_rel_H1"])})
     (OUT / "dissdisp_rows_all.json").write_text(json.dumps(drows, indent=0))
     print(len(rows), "convergence rows,", len(drows), "dissdisp rows (all)")
+    # analysis/data/scalability-results.csv (scripts/scalability_sweep.py:183-230): whole-process wall seconds,
+    # Nel=640, R=1, Dt=8e-5, T=0.05; mean over the repeats per (scheme, nprocs)
+    acc = {}
+    with open(REF / "scalability-results.csv") as fh:
+        for row in csv.DictReader(fh):
+            if row["returncode"] == "0":
+                acc.setdefault((row["scheme"], int(row["nprocs"])), []).append(float(row["seconds"]))
+    table = {}
+    for (scheme, nprocs), secs in sorted(acc.items()):
+        table.setdefault(scheme, {})[str(nprocs)] = round(sum(secs) / len(secs), 3)
+    (OUT / "scalability_seconds.json").write_text(json.dumps(table, indent=0))
+    print(len(acc), "scalability (scheme, nprocs) means")
 
 
 if __name__ == "__main__":

@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""Run the reference's own sweep drivers UNMODIFIED against this repository's launcher and host executables,
+and compare the tables they write with the reference's result tables.
+
+The drivers (scripts/convergence_sweep.py:86-96, scripts/dissipation_dispersion_sweep.py:113-122,
+scripts/scalability_sweep.py:71-85) locate everything relative to their own file: `../parameters/
+standing-mode-wsol.json`, `../build/main-theta`, `../build/main-newmark`, and start
+`<launcher> -np P [--bind-to core --map-by socket] <binary> <params.json>` from `build/`.  `checkout()` lays
+that directory tree out in a scratch directory -- the scripts and parameter files are copied there from the
+reference at run time, never into this repository -- with `build/main-*` pointing at the executables to test,
+and `run_script()` starts a driver with `--launcher tools/mpirun-shim` (the product's wave-mpirun).
+
+Where there is a GPU, `build/main-*` are the product's executables (nmpde-wave-equation_b200/bin/).  The
+reference does not exist on the GPU box, so in this container -- no GPU -- the drivers run against the host
+classes linked with the TEST DOUBLE of the C ABI (tests/abi_double/, numerics = the CPU oracle): everything
+above the ABI (launcher, parameter reader, folder and CSV conventions, exit codes) is the product's code.
+
+    python tools/reference_scripts_report.py run  --reference /root/reference --work /tmp/sweeps \\
+        --script convergence_sweep.py -- --nprocs 4 --nel 10 20 40
+    python tools/reference_scripts_report.py report --conv a.csv [b.csv ...] --diss d.csv --scal s.csv \\
+        --out profiles/r2_reference_scripts.md
+"""
+import argparse
+import csv
+import json
+import math
+import os
+import shutil
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+SHIM = ROOT / "tools" / "mpirun-shim"
+TIGHT_CG = {"WAVE_CG_REDUCE": "1e-13", "WAVE_CG_TOL": "1e-30"}  # the reference's AMG-CG lands far below its 1e-6 bar
+BINS = [1e-6, 1e-5, 1e-4, 1e-3]
+
+
+def checkout(reference, work, bin_dir):
+    """The directory tree the drivers expect, in `work`: scripts/ and parameters/ copied from the reference,
+    build/main-theta and build/main-newmark -> the executables in `bin_dir`."""
+    reference, work, bin_dir = Path(reference), Path(work), Path(bin_dir)
+    work.mkdir(parents=True, exist_ok=True)
+    for sub in ("scripts", "parameters"):
+        if not (work / sub).exists():
+            shutil.copytree(reference / sub, work / sub)
+    (work / "build").mkdir(exist_ok=True)
+    for exe in ("main-theta", "main-newmark"):
+        link = work / "build" / exe
+        if link.is_symlink() or link.exists():
+            link.unlink()
+        link.symlink_to(bin_dir / exe)
+    return work
+
+
+def run_script(work, script, script_args, env=None, timeout=None):
+    """Start one driver the way its docstring says (from build/), with this repository's launcher."""
+    work = Path(work)
+    cmd = [sys.executable, str(work / "scripts" / script), "--launcher", str(SHIM), *script_args]
+    e = dict(os.environ)
+    e.update(env or {})
+    t0 = time.time()
+    r = subprocess.run(cmd, cwd=work / "build", capture_output=True, text=True, env=e, timeout=timeout)
+    return r, time.time() - t0
+
+
+# ---- comparison with the reference's tables (fixtures tests/golden/*_rows_all.json) ---------------------
+def _f(x):
+    try:
+        return float(x)
+    except (TypeError, ValueError):
+        return None
+
+
+def _dev(got, gold):
+    worst = 0.0
+    for a, b in zip(got, gold):
+        if b is None or not math.isfinite(b):
+            return None  # the reference's own run blew up: nothing to compare
+        if a is None or not math.isfinite(a):
+            return float("inf")
+        worst = max(worst, abs(a - b) / abs(b) if b != 0 else abs(a))
+    return worst
+
+
+def _class(explicit, gold):
+    if any(g is None or not math.isfinite(g) for g in gold):
+        return "reference value nan/inf (its run blew up)"
+    if explicit:
+        return "explicit, printed error > 1.5 (unstable run)" if max(gold[:2]) > 1.5 else \
+            "explicit (theta=0, beta=0), printed error <= 1.5"
+    return "implicit (theta=1/2, theta=1, beta=1/4)"
+
+
+def _table(rows):
+    classes = {}
+    for klass, d in rows:
+        c = classes.setdefault(klass, [0] * (len(BINS) + 2))
+        c[0] += 1
+        if d is None:
+            c[-1] += 1
+            continue
+        for k, b in enumerate(BINS):
+            if d <= b:
+                c[1 + k] += 1
+                break
+        else:
+            c[-1] += 1
+    out = ["| class | rows | <= 1e-6 | <= 1e-5 | <= 1e-4 | <= 1e-3 | worse / not comparable |", "|---|---|---|---|---|---|---|"]
+    for name in sorted(classes):
+        c = classes[name]
+        out.append(f"| {name} | {c[0]} | " + " | ".join(str(x) for x in c[1:]) + " |")
+    return out
+
+
+def compare_convergence(files):
+    """Rows of the drivers' merged convergence-results.csv against analysis/data/convergence-results.csv."""
+    gold = {}
+    for g in json.loads((ROOT / "tests" / "golden" / "convergence_rows_all.json").read_text()):
+        par = g["Theta"] if g["scheme"] == "theta" else g["Beta"]
+        gold[(g["scheme"], g["Nel"], g["R"], float(g["Dt"]), float(par))] = g
+    rows, unmatched, seen = [], 0, set()
+    for f in files:
+        for r in csv.DictReader(Path(f).open()):
+            scheme = "theta" if r["method"].startswith("theta") else "newmark"
+            par = float(r["theta"]) if scheme == "theta" else float(r["beta"])
+            key = (scheme, int(r["N_el_x"]), int(r["r"]), float(r["dt"]), par)
+            g = gold.get(key)
+            if g is None or key in seen:
+                unmatched += 1
+                continue
+            seen.add(key)
+            want = [g["rel_L2"], g["rel_H1"]]
+            d = _dev([_f(r["rel_L2_error_final"]), _f(r["rel_H1_error_final"])], want)
+            rows.append({"key": key, "line": g["line"], "class": _class(par == 0.0, want), "dev": d})
+    return rows, unmatched, len(gold)
+
+
+def compare_dissdisp(f):
+    gold = {}
+    for g in json.loads((ROOT / "tests" / "golden" / "dissdisp_rows_all.json").read_text()):
+        gold[(g["scheme"], g["Nel"], g["R"], float(g["Dt"]))] = g
+    rows, unmatched = [], 0
+    for r in csv.DictReader(Path(f).open()):
+        key = (r["scheme"], int(r["Nel"]), int(r["R"]), float(r["dt"]))
+        g = gold.get(key)
+        if g is None:
+            unmatched += 1
+            continue
+        names = ("energy_ratio", "max_rel_L2", "final_rel_L2", "final_rel_H1")
+        want = [g[k] for k in names]
+        got = [_f(r[k]) for k in names]
+        rows.append({"key": key, "line": g["line"], "class": _class(key[0] in ("theta-0.0", "newmark-0.00"), want[1:]),
+                     "dev": _dev(got, want), "energy_ratio": (got[0], want[0])})
+    return rows, unmatched, len(gold)
+
+
+def report(args):
+    out = ["# The reference's sweep drivers, unmodified, against this repository's launcher and host executables",
+           "",
+           "`tools/reference_scripts_report.py`: `scripts/convergence_sweep.py`, `scripts/dissipation_dispersion_sweep.py`",
+           "and `scripts/scalability_sweep.py` copied at run time from the reference into a scratch checkout layout",
+           "(`scripts/`, `parameters/`, `build/main-theta`, `build/main-newmark`) and started from `build/` with",
+           "`--launcher tools/mpirun-shim` -- no edit to any of them.  The launcher is the product's `wave-mpirun`",
+           "(mpirun's command line; `-np 4 --bind-to core --map-by socket <binary> <file>` as the drivers build it).",
+           "",
+           "**Where this ran.** In the build container, which has the reference but no GPU; the GPU box has a GPU but",
+           "no reference (and reference sources may not be copied into this repository), so the drivers cannot meet the",
+           "GPU.  `build/main-*` were therefore the product's host classes (`nmpde-wave-equation_b200/host/*.cpp`,",
+           "unchanged: parameter reader, folder naming, CSV writers, exit codes) linked with the **test double** of the C",
+           "ABI (`tests/abi_double/wave_abi_on_oracle.cpp`: the ~25 entry points the host classes call, implemented on",
+           "the CPU oracle).  What this establishes is the drop-in property *above* the ABI: the drivers find the",
+           "binaries, their parameter files parse, their launcher command line is accepted, and the files they read back",
+           "(`../results/<method>-<stem>/convergence.csv`, `run-R…/energy.csv`, `error.csv`, `probe.csv`) are where and",
+           "what they expect.  *Below* the ABI, the same rows through libwavegpu on a B200 are in",
+           "`profiles/r2_golden_all.md` (library calls) and `tests/test_gpu_cli.py` (executables + launcher, the",
+           "drivers' recipe replayed).  CG solved tightly (`WAVE_CG_REDUCE=1e-13`), as in those.",
+           ""]
+    if args.conv:
+        rows, unmatched, total = compare_convergence(args.conv)
+        out += [f"## convergence_sweep.py: {len(rows)} of the {total} rows of analysis/data/convergence-results.csv regenerated",
+                "",
+                f"Arguments: `{args.conv_args}`.  Deviation = |regenerated - printed| / printed, the larger of the final",
+                "relative L2 and H1 errors (7 printed digits).",
+                "", *_table([(r["class"], r["dev"]) for r in rows]), ""]
+        fin = [r for r in rows if r["dev"] is not None and math.isfinite(r["dev"])]
+        exact = sum(1 for r in fin if r["dev"] <= 5e-7)
+        out += [f"{exact} rows reproduce every printed digit (deviation <= 5e-7, the rounding of a 7-digit number).  "
+                f"Rows the driver wrote that the table does not hold: {unmatched}.", ""]
+        worst = sorted((r for r in fin if r["class"].startswith("implicit")), key=lambda r: -r["dev"])[:5]
+        if worst:
+            out += ["Largest deviations among the implicit rows:", "", "| csv line | scheme, Nel, R, dt, parameter | deviation |",
+                    "|---|---|---|"]
+            out += [f"| {r['line']} | {r['key']} | {r['dev']:.1e} |" for r in worst] + [""]
+    if args.diss:
+        rows, unmatched, total = compare_dissdisp(args.diss)
+        out += [f"## dissipation_dispersion_sweep.py: {len(rows)} of the {total} rows of analysis/data/dissdisp-results.csv regenerated",
+                "",
+                f"Arguments: `{args.diss_args}` (the driver's defaults: Nel = 60, R = 1, T = 5, eleven time steps, logging",
+                "every step; the driver computes the energy ratio, the maximal and final errors from the `energy.csv` /",
+                "`error.csv` of every run).  Deviation = the largest over energy ratio, max / final rel-L2, final rel-H1.",
+                "", *_table([(r["class"], r["dev"]) for r in rows]), ""]
+        same = sum(1 for r in rows if r["energy_ratio"][0] == r["energy_ratio"][1])
+        out += [f"Energy ratios identical to the table's to the last bit: {same} of {len(rows)}.  "
+                f"Rows without a partner in the table: {unmatched}.", ""]
+    if args.scal:
+        out += ["## scalability_sweep.py --nprocs 1",
+                "",
+                "The driver's fixed configuration (Nel = 640, R = 1, Dt = 8e-5, T = 0.05: 410 881 DoFs, 625 steps), whole-",
+                "process wall time per scheme as the driver measures it.  Here that is the time of the **CPU oracle** behind",
+                f"the test double ({args.scal_note}), so the column says nothing about the GPU; it is listed to show the",
+                "driver's table is produced.  The reference's own figure on one Xeon Gold 6238R core is next to it; the same",
+                "configuration through libwavegpu on a B200 is in `profiles/r1_published_config.md`.",
+                "", "| scheme | returncode | seconds (oracle behind the double) | reference table, nprocs = 1 (mean) |", "|---|---|---|---|"]
+        ref = {}
+        fx = ROOT / "tests" / "golden" / "scalability_np1.json"
+        if fx.exists():
+            ref = json.loads(fx.read_text())
+        for r in csv.DictReader(Path(args.scal).open()):
+            out.append(f"| {r['scheme']} | {r['returncode']} | {float(r['seconds']):.1f} | {ref.get(r['scheme'], '–')} |")
+        out.append("")
+    Path(args.out).write_text("\n".join(out))
+    print(f"wrote {args.out}")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    r = sub.add_parser("run")
+    r.add_argument("--reference", default="/root/reference")
+    r.add_argument("--work", required=True)
+    r.add_argument("--script", required=True)
+    r.add_argument("--bin", default=None, help="directory with main-theta / main-newmark (default: build the test double)")
+    r.add_argument("--tight-cg", action="store_true")
+    r.add_argument("script_args", nargs="*")
+    p = sub.add_parser("report")
+    p.add_argument("--conv", nargs="*", default=[])
+    p.add_argument("--conv-args", default="")
+    p.add_argument("--diss", default=None)
+    p.add_argument("--diss-args", default="--nprocs 4")
+    p.add_argument("--scal", default=None)
+    p.add_argument("--scal-note", default="OpenMP")
+    p.add_argument("--out", required=True)
+    args = ap.parse_args()
+    if args.cmd == "report":
+        report(args)
+        return
+    bin_dir = args.bin
+    if bin_dir is None:
+        sys.path.insert(0, str(ROOT / "tests" / "abi_double"))
+        import build_double
+
+        bin_dir = build_double.build()
+    checkout(args.reference, args.work, bin_dir)
+    res, secs = run_script(args.work, args.script, args.script_args, env=TIGHT_CG if args.tight_cg else None)
+    sys.stdout.write(res.stdout[-4000:])
+    sys.stderr.write(res.stderr[-4000:])
+    print(f"[{args.script}] exit {res.returncode} after {secs:.1f} s; outputs in {Path(args.work) / 'build'}")
+    sys.exit(res.returncode)
+
+
+if __name__ == "__main__":
+    main()
