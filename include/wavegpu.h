@@ -59,7 +59,7 @@ enum { WAVE_MAT_M = 0, WAVE_MAT_K = 1, WAVE_MAT_SYS1 = 2, WAVE_MAT_SYS2 = 3 };
 /* WAVE_PRECOND_MG: geometric multigrid V-cycle ([P2 ->] P1 -> P1 on Nel/2, Nel/4, ...; rediscretised
    coarse operators, damped-Jacobi smoothing), the structured-mesh counterpart of the reference's
    Trilinos ML AMG with Chebyshev smoothing; used for the solves with the stiffness term (matrix_a /
-   matrix_u), Jacobi for the mass-only solves; single rank. */
+   matrix_u), Jacobi for the mass-only solves; one rank or strips over several ranks (wave_mg_plan). */
 enum { WAVE_PRECOND_JACOBI = 0, WAVE_PRECOND_NONE = 1, WAVE_PRECOND_MG = 2 };
 
 typedef struct {

@@ -40,7 +40,7 @@ BINS = [1e-6, 1e-5, 1e-4, 1e-3]
 def checkout(reference, work, bin_dir):
     """The directory tree the drivers expect, in `work`: scripts/ and parameters/ copied from the reference,
     build/main-theta and build/main-newmark -> the executables in `bin_dir`."""
-    reference, work, bin_dir = Path(reference), Path(work), Path(bin_dir)
+    reference, work, bin_dir = Path(reference).resolve(), Path(work).resolve(), Path(bin_dir).resolve()
     work.mkdir(parents=True, exist_ok=True)
     for sub in ("scripts", "parameters"):
         if not (work / sub).exists():
@@ -156,70 +156,87 @@ def compare_dissdisp(f):
     return rows, unmatched, len(gold)
 
 
+def _conv_section(title, files, how, out):
+    rows, unmatched, total = compare_convergence(files)
+    out += [f"### convergence_sweep.py: {len(rows)} of the {total} rows of analysis/data/convergence-results.csv regenerated", "",
+            f"Arguments: `{how}`.  Deviation = |regenerated - printed| / printed, the larger of the final relative L2 and",
+            "H1 errors (7 printed digits).", "", *_table([(r["class"], r["dev"]) for r in rows]), ""]
+    fin = [r for r in rows if r["dev"] is not None and math.isfinite(r["dev"])]
+    exact = sum(1 for r in fin if r["dev"] <= 5e-7)
+    out += [f"{exact} rows reproduce every printed digit (deviation <= 5e-7, the rounding of a 7-digit number).  "
+            f"Rows the driver wrote that the table does not hold: {unmatched}.", ""]
+    worst = sorted((r for r in fin if r["class"].startswith("implicit") and r["dev"] > 1e-6), key=lambda r: -r["dev"])[:5]
+    if worst:
+        out += ["Largest deviations among the implicit rows (P2 rows with printed errors <= 1e-4, where the reference's own",
+                "theta = 1/2 and Newmark-1/4 rows -- the same scheme -- differ by as much because its CG stops at 1e-6):", "",
+                "| csv line | scheme | Nel | R | dt | theta / beta | deviation |", "|---|---|---|---|---|---|---|"]
+        out += [f"| {r['line']} | {r['key'][0]} | {r['key'][1]} | {r['key'][2]} | {r['key'][3]:g} | {r['key'][4]:g} | {r['dev']:.1e} |"
+                for r in worst] + [""]
+    return rows
+
+
+def _diss_section(f, how, out):
+    rows, unmatched, total = compare_dissdisp(f)
+    out += [f"### dissipation_dispersion_sweep.py: {len(rows)} of the {total} rows of analysis/data/dissdisp-results.csv regenerated", "",
+            f"Arguments: `{how}` (Nel = 60, R = 1, T = 5, logging every step; the driver computes the energy ratio and the",
+            "maximal / final errors from the `energy.csv` / `error.csv` / `probe.csv` it finds under the run folder it predicts).",
+            "Deviation = the largest over energy ratio, max / final rel-L2, final rel-H1.", "",
+            *_table([(r["class"], r["dev"]) for r in rows]), ""]
+    same = sum(1 for r in rows if r["energy_ratio"][0] == r["energy_ratio"][1])
+    out += [f"Energy ratios identical to the table's to the last bit: {same} of {len(rows)}.  "
+            f"Rows without a partner in the table: {unmatched}.", ""]
+    return rows
+
+
 def report(args):
-    out = ["# The reference's sweep drivers, unmodified, against this repository's launcher and host executables",
+    out = ["# The reference's sweep drivers, unmodified, against this repository's launcher and executables (row f3)",
            "",
            "`tools/reference_scripts_report.py`: `scripts/convergence_sweep.py`, `scripts/dissipation_dispersion_sweep.py`",
-           "and `scripts/scalability_sweep.py` copied at run time from the reference into a scratch checkout layout",
+           "and `scripts/scalability_sweep.py`, copied at run time from the reference into a scratch checkout layout",
            "(`scripts/`, `parameters/`, `build/main-theta`, `build/main-newmark`) and started from `build/` with",
-           "`--launcher tools/mpirun-shim` -- no edit to any of them.  The launcher is the product's `wave-mpirun`",
-           "(mpirun's command line; `-np 4 --bind-to core --map-by socket <binary> <file>` as the drivers build it).",
-           "",
-           "**Where this ran.** In the build container, which has the reference but no GPU; the GPU box has a GPU but",
-           "no reference (and reference sources may not be copied into this repository), so the drivers cannot meet the",
-           "GPU.  `build/main-*` were therefore the product's host classes (`nmpde-wave-equation_b200/host/*.cpp`,",
-           "unchanged: parameter reader, folder naming, CSV writers, exit codes) linked with the **test double** of the C",
-           "ABI (`tests/abi_double/wave_abi_on_oracle.cpp`: the ~25 entry points the host classes call, implemented on",
-           "the CPU oracle).  What this establishes is the drop-in property *above* the ABI: the drivers find the",
-           "binaries, their parameter files parse, their launcher command line is accepted, and the files they read back",
-           "(`../results/<method>-<stem>/convergence.csv`, `run-R…/energy.csv`, `error.csv`, `probe.csv`) are where and",
-           "what they expect.  *Below* the ABI, the same rows through libwavegpu on a B200 are in",
-           "`profiles/r2_golden_all.md` (library calls) and `tests/test_gpu_cli.py` (executables + launcher, the",
-           "drivers' recipe replayed).  CG solved tightly (`WAVE_CG_REDUCE=1e-13`), as in those.",
+           "`--launcher tools/mpirun-shim` -- no edit to any of them; the copies are never committed.  The launcher is the",
+           "product's `wave-mpirun` (mpirun's command line: `-np 4 --bind-to core --map-by socket <binary> <file>` as the",
+           "drivers build it; one rank per visible GPU).  CG solved tightly (`WAVE_CG_REDUCE=1e-13`): the reference's",
+           "AMG-preconditioned solves land far below their 1e-6 stopping bar, Jacobi-CG stops at it.",
            ""]
-    if args.conv:
-        rows, unmatched, total = compare_convergence(args.conv)
-        out += [f"## convergence_sweep.py: {len(rows)} of the {total} rows of analysis/data/convergence-results.csv regenerated",
-                "",
-                f"Arguments: `{args.conv_args}`.  Deviation = |regenerated - printed| / printed, the larger of the final",
-                "relative L2 and H1 errors (7 printed digits).",
-                "", *_table([(r["class"], r["dev"]) for r in rows]), ""]
-        fin = [r for r in rows if r["dev"] is not None and math.isfinite(r["dev"])]
-        exact = sum(1 for r in fin if r["dev"] <= 5e-7)
-        out += [f"{exact} rows reproduce every printed digit (deviation <= 5e-7, the rounding of a 7-digit number).  "
-                f"Rows the driver wrote that the table does not hold: {unmatched}.", ""]
-        worst = sorted((r for r in fin if r["class"].startswith("implicit")), key=lambda r: -r["dev"])[:5]
-        if worst:
-            out += ["Largest deviations among the implicit rows:", "", "| csv line | scheme, Nel, R, dt, parameter | deviation |",
-                    "|---|---|---|"]
-            out += [f"| {r['line']} | {r['key']} | {r['dev']:.1e} |" for r in worst] + [""]
-    if args.diss:
-        rows, unmatched, total = compare_dissdisp(args.diss)
-        out += [f"## dissipation_dispersion_sweep.py: {len(rows)} of the {total} rows of analysis/data/dissdisp-results.csv regenerated",
-                "",
-                f"Arguments: `{args.diss_args}` (the driver's defaults: Nel = 60, R = 1, T = 5, eleven time steps, logging",
-                "every step; the driver computes the energy ratio, the maximal and final errors from the `energy.csv` /",
-                "`error.csv` of every run).  Deviation = the largest over energy ratio, max / final rel-L2, final rel-H1.",
-                "", *_table([(r["class"], r["dev"]) for r in rows]), ""]
-        same = sum(1 for r in rows if r["energy_ratio"][0] == r["energy_ratio"][1])
-        out += [f"Energy ratios identical to the table's to the last bit: {same} of {len(rows)}.  "
-                f"Rows without a partner in the table: {unmatched}.", ""]
-    if args.scal:
-        out += ["## scalability_sweep.py --nprocs 1",
-                "",
-                "The driver's fixed configuration (Nel = 640, R = 1, Dt = 8e-5, T = 0.05: 410 881 DoFs, 625 steps), whole-",
-                "process wall time per scheme as the driver measures it.  Here that is the time of the **CPU oracle** behind",
-                f"the test double ({args.scal_note}), so the column says nothing about the GPU; it is listed to show the",
-                "driver's table is produced.  The reference's own figure on one Xeon Gold 6238R core is next to it; the same",
-                "configuration through libwavegpu on a B200 is in `profiles/r1_published_config.md`.",
-                "", "| scheme | returncode | seconds (oracle behind the double) | reference table, nprocs = 1 (mean) |", "|---|---|---|---|"]
-        ref = {}
-        fx = ROOT / "tests" / "golden" / "scalability_np1.json"
-        if fx.exists():
-            ref = json.loads(fx.read_text())
-        for r in csv.DictReader(Path(args.scal).open()):
-            out.append(f"| {r['scheme']} | {r['returncode']} | {float(r['seconds']):.1f} | {ref.get(r['scheme'], '–')} |")
-        out.append("")
+    if args.b200_conv or args.b200_diss:
+        out += ["## 1. On a B200, through the product's executables and libwavegpu", "",
+                "`tools/run_reference_drivers.sh nmpde-wave-equation_b200/bin <scratch copy> gpurun_out/…` on one B200",
+                f"({args.b200_note}).  Every run is a fresh process (CUDA context + set-up: 2.3-5.8 s of wall time per run as",
+                "the drivers log it, for 0.004-0.07 s inside the time loop), so the grid is small; raw files:",
+                "`profiles/r2_reference_scripts_b200/`.", ""]
+        if args.b200_conv:
+            _conv_section("b200", args.b200_conv, args.b200_conv_args, out)
+        if args.b200_diss:
+            _diss_section(args.b200_diss, args.b200_diss_args, out)
+    if args.conv or args.diss or args.scal:
+        out += ["## 2. In the build container (no GPU), host classes on the test double of the C ABI", "",
+                "The larger grids.  `build/main-*` are the product's host sources (`nmpde-wave-equation_b200/host/*.cpp`,",
+                "unchanged: parameter reader, folder naming, CSV writers, exit codes) linked with",
+                "`tests/abi_double/wave_abi_on_oracle.cpp` -- the ~25 entry points the host classes call, implemented on the CPU",
+                "oracle -- instead of libwavegpu.so (test infrastructure, built into `tests/_build/` only).  This exercises",
+                "everything *above* the ABI with the drivers' full parameter ranges; *below* the ABI the same rows through",
+                "libwavegpu are section 1 and `profiles/r2_golden_all.md` (all 537 rows, library calls).  The same flow is a",
+                "test: `tests/test_reference_scripts_cpu.py`.", ""]
+        if args.conv:
+            _conv_section("cpu", args.conv, args.conv_args, out)
+        if args.diss:
+            _diss_section(args.diss, args.diss_args, out)
+        if args.scal:
+            out += ["### scalability_sweep.py --nprocs 1", "",
+                    "The driver's fixed configuration (Nel = 640, R = 1, Dt = 8e-5, T = 0.05: 410 881 DoFs, 625 steps), whole-",
+                    "process wall time per scheme as the driver measures it.  Here that is the time of the **CPU oracle** behind",
+                    f"the test double ({args.scal_note}): it says nothing about the GPU and is listed to show that the driver's",
+                    "table is produced (return codes 0).  The reference's own figures (AMG-CG, Xeon Gold 6238R) are next to it;",
+                    "the same configuration through libwavegpu on a B200 is in `profiles/r1_published_config.md`.", "",
+                    "| scheme | returncode | seconds (oracle behind the double) | reference table: 1 rank | 16 ranks | 32 ranks |",
+                    "|---|---|---|---|---|---|"]
+            ref = json.loads((ROOT / "tests" / "golden" / "scalability_seconds.json").read_text())
+            for r in csv.DictReader(Path(args.scal).open()):
+                g = ref.get(r["scheme"], {})
+                out.append(f"| {r['scheme']} | {r['returncode']} | {float(r['seconds']):.1f} | {g.get('1', '–')} | "
+                           f"{g.get('16', '–')} | {g.get('32', '–')} |")
+            out.append("")
     Path(args.out).write_text("\n".join(out))
     print(f"wrote {args.out}")
 
@@ -241,6 +258,11 @@ def main():
     p.add_argument("--diss-args", default="--nprocs 4")
     p.add_argument("--scal", default=None)
     p.add_argument("--scal-note", default="OpenMP")
+    p.add_argument("--b200-conv", nargs="*", default=[])
+    p.add_argument("--b200-conv-args", default="")
+    p.add_argument("--b200-diss", default=None)
+    p.add_argument("--b200-diss-args", default="")
+    p.add_argument("--b200-note", default="")
     p.add_argument("--out", required=True)
     args = ap.parse_args()
     if args.cmd == "report":
