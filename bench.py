@@ -456,8 +456,9 @@ def main():
     peak, peak_src = hbm_peak()
     nnz = g.nnz_local
     kernels = []
-    names = ("k_spmv (CG A*d with fused d.Ad)", "k_cg_update (g += alpha Ad, h = D^-1 g, g.g, g.h)",
-             "k_cg_direction (x += alpha d, d = beta d - h)")
+    # kernel names as the ncu launch lists under profiles/ show them
+    names = (("k_spmv_st" if info["stencil_rows"] else "k_spmv") + " (CG A*d with fused d.Ad)",
+             "k_cg_update (g += alpha Ad, h = D^-1 g, g.g, g.h)", "k_cg_direction (x += alpha d, d = beta d - h)")
     alg = (float(info["spmv_bytes"]), 40.0 * g.nown, 40.0 * g.nown)
     for k in range(3):
         if kt_n[k] > 0:
@@ -502,7 +503,7 @@ def main():
         roofline["spmv_csr_equivalent"] = {
             "bytes": csr_bytes, "GB/s": csr_bytes / (sp["avg_launch_ms_in_step"] * 1e-3) / 1e9,
             "x_peak": csr_bytes / (sp["avg_launch_ms_in_step"] * 1e-3) / 1e9 / peak,
-            "note": "k_spmv's frac is against the 16 B/row the table-driven operator still has to move "
+            "note": "k_spmv_st's frac is against the 16 B/row the table-driven operator still has to move "
                     "(x in, y out); run with --no-stencil for the SELL kernel's own roofline"}
     if roofline is not None:
         roofline["spmv_l2_flushed_single_launch"] = {"ms": ms_fl, "GB/s": by_fl / ms_fl / 1e6,

@@ -137,12 +137,13 @@ def compare_convergence(files):
     return rows, unmatched, len(gold)
 
 
-def compare_dissdisp(f):
+def compare_dissdisp(files):
+    files = [files] if isinstance(files, (str, Path)) else list(files)
     gold = {}
     for g in json.loads((ROOT / "tests" / "golden" / "dissdisp_rows_all.json").read_text()):
         gold[(g["scheme"], g["Nel"], g["R"], float(g["Dt"]))] = g
     rows, unmatched = [], 0
-    for r in csv.DictReader(Path(f).open()):
+    for r in (row for f in files for row in csv.DictReader(Path(f).open())):
         key = (r["scheme"], int(r["Nel"]), int(r["R"]), float(r["dt"]))
         g = gold.get(key)
         if g is None:
@@ -254,13 +255,13 @@ def main():
     p = sub.add_parser("report")
     p.add_argument("--conv", nargs="*", default=[])
     p.add_argument("--conv-args", default="")
-    p.add_argument("--diss", default=None)
+    p.add_argument("--diss", nargs="*", default=[])
     p.add_argument("--diss-args", default="--nprocs 4")
     p.add_argument("--scal", default=None)
     p.add_argument("--scal-note", default="OpenMP")
     p.add_argument("--b200-conv", nargs="*", default=[])
     p.add_argument("--b200-conv-args", default="")
-    p.add_argument("--b200-diss", default=None)
+    p.add_argument("--b200-diss", nargs="*", default=[])
     p.add_argument("--b200-diss-args", default="")
     p.add_argument("--b200-note", default="")
     p.add_argument("--out", required=True)
