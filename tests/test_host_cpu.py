@@ -39,6 +39,26 @@ def test_no_device_fails_loudly():
     assert ei.value.code == -3 and "no CPU fallback" in str(ei.value)
 
 
+def test_product_never_links_or_loads_the_oracle_or_the_test_double():
+    """The oracle (oracle/) and the test double of the ABI (tests/abi_double/) are test infrastructure: the
+    product library and executables neither contain nor depend on them, no product source refers to their
+    files, and the executables fail with the library's "no CPU fallback" message where there is no GPU."""
+    pkg = ROOT / "nmpde-wave-equation_b200"
+    lib = pkg / "lib" / "libwavegpu.so"
+    syms = subprocess.run(["nm", "-D", "--defined-only", str(lib)], capture_output=True, text=True, check=True).stdout
+    assert "wave_create" in syms and "oracle_" not in syms
+    for exe in ("main-newmark", "main-theta", "wave-mpirun"):
+        needed = subprocess.run(["readelf", "-d", str(BIN / exe)], capture_output=True, text=True, check=True).stdout
+        assert "libwavegpu.so" in needed and "oracle" not in needed and "tests/_build" not in needed, exe
+    needed = subprocess.run(["readelf", "-d", str(lib)], capture_output=True, text=True, check=True).stdout
+    assert "oracle" not in needed
+    for src in list(pkg.rglob("*.py")) + list((pkg / "csrc").iterdir()) + list((pkg / "host").iterdir()):
+        if src.is_file():
+            text = src.read_text(errors="ignore")
+            for banned in ("wave_oracle", "libwaveoracle", "abi_double", "from oracle", "import oracle", "oracle/"):
+                assert banned not in text, f"{src.name} refers to {banned}"
+
+
 @pytest.mark.parametrize("nx,ny,r", [(1, 1, 1), (1, 1, 2), (2, 1, 2), (1, 3, 2), (3, 2, 1), (5, 4, 2), (7, 3, 1),
                                      (4, 6, 2), (16, 9, 2), (9, 16, 1)])
 def test_closed_form_numbering_is_first_touch(nx, ny, r):
